@@ -1,0 +1,138 @@
+// common.cuh — shared device/host definitions of the B200 DEFLATE engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nxgpu {
+
+constexpr int kNumSMs = 148;             // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+constexpr int kWindow = 32768;           // RFC 1951 maximum match distance
+constexpr int kMinMatch = 4;             // shortest match the LZ77 stage emits
+constexpr int kMaxMatch = 258;
+
+// LZ77 token, one u32: literal = byte value; match = 1<<31 | (len-3)<<15 | (dist-1)
+__host__ __device__ inline uint32_t tok_match(uint32_t len, uint32_t dist) { return 0x80000000u | ((len - 3) << 15) | (dist - 1); }
+__host__ __device__ inline bool tok_is_match(uint32_t t) { return (t >> 31) != 0; }
+__host__ __device__ inline uint32_t tok_len(uint32_t t) { return ((t >> 15) & 0xff) + 3; }
+__host__ __device__ inline uint32_t tok_dist(uint32_t t) { return (t & 0x7fff) + 1; }
+
+// length (3..258) -> code index 0..28 plus extra bits (RFC 1951 §3.2.5)
+__host__ __device__ inline void len_code(uint32_t len, uint32_t &code, uint32_t &nextra, uint32_t &extra)
+{
+	uint32_t l = len - 3;
+	if (l < 8) { code = l; nextra = 0; extra = 0; return; }
+	if (l == 255) { code = 28; nextra = 0; extra = 0; return; }
+#ifdef __CUDA_ARCH__
+	uint32_t nb = 31 - __clz(l);
+#else
+	uint32_t nb = 31 - __builtin_clz(l);
+#endif
+	code = 4 * (nb - 1) + ((l >> (nb - 2)) & 3);
+	nextra = nb - 2;
+	extra = l & ((1u << nextra) - 1);
+}
+// distance (1..32768) -> code index 0..29 plus extra bits
+__host__ __device__ inline void dist_code(uint32_t dist, uint32_t &code, uint32_t &nextra, uint32_t &extra)
+{
+	uint32_t d = dist - 1;
+	if (d < 4) { code = d; nextra = 0; extra = 0; return; }
+#ifdef __CUDA_ARCH__
+	uint32_t nb = 31 - __clz(d);
+#else
+	uint32_t nb = 31 - __builtin_clz(d);
+#endif
+	code = 2 * nb + ((d >> (nb - 1)) & 1);
+	nextra = nb - 1;
+	extra = d & ((1u << nextra) - 1);
+}
+
+// ---- device job descriptors (host fills, kernels read) ----
+struct DeflateJob {
+	const uint8_t *src;     // first NEW byte; src[-hist_len .. -1] is dictionary
+	uint32_t src_len;
+	uint32_t hist_len;
+	uint8_t *out;           // 16-byte aligned private output slot
+	uint32_t out_cap;
+	uint32_t flags;         // NXGPU_F_*
+	const uint8_t *dht;     // optional caller-supplied dynamic header (bits from HLIT), nxu_run_job path
+	uint32_t dht_bits;
+	uint32_t *lzcount;      // optional 316 counters out (COUNT function codes)
+	uint32_t pad_;
+};
+struct DeflateOut {
+	int32_t rc;
+	uint32_t out_len;
+	uint32_t tebc;
+	uint32_t n_tokens;
+	uint32_t btype;         // 0 stored, 1 fixed, 2 dynamic
+	uint32_t reserved[3];
+};
+
+struct InflateJob {
+	const uint8_t *src;
+	uint32_t src_len;
+	uint32_t wrap;
+	uint8_t *dst;           // dst[-hist_len..-1] window
+	uint32_t dst_cap;
+	uint32_t hist_len;
+};
+struct InflateOut {
+	int32_t rc;
+	uint32_t out_len;
+	uint32_t in_used;
+	uint32_t flags;
+	uint32_t trailer_crc;   // from the stream (gzip) / adler (zlib)
+	uint32_t trailer_isize;
+	uint32_t reserved[2];
+};
+
+struct CksumJob {
+	const uint8_t *src;
+	uint64_t len;
+};
+
+// deflate tuning per zlib-style level
+struct LevelParams { int depth; int lazy; int nice; };
+__host__ __device__ inline LevelParams level_params(int level)
+{
+	switch (level) {
+	case 1: return { 4, 0, 32 };
+	case 2: return { 6, 0, 64 };
+	case 3: return { 8, 0, 128 };
+	case 4: return { 12, 16, 128 };
+	case 5: return { 20, 32, 258 };
+	case 6: return { 32, 32, 258 };
+	case 7: return { 48, 64, 258 };
+	case 8: return { 96, 258, 258 };
+	case 9: return { 200, 258, 258 };
+	default: return { 32, 32, 258 };
+	}
+}
+
+#define NXGPU_CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { nxgpu::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); return NXGPU_E_NODEV; } } while (0)
+void set_error(const char *fmt, ...);
+
+// kernel launchers (defined in the .cu files)
+size_t deflate_smem_bytes();
+cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_jobs, int level,
+			   uint32_t *tok_scratch, uint32_t tok_stride, int grid, cudaStream_t s);
+cudaError_t launch_inflate(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s);
+// checksum.cu
+cudaError_t checksum_init_tables();
+size_t checksum_range_bytes();
+size_t checksum_partial_bytes();
+void checksum_fill_range(void *ranges, size_t idx, const void *src, uint64_t len, uint64_t after, uint32_t job);
+cudaError_t launch_checksum_ranges(const void *d_ranges, uint32_t n_ranges, void *d_parts, int which, cudaStream_t s);
+cudaError_t launch_checksum_combine(const void *d_ranges, const void *d_parts, const uint32_t *d_rs, uint32_t n_jobs,
+				    const uint32_t *d_crc_seed, const uint32_t *d_adler_seed,
+				    uint32_t *d_crc_out, uint32_t *d_adler_out, cudaStream_t s);
+cudaError_t launch_ranges_from_inflate(const InflateJob *jobs, const InflateOut *outs, uint32_t n, void *d_ranges, uint32_t *d_rs, cudaStream_t s);
+uint32_t host_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2);
+// stitch.cu
+cudaError_t launch_scan_offsets(const DeflateOut *outs, uint32_t n, uint64_t base, uint64_t *offsets, cudaStream_t s);
+cudaError_t launch_gather(const DeflateJob *jobs, const DeflateOut *outs, const uint64_t *offsets, uint32_t n,
+			  uint8_t *dst, uint64_t dst_cap, cudaStream_t s);
+cudaError_t launch_finish_stream(const DeflateOut *outs, const uint64_t *offsets, uint32_t n, uint8_t *dst, uint64_t dst_cap,
+				 int wrap, const uint32_t *d_crc, const uint32_t *d_adler, uint64_t src_len, uint64_t *d_total, cudaStream_t s);
+
+} // namespace nxgpu

@@ -1,0 +1,474 @@
+// inflate.cu — the NX decompress function (inc_nx/nxu.h:812) as a batched
+// sm_100a kernel: one warp per independent member / sync-point segment.
+//
+// Per warp: lane 0 walks the Huffman stream through shared-memory lookup tables (10-bit
+// lit/len, 9-bit distance, canonical fall-back for longer codes) and queues up to 32 symbols;
+// then all 32 lanes materialise the queue — a shuffle prefix sum gives every symbol its output
+// offset, literals are stored in parallel and each match is copied by the whole warp.  The
+// window is the output buffer itself (L1/L2-resident), so no history copies are needed
+// (the reference's host side copies 32 KiB per job, lib/nx_inflate.c:1633-1687).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+#include "../../include/nxgpu.h"
+
+namespace nxgpu {
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kLitBits = 10, kDistBits = 9;
+
+struct WarpTables {
+	uint32_t lit[1 << kLitBits];      // codelen | type<<4 | nextra<<6 | value<<10   (0 = slow path)
+	uint32_t dist[1 << kDistBits];    // codelen | nextra<<4 | base<<8
+	uint16_t lit_sorted[288];
+	uint16_t dist_sorted[32];
+	uint16_t lit_count[16], dist_count[16];
+	uint8_t lens[320];
+	uint32_t q[32];                   // decoded symbols: literal, or tok_match(len, dist)
+};
+
+__constant__ uint16_t k_len_base[29] = { 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258 };
+__constant__ uint8_t k_len_extra[29] = { 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0 };
+__constant__ uint16_t k_dist_base[30] = { 1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577 };
+__constant__ uint8_t k_dist_extra[30] = { 0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13 };
+__constant__ uint8_t k_clorder[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
+
+// LSB-first bit reader over global memory (lane 0 only)
+struct BitReader {
+	const uint8_t *src;
+	uint32_t len;       // valid bytes
+	uint32_t pos;       // bytes loaded so far (may run past len: zero fill)
+	uint64_t buf;
+	uint32_t cnt;
+
+	__device__ __forceinline__ void init(const uint8_t *s, uint32_t n, uint32_t start)
+	{
+		src = s; len = n; pos = start; buf = 0; cnt = 0;
+		// byte loads until the address is 4-byte aligned
+		while (((reinterpret_cast<uintptr_t>(src) + pos) & 3) && cnt <= 56) {
+			uint64_t b = pos < len ? src[pos] : 0;
+			buf |= b << cnt; cnt += 8; pos++;
+		}
+	}
+	__device__ __forceinline__ void refill()
+	{
+		while (cnt <= 32) {
+			uint32_t w;
+			if (pos + 4 <= len) {
+				w = *reinterpret_cast<const uint32_t *>(src + pos);
+			} else {
+				w = 0;
+				for (int k = 0; k < 4; k++)
+					if (pos + k < len)
+						w |= (uint32_t)src[pos + k] << (8 * k);
+			}
+			buf |= (uint64_t)w << cnt;
+			cnt += 32; pos += 4;
+		}
+	}
+	__device__ __forceinline__ uint32_t peek(uint32_t n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
+	__device__ __forceinline__ void drop(uint32_t n) { buf >>= n; cnt -= n; }
+	__device__ __forceinline__ uint32_t get(uint32_t n) { uint32_t v = peek(n); drop(n); return v; }
+	__device__ __forceinline__ uint64_t bits_used() const { return (uint64_t)pos * 8 - cnt; }
+	__device__ __forceinline__ bool overrun() const { return bits_used() > (uint64_t)len * 8; }
+};
+
+// canonical decode, one bit at a time (codes longer than the primary table)
+__device__ int slow_decode(BitReader &br, const uint16_t *count, const uint16_t *sorted)
+{
+	int code = 0, first = 0, index = 0;
+	for (int l = 1; l <= 15; l++) {
+		code |= (int)br.get(1);
+		int c = count[l];
+		if (code - c < first)
+			return sorted[index + (code - first)];
+		index += c; first += c; first <<= 1; code <<= 1;
+	}
+	return -1;
+}
+
+// warp-cooperative: lens[n] -> primary LUT + canonical arrays.  Returns false if over-subscribed.
+__device__ bool build_table(const uint8_t *lens, int n, uint32_t *lut, int lut_bits, uint16_t *count,
+			    uint16_t *sorted, bool is_dist)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t lt = (1u << lane) - 1;
+	// per-length counts and per-symbol rank inside its length class
+	uint32_t my_cnt = 0;                 // lane l (1..15) holds count[l]
+	uint32_t ranks[9];
+#pragma unroll
+	for (int g = 0; g < 9; g++) {
+		if (g * 32 >= n)
+			break;
+		const int s = g * 32 + lane;
+		const int l = s < n ? lens[s] : 0;
+		uint32_t r = 0;
+		for (int L = 1; L <= 15; L++) {
+			const uint32_t m = __ballot_sync(0xffffffffu, l == L);
+			const uint32_t base = __shfl_sync(0xffffffffu, my_cnt, L);
+			if (l == L)
+				r = base + __popc(m & lt);
+			if ((int)lane == L)
+				my_cnt += __popc(m);
+		}
+		ranks[g] = r;
+	}
+	// Kraft check + first code / offset per length (every lane computes the same small scan)
+	uint32_t next_code = 0, offs = 0, my_next = 0, my_offs = 0;
+	int left = 1;
+	bool over = false;
+	for (int L = 1; L <= 15; L++) {
+		const uint32_t c = __shfl_sync(0xffffffffu, my_cnt, L);
+		left = (left << 1) - (int)c;
+		if (left < 0)
+			over = true;
+		if ((int)lane == L) { my_next = next_code; my_offs = offs; }
+		next_code = (next_code + c) << 1;
+		offs += c;
+	}
+	if (lane < 16)
+		count[lane] = (lane == 0) ? 0 : (uint16_t)my_cnt;
+	if (over)
+		return false;
+	for (int i = lane; i < (1 << lut_bits); i += 32)
+		lut[i] = 0;
+	__syncwarp();
+#pragma unroll
+	for (int g = 0; g < 9; g++) {
+		if (g * 32 >= n)
+			break;
+		const int s = g * 32 + lane;
+		const int l = s < n ? lens[s] : 0;
+		const uint32_t nc = __shfl_sync(0xffffffffu, my_next, l & 31);
+		const uint32_t of = __shfl_sync(0xffffffffu, my_offs, l & 31);
+		if (l) {
+			const uint32_t r = ranks[g];
+			sorted[of + r] = (uint16_t)s;
+			if (l <= lut_bits) {
+				const uint32_t code = __brev(nc + r) >> (32 - l);
+				uint32_t e;
+				if (is_dist) {
+					e = s < 30 ? ((uint32_t)l | ((uint32_t)k_dist_extra[s] << 4) | ((uint32_t)k_dist_base[s] << 8)) : 0;
+				} else if (s < 256) {
+					e = (uint32_t)l | (0u << 4) | ((uint32_t)s << 10);
+				} else if (s == 256) {
+					e = (uint32_t)l | (2u << 4);
+				} else if (s < 286) {
+					e = (uint32_t)l | (1u << 4) | ((uint32_t)k_len_extra[s - 257] << 6) | ((uint32_t)k_len_base[s - 257] << 10);
+				} else {
+					e = 0;
+				}
+				if (e)
+					for (uint32_t k = code; k < (1u << lut_bits); k += (1u << l))
+						lut[k] = e;
+			}
+		}
+	}
+	__syncwarp();
+	return true;
+}
+
+__device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t lt = (1u << lane) - 1;
+	BitReader br;
+	int rc = 0;                      // uniform after each broadcast
+	uint32_t out = 0;
+	uint32_t start = 0, wrap = J.wrap;
+	uint32_t tr_crc = 0, tr_isize = 0, flags = 0;
+
+	// ---- container header (lane 0), lib/nx_inflate.c:329-730 does this on the host ----
+	if (lane == 0) {
+		const uint8_t *s = J.src;
+		const uint32_t n = J.src_len;
+		if (wrap == NXGPU_WRAP_AUTO) {
+			if (n >= 2 && s[0] == 0x1f && s[1] == 0x8b) wrap = NXGPU_WRAP_GZIP;
+			else if (n >= 2 && (s[0] & 0x0f) == 8 && (((uint32_t)s[0] << 8 | s[1]) % 31) == 0) wrap = NXGPU_WRAP_ZLIB;
+			else wrap = NXGPU_WRAP_RAW;
+		}
+		if (wrap == NXGPU_WRAP_GZIP) {
+			if (n < 18 || s[0] != 0x1f || s[1] != 0x8b || s[2] != 8) rc = NXGPU_E_DATA;
+			else {
+				const uint32_t flg = s[3];
+				uint32_t p = 10;
+				if (flg & 4) { if (p + 2 <= n) p += 2 + (s[p] | (uint32_t)s[p + 1] << 8); else p = n + 1; }
+				if (flg & 8) { while (p < n && s[p]) p++; p++; }
+				if (flg & 16) { while (p < n && s[p]) p++; p++; }
+				if (flg & 2) p += 2;
+				if (p > n) rc = NXGPU_E_DATA;
+				start = p;
+			}
+		} else if (wrap == NXGPU_WRAP_ZLIB) {
+			if (n < 6 || (s[0] & 0x0f) != 8 || (((uint32_t)s[0] << 8 | s[1]) % 31) || (s[1] & 0x20)) rc = NXGPU_E_DATA;
+			start = 2;
+		}
+		if (!rc)
+			br.init(J.src, J.src_len, start);
+	}
+	rc = __shfl_sync(0xffffffffu, rc, 0);
+
+	bool final_block = false;
+	while (!rc && !final_block) {
+		// ---- block header (lane 0) ----
+		uint32_t btype = 0, stored_len = 0, stored_at = 0;
+		int hlit = 0, hdist = 0;
+		if (lane == 0) {
+			br.refill();
+			const uint32_t h = br.get(3);
+			final_block = h & 1;
+			btype = h >> 1;
+			if (btype == 0) {
+				br.drop(br.cnt & 7);
+				br.refill();
+				const uint32_t v = br.get(32);
+				if (((v ^ (v >> 16)) & 0xffff) != 0xffff) rc = NXGPU_E_DATA;
+				stored_len = v & 0xffff;
+				// give the buffered bytes back: stored data is copied straight from memory
+				stored_at = br.pos - (br.cnt >> 3);
+			} else if (btype == 2) {
+				const uint32_t v = br.get(14);
+				hlit = (int)(v & 31) + 257; hdist = (int)((v >> 5) & 31) + 1;
+				const int hclen = (int)(v >> 10) + 4;
+				if (hlit > 286 || hdist > 30) rc = NXGPU_E_DATA;
+				// code-length code: 19 symbols, <= 7 bits, decoded canonically
+				uint8_t cl[19];
+				for (int i = 0; i < 19; i++) cl[i] = 0;
+				for (int i = 0; i < hclen; i++) { br.refill(); cl[k_clorder[i]] = (uint8_t)br.get(3); }
+				uint16_t ccount[16], csorted[19], coffs[16];
+				for (int i = 0; i < 16; i++) ccount[i] = 0;
+				for (int i = 0; i < 19; i++) ccount[cl[i]]++;
+				ccount[0] = 0;
+				int left = 1;
+				for (int l = 1; l <= 7; l++) { left = (left << 1) - ccount[l]; if (left < 0) rc = NXGPU_E_DATA; }
+				coffs[1] = 0;
+				for (int l = 1; l < 15; l++) coffs[l + 1] = coffs[l] + ccount[l];
+				for (int i = 0; i < 19; i++) if (cl[i]) csorted[coffs[cl[i]]++] = (uint16_t)i;
+				int n = 0;
+				while (!rc && n < hlit + hdist) {
+					br.refill();
+					const int sym = slow_decode(br, ccount, csorted);
+					if (sym < 0) { rc = NXGPU_E_DATA; break; }
+					if (sym < 16) { T.lens[n++] = (uint8_t)sym; continue; }
+					int rep, val = 0;
+					if (sym == 16) { if (n == 0) { rc = NXGPU_E_DATA; break; } val = T.lens[n - 1]; rep = 3 + (int)br.get(2); }
+					else if (sym == 17) rep = 3 + (int)br.get(3);
+					else rep = 11 + (int)br.get(7);
+					if (n + rep > hlit + hdist) { rc = NXGPU_E_DATA; break; }
+					while (rep--) T.lens[n++] = (uint8_t)val;
+				}
+				if (!rc && T.lens[256] == 0) rc = NXGPU_E_DATA;
+				if (br.overrun()) rc = NXGPU_E_DATA;
+			} else if (btype == 3) {
+				rc = NXGPU_E_DATA;
+			}
+		}
+		rc = __shfl_sync(0xffffffffu, rc, 0);
+		btype = __shfl_sync(0xffffffffu, btype, 0);
+		final_block = __shfl_sync(0xffffffffu, (int)final_block, 0) != 0;
+		if (rc)
+			break;
+
+		if (btype == 0) {
+			stored_len = __shfl_sync(0xffffffffu, stored_len, 0);
+			stored_at = __shfl_sync(0xffffffffu, stored_at, 0);
+			if (stored_at + stored_len > J.src_len) { rc = NXGPU_E_DATA; break; }
+			if (out + stored_len > J.dst_cap) { rc = NXGPU_E_BUF; break; }
+			for (uint32_t i = lane; i < stored_len; i += 32)
+				J.dst[out + i] = J.src[stored_at + i];
+			out += stored_len;
+			if (lane == 0)
+				br.init(J.src, J.src_len, stored_at + stored_len);
+			__syncwarp();
+			continue;
+		}
+
+		// ---- decode tables ----
+		if (btype == 1) {
+			for (int i = lane; i < 288; i += 32)
+				T.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+			T.lens[288 + lane] = 5;
+			hlit = 288; hdist = 30;
+		} else {
+			hlit = __shfl_sync(0xffffffffu, hlit, 0);
+			hdist = __shfl_sync(0xffffffffu, hdist, 0);
+		}
+		__syncwarp();
+		bool ok = build_table(T.lens, hlit, T.lit, kLitBits, T.lit_count, T.lit_sorted, false);
+		ok = build_table(T.lens + hlit, hdist, T.dist, kDistBits, T.dist_count, T.dist_sorted, true) && ok;
+		if (!ok) { rc = NXGPU_E_DATA; break; }
+
+		// ---- symbols ----
+		bool block_done = false;
+		while (!block_done && !rc) {
+			uint32_t qn = 0;
+			if (lane == 0) {
+				while (qn < 32) {
+					br.refill();
+					uint32_t e = T.lit[br.peek(kLitBits)];
+					uint32_t type, value, nextra;
+					if (e & 15) {
+						br.drop(e & 15);
+						type = (e >> 4) & 3; nextra = (e >> 6) & 15; value = e >> 10;
+					} else {
+						const int sym = slow_decode(br, T.lit_count, T.lit_sorted);
+						if (sym < 0 || sym >= 286) { rc = NXGPU_E_DATA; break; }
+						if (sym < 256) { type = 0; value = sym; nextra = 0; }
+						else if (sym == 256) { type = 2; value = 0; nextra = 0; }
+						else { type = 1; value = k_len_base[sym - 257]; nextra = k_len_extra[sym - 257]; }
+					}
+					if (type == 0) { T.q[qn++] = value; continue; }
+					if (type == 2) { block_done = true; break; }
+					const uint32_t len = value + br.get(nextra);
+					br.refill();
+					uint32_t d = T.dist[br.peek(kDistBits)];
+					uint32_t dbase, dextra;
+					if (d & 15) {
+						br.drop(d & 15);
+						dextra = (d >> 4) & 15; dbase = d >> 8;
+					} else {
+						const int ds = slow_decode(br, T.dist_count, T.dist_sorted);
+						if (ds < 0 || ds >= 30) { rc = NXGPU_E_DATA; break; }
+						dbase = k_dist_base[ds]; dextra = k_dist_extra[ds];
+					}
+					const uint32_t dist = dbase + br.get(dextra);
+					T.q[qn++] = tok_match(len, dist);
+				}
+				if (br.overrun())
+					rc = NXGPU_E_DATA;
+			}
+			__syncwarp();
+			qn = __shfl_sync(0xffffffffu, qn, 0);
+			rc = __shfl_sync(0xffffffffu, rc, 0);
+			block_done = __shfl_sync(0xffffffffu, (int)block_done, 0) != 0;
+			if (rc)
+				break;
+			// ---- materialise the queue ----
+			const uint32_t t = lane < qn ? T.q[lane] : 0;
+			const bool is_m = lane < qn && tok_is_match(t);
+			const uint32_t mylen = lane < qn ? (is_m ? tok_len(t) : 1) : 0;
+			uint32_t incl = mylen;
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+				if (lane >= (uint32_t)o)
+					incl += y;
+			}
+			const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+			const uint32_t my_out = out + incl - mylen;
+			if (out + total > J.dst_cap) { rc = NXGPU_E_BUF; break; }
+			const bool bad = is_m && tok_dist(t) > my_out + J.hist_len;
+			if (__any_sync(0xffffffffu, bad)) { rc = NXGPU_E_DATA; break; }
+			if (lane < qn && !is_m)
+				J.dst[my_out] = (uint8_t)t;
+			uint32_t mm = __ballot_sync(0xffffffffu, is_m);
+			__syncwarp();
+			while (mm) {
+				const int src_lane = __ffs(mm) - 1;
+				mm &= mm - 1;
+				const uint32_t mt = __shfl_sync(0xffffffffu, t, src_lane);
+				const uint32_t mo = __shfl_sync(0xffffffffu, my_out, src_lane);
+				const uint32_t len = tok_len(mt), dist = tok_dist(mt);
+				uint8_t *d = J.dst + mo;
+				if (dist >= len || dist >= 32) {
+					// each 32-byte pass reads bytes that earlier passes (or earlier symbols) wrote
+					for (uint32_t k = 0; k < len; k += 32) {
+						if (k + lane < len)
+							d[k + lane] = *(volatile const uint8_t *)(d + k + lane - dist);
+						if (dist < len)
+							__syncwarp();
+					}
+				} else {
+					// short period: the pattern d[-dist..-1] repeats
+					for (uint32_t k = lane; k < len; k += 32)
+						d[k] = *(volatile const uint8_t *)(d - dist + (k % dist));
+				}
+				__syncwarp();
+			}
+			(void)lt;
+			out += total;
+		}
+	}
+
+	// ---- trailer (lane 0) ----
+	uint32_t in_used = 0;
+	if (lane == 0) {
+		if (!rc) {
+			flags |= 1;
+			uint32_t p = (uint32_t)((br.bits_used() + 7) >> 3);
+			const uint8_t *s = J.src;
+			if (wrap == NXGPU_WRAP_GZIP) {
+				if (p + 8 > J.src_len) rc = NXGPU_E_DATA;
+				else {
+					tr_crc = s[p] | (uint32_t)s[p + 1] << 8 | (uint32_t)s[p + 2] << 16 | (uint32_t)s[p + 3] << 24;
+					tr_isize = s[p + 4] | (uint32_t)s[p + 5] << 8 | (uint32_t)s[p + 6] << 16 | (uint32_t)s[p + 7] << 24;
+					p += 8;
+				}
+			} else if (wrap == NXGPU_WRAP_ZLIB) {
+				if (p + 4 > J.src_len) rc = NXGPU_E_DATA;
+				else {
+					tr_crc = (uint32_t)s[p] << 24 | (uint32_t)s[p + 1] << 16 | (uint32_t)s[p + 2] << 8 | s[p + 3];
+					p += 4;
+				}
+			}
+			if (p > J.src_len) rc = NXGPU_E_DATA;
+			in_used = p;
+		}
+		O.rc = rc;
+		O.out_len = out;
+		O.in_used = in_used;
+		O.flags = flags | (wrap << 8);
+		O.trailer_crc = tr_crc;
+		O.trailer_isize = tr_isize;
+	}
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+inflate_kernel(const InflateJob *__restrict__ jobs, InflateOut *__restrict__ outs, uint32_t n_jobs, uint32_t *next_job)
+{
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	WarpTables &T = reinterpret_cast<WarpTables *>(smem_raw)[threadIdx.x >> 5];
+	const uint32_t lane = threadIdx.x & 31;
+	for (;;) {
+		// dynamic work distribution: members differ a lot in cost
+		uint32_t j = 0;
+		if (lane == 0)
+			j = atomicAdd(next_job, 1u);
+		j = __shfl_sync(0xffffffffu, j, 0);
+		if (j >= n_jobs)
+			break;
+		const InflateJob J = jobs[j];
+		inflate_one(J, outs[j], T);
+		__syncwarp();
+	}
+}
+
+} // namespace
+
+cudaError_t launch_inflate(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s)
+{
+	static bool configured = false;
+	const size_t smem = sizeof(WarpTables) * kWarpsPerCta;
+	if (!configured) {
+		cudaError_t e = cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess)
+			return e;
+		configured = true;
+	}
+	cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
+	if (e != cudaSuccess)
+		return e;
+	// persistent grid: CTAs-per-SM limited by shared memory (about 3 with 8 warps each)
+	int per_sm = 1;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_kernel, kWarpsPerCta * 32, smem);
+	if (per_sm < 1)
+		per_sm = 1;
+	uint32_t want = (n_jobs + kWarpsPerCta - 1) / kWarpsPerCta;
+	uint32_t grid = (uint32_t)(kNumSMs * per_sm);
+	if (want < grid)
+		grid = want ? want : 1;
+	inflate_kernel<<<grid, kWarpsPerCta * 32, smem, s>>>(jobs, outs, n_jobs, counter);
+	return cudaGetLastError();
+}
+
+} // namespace nxgpu

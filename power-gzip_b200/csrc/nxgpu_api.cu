@@ -1,0 +1,783 @@
+// nxgpu_api.cu — host side of the batch extension declared in include/nxgpu.h: context,
+// scratch management, job marshalling, launches.  No compute happens on the host: if the
+// device or a launch fails every entry point returns a negative code and nxgpu_last_error()
+// says why.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "../../include/nxgpu.h"
+
+namespace nxgpu {
+
+static thread_local char t_err[512];
+void set_error(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(t_err, sizeof(t_err), fmt, ap);
+	va_end(ap);
+}
+
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	int reserve(size_t bytes)
+	{
+		if (bytes <= cap)
+			return 0;
+		if (p)
+			cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 8 + 4096;
+		if (cudaMalloc(&p, want) != cudaSuccess) {
+			cudaGetLastError();
+			want = bytes;
+			if (cudaMalloc(&p, want) != cudaSuccess) {
+				set_error("cudaMalloc(%zu) failed", want);
+				p = nullptr;
+				return NXGPU_E_MEM;
+			}
+		}
+		cap = want;
+		return 0;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	int reserve(size_t bytes)
+	{
+		if (bytes <= cap)
+			return 0;
+		if (p)
+			cudaFreeHost(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 8 + 4096;
+		if (cudaMallocHost(&p, want) != cudaSuccess) {
+			set_error("cudaMallocHost(%zu) failed", want);
+			cudaGetLastError();
+			return NXGPU_E_MEM;
+		}
+		cap = want;
+		return 0;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct KernelTimer {
+	std::vector<cudaEvent_t> ev;      // start/stop pairs
+	size_t used = 0;
+	double ms_total = 0;
+	uint64_t launches = 0;
+};
+
+} // namespace nxgpu
+
+using namespace nxgpu;
+
+struct nxgpu_ctx {
+	int dev = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t t0 = nullptr, t1 = nullptr;
+	uint64_t launches = 0;
+	DevBuf d_jobs, d_outs, d_tok, d_slots, d_ranges, d_parts, d_rs, d_seeds, d_cks, d_in, d_out, d_offsets, d_misc, d_dst_ptrs;
+	PinBuf h_jobs, h_outs, h_misc, h_stage;
+	KernelTimer timers[3];           // 0 deflate, 1 inflate, 2 checksum
+	bool timing = true;
+};
+
+namespace {
+
+int fam_index(const char *f)
+{
+	if (!strcmp(f, "deflate")) return 0;
+	if (!strcmp(f, "inflate")) return 1;
+	if (!strcmp(f, "checksum")) return 2;
+	return -1;
+}
+
+void timer_begin(nxgpu_ctx *c, int fam)
+{
+	KernelTimer &t = c->timers[fam];
+	if (!c->timing)
+		return;
+	if (t.used + 2 > t.ev.size()) {
+		cudaEvent_t a, b;
+		cudaEventCreate(&a); cudaEventCreate(&b);
+		t.ev.push_back(a); t.ev.push_back(b);
+	}
+	cudaEventRecord(t.ev[t.used], c->stream);
+}
+void timer_end(nxgpu_ctx *c, int fam)
+{
+	KernelTimer &t = c->timers[fam];
+	c->launches++;
+	if (!c->timing)
+		return;
+	cudaEventRecord(t.ev[t.used + 1], c->stream);
+	t.used += 2;
+	t.launches++;
+}
+void timer_collect(nxgpu_ctx *c)
+{
+	for (int f = 0; f < 3; f++) {
+		KernelTimer &t = c->timers[f];
+		for (size_t i = 0; i + 1 < t.used; i += 2) {
+			float ms = 0;
+			if (cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]) == cudaSuccess)
+				t.ms_total += ms;
+		}
+		t.used = 0;
+	}
+}
+
+__global__ void scatter_outputs_kernel(const DeflateJob *__restrict__ jobs, const DeflateOut *__restrict__ outs,
+				       uint8_t *const *__restrict__ dsts, const uint32_t *__restrict__ caps, uint32_t n)
+{
+	for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+		if (outs[i].rc != 0 || outs[i].out_len > caps[i])
+			continue;
+		const uint32_t len = outs[i].out_len;
+		const uint8_t *s = jobs[i].out;
+		uint8_t *d = dsts[i];
+		for (uint32_t k = threadIdx.x; k < len; k += blockDim.x)
+			d[k] = s[k];
+	}
+}
+
+__global__ void write_bytes_kernel(uint8_t *dst, uint64_t v, int n)
+{
+	for (int k = 0; k < n; k++)
+		dst[k] = (uint8_t)(v >> (8 * k));
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+} // namespace
+
+extern "C" {
+
+const char *nxgpu_last_error(void) { return t_err; }
+
+int nxgpu_open(int dev, nxgpu_ctx **out)
+{
+	t_err[0] = 0;
+	if (!out)
+		return NXGPU_E_ARG;
+	*out = nullptr;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+		return NXGPU_E_NODEV;
+	}
+	if (dev < 0) {
+		const char *lr = getenv("LOCAL_RANK");
+		dev = lr ? atoi(lr) % ndev : 0;
+	}
+	if (dev >= ndev) {
+		set_error("device %d out of range (%d present)", dev, ndev);
+		return NXGPU_E_NODEV;
+	}
+	NXGPU_CUDA_OK(cudaSetDevice(dev));
+	cudaDeviceProp prop;
+	NXGPU_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+	if (prop.major < 10) {
+		set_error("device %d is sm_%d%d; this engine is built for sm_100a only", dev, prop.major, prop.minor);
+		return NXGPU_E_NODEV;
+	}
+	nxgpu_ctx *c = new nxgpu_ctx();
+	c->dev = dev;
+	NXGPU_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	NXGPU_CUDA_OK(cudaEventCreate(&c->t0));
+	NXGPU_CUDA_OK(cudaEventCreate(&c->t1));
+	NXGPU_CUDA_OK(checksum_init_tables());
+	*out = c;
+	return 0;
+}
+
+void nxgpu_close(nxgpu_ctx *c)
+{
+	if (!c)
+		return;
+	cudaSetDevice(c->dev);
+	cudaStreamSynchronize(c->stream);
+	DevBuf *db[] = { &c->d_jobs, &c->d_outs, &c->d_tok, &c->d_slots, &c->d_ranges, &c->d_parts, &c->d_rs, &c->d_seeds,
+			 &c->d_cks, &c->d_in, &c->d_out, &c->d_offsets, &c->d_misc, &c->d_dst_ptrs };
+	for (DevBuf *b : db) b->release();
+	PinBuf *pb[] = { &c->h_jobs, &c->h_outs, &c->h_misc, &c->h_stage };
+	for (PinBuf *b : pb) b->release();
+	for (int f = 0; f < 3; f++)
+		for (cudaEvent_t e : c->timers[f].ev) cudaEventDestroy(e);
+	cudaEventDestroy(c->t0); cudaEventDestroy(c->t1);
+	cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int nxgpu_dev_alloc(nxgpu_ctx *c, size_t bytes, void **dptr)
+{
+	if (!c || !dptr) return NXGPU_E_ARG;
+	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
+	NXGPU_CUDA_OK(cudaMalloc(dptr, bytes ? bytes : 1));
+	return 0;
+}
+int nxgpu_dev_free(nxgpu_ctx *c, void *dptr)
+{
+	if (!c) return NXGPU_E_ARG;
+	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
+	NXGPU_CUDA_OK(cudaFree(dptr));
+	return 0;
+}
+int nxgpu_memcpy_h2d(nxgpu_ctx *c, void *dptr, const void *hptr, size_t bytes)
+{
+	if (!c) return NXGPU_E_ARG;
+	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
+	NXGPU_CUDA_OK(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, c->stream));
+	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+int nxgpu_memcpy_d2h(nxgpu_ctx *c, void *hptr, const void *dptr, size_t bytes)
+{
+	if (!c) return NXGPU_E_ARG;
+	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
+	NXGPU_CUDA_OK(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+int nxgpu_host_alloc(size_t bytes, void **hptr)
+{
+	if (!hptr) return NXGPU_E_ARG;
+	NXGPU_CUDA_OK(cudaMallocHost(hptr, bytes ? bytes : 1));
+	return 0;
+}
+int nxgpu_host_free(void *hptr)
+{
+	NXGPU_CUDA_OK(cudaFreeHost(hptr));
+	return 0;
+}
+int nxgpu_sync(nxgpu_ctx *c)
+{
+	if (!c) return NXGPU_E_ARG;
+	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+int nxgpu_timer_start(nxgpu_ctx *c)
+{
+	if (!c) return NXGPU_E_ARG;
+	NXGPU_CUDA_OK(cudaEventRecord(c->t0, c->stream));
+	return 0;
+}
+int nxgpu_timer_stop(nxgpu_ctx *c, float *ms)
+{
+	if (!c || !ms) return NXGPU_E_ARG;
+	NXGPU_CUDA_OK(cudaEventRecord(c->t1, c->stream));
+	NXGPU_CUDA_OK(cudaEventSynchronize(c->t1));
+	NXGPU_CUDA_OK(cudaEventElapsedTime(ms, c->t0, c->t1));
+	return 0;
+}
+uint64_t nxgpu_launch_count(nxgpu_ctx *c) { return c ? c->launches : 0; }
+int nxgpu_kernel_time(nxgpu_ctx *c, const char *family, double *ms_total, uint64_t *launches)
+{
+	const int f = family ? fam_index(family) : -1;
+	if (!c || f < 0) return NXGPU_E_ARG;
+	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	timer_collect(c);
+	if (ms_total) *ms_total = c->timers[f].ms_total;
+	if (launches) *launches = c->timers[f].launches;
+	return 0;
+}
+void nxgpu_kernel_time_reset(nxgpu_ctx *c)
+{
+	if (!c) return;
+	cudaStreamSynchronize(c->stream);
+	timer_collect(c);
+	for (int f = 0; f < 3; f++) { c->timers[f].ms_total = 0; c->timers[f].launches = 0; }
+}
+
+uint32_t nxgpu_deflate_bound(uint32_t src_len)
+{
+	// stored blocks are the worst case: 5 bytes per 65535 plus the joiner
+	return src_len + 5 * (src_len / 65535 + 1) + 16;
+}
+uint64_t nxgpu_deflate_stream_bound(uint64_t src_len, uint32_t chunk)
+{
+	if (chunk == 0) chunk = 262144;
+	const uint64_t n = (src_len + chunk - 1) / chunk + 1;
+	return src_len + n * (5 * (uint64_t)(chunk / 65535 + 1) + 16) + 32;
+}
+
+uint32_t nxgpu_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2) { return host_crc32_combine(crc1, crc2, len2); }
+uint32_t nxgpu_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2)
+{
+	const uint64_t B = 65521, rem = len2 % B;
+	uint64_t s1 = a1 & 0xffff, s2 = (rem * s1) % B;
+	s1 += (a2 & 0xffff) + B - 1;
+	s2 += ((a1 >> 16) & 0xffff) + ((a2 >> 16) & 0xffff) + B - rem;
+	return (uint32_t)((s1 % B) | ((s2 % B) << 16));
+}
+
+/* ------------------------------ checksums ------------------------------ */
+
+// Device-resident inputs: items[i].src are device pointers.  Cuts big items into ranges so that
+// the whole GPU works on one buffer; results land in d_cks (crc[n], adler[n]).
+static int checksum_device(nxgpu_ctx *c, const nxgpu_cksum_item *items, size_t n, int which)
+{
+	uint64_t total = 0;
+	for (size_t i = 0; i < n; i++) total += items[i].len;
+	// range size: at least 256 KiB, and about 8 ranges per SM for one large buffer
+	uint64_t rsz = total / (uint64_t)(kNumSMs * 8);
+	rsz = (rsz + 32767) / 32768 * 32768;
+	if (rsz < 262144) rsz = 262144;
+	size_t nr = 0;
+	for (size_t i = 0; i < n; i++) nr += items[i].len ? (items[i].len + rsz - 1) / rsz : 1;
+	const size_t rb = checksum_range_bytes(), pb = checksum_partial_bytes();
+	int rc;
+	const size_t hbytes = nr * rb + (n + 1) * 4 + n * 8;
+	if ((rc = c->h_misc.reserve(hbytes))) return rc;
+	if ((rc = c->d_ranges.reserve(hbytes))) return rc;
+	if ((rc = c->d_parts.reserve(nr * pb))) return rc;
+	if ((rc = c->d_cks.reserve(n * 8 + 16))) return rc;
+	uint8_t *h = static_cast<uint8_t *>(c->h_misc.p);
+	uint32_t *rs = reinterpret_cast<uint32_t *>(h + nr * rb);
+	uint32_t *seeds = rs + (n + 1);
+	size_t r = 0;
+	for (size_t i = 0; i < n; i++) {
+		rs[i] = (uint32_t)r;
+		const uint64_t len = items[i].len;
+		if (len == 0) { checksum_fill_range(h, r++, items[i].src, 0, 0, (uint32_t)i); }
+		for (uint64_t o = 0; o < len; o += rsz) {
+			const uint64_t l = len - o < rsz ? len - o : rsz;
+			checksum_fill_range(h, r++, static_cast<const uint8_t *>(items[i].src) + o, l, len - o - l, (uint32_t)i);
+		}
+		seeds[i] = items[i].crc_seed;
+		seeds[n + i] = items[i].adler_seed;
+	}
+	rs[n] = (uint32_t)r;
+	NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_ranges.p, h, hbytes, cudaMemcpyHostToDevice, c->stream));
+	uint8_t *d = static_cast<uint8_t *>(c->d_ranges.p);
+	const uint32_t *d_rs = reinterpret_cast<const uint32_t *>(d + nr * rb);
+	const uint32_t *d_seeds = d_rs + (n + 1);
+	uint32_t *d_crc = static_cast<uint32_t *>(c->d_cks.p), *d_adler = d_crc + n;
+	timer_begin(c, 2);
+	NXGPU_CUDA_OK(launch_checksum_ranges(d, (uint32_t)nr, c->d_parts.p, which, c->stream));
+	timer_end(c, 2);
+	NXGPU_CUDA_OK(launch_checksum_combine(d, c->d_parts.p, d_rs, (uint32_t)n, d_seeds, d_seeds + n,
+					      (which & 1) ? d_crc : nullptr, (which & 2) ? d_adler : nullptr, c->stream));
+	c->launches++;
+	return 0;
+}
+
+int nxgpu_checksum_batch(nxgpu_ctx *c, const nxgpu_cksum_item *items, size_t n, nxgpu_cksum_result *results, int mem)
+{
+	if (!c || (!items && n) || (!results && n)) return NXGPU_E_ARG;
+	if (n == 0) return 0;
+	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
+	int rc;
+	std::vector<nxgpu_cksum_item> dev_items;
+	const nxgpu_cksum_item *use = items;
+	if (mem == NXGPU_MEM_HOST) {
+		uint64_t total = 0;
+		for (size_t i = 0; i < n; i++) total += align_up(items[i].len, 16);
+		if ((rc = c->d_in.reserve(total + 16))) return rc;
+		dev_items.assign(items, items + n);
+		uint64_t o = 0;
+		for (size_t i = 0; i < n; i++) {
+			uint8_t *dp = static_cast<uint8_t *>(c->d_in.p) + o;
+			if (items[i].len && !items[i].src) return NXGPU_E_ARG;
+			if (items[i].len)
+				NXGPU_CUDA_OK(cudaMemcpyAsync(dp, items[i].src, items[i].len, cudaMemcpyHostToDevice, c->stream));
+			dev_items[i].src = dp;
+			o += align_up(items[i].len, 16);
+		}
+		use = dev_items.data();
+	}
+	if ((rc = checksum_device(c, use, n, 3))) return rc;
+	if ((rc = c->h_outs.reserve(n * 8))) return rc;
+	NXGPU_CUDA_OK(cudaMemcpyAsync(c->h_outs.p, c->d_cks.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	const uint32_t *h = static_cast<const uint32_t *>(c->h_outs.p);
+	for (size_t i = 0; i < n; i++) { results[i].crc32 = h[i]; results[i].adler32 = h[n + i]; }
+	return 0;
+}
+
+int nxgpu_crc32(nxgpu_ctx *c, uint32_t seed, const void *src, uint64_t len, int mem, uint32_t *out)
+{
+	nxgpu_cksum_item it = { src, len, seed, 1 };
+	nxgpu_cksum_result r;
+	int rc = nxgpu_checksum_batch(c, &it, 1, &r, mem);
+	if (!rc && out) *out = r.crc32;
+	return rc;
+}
+int nxgpu_adler32(nxgpu_ctx *c, uint32_t seed, const void *src, uint64_t len, int mem, uint32_t *out)
+{
+	nxgpu_cksum_item it = { src, len, 0, seed };
+	nxgpu_cksum_result r;
+	int rc = nxgpu_checksum_batch(c, &it, 1, &r, mem);
+	if (!rc && out) *out = r.adler32;
+	return rc;
+}
+
+/* ------------------------------- deflate ------------------------------- */
+
+// Core: all pointers in `jobs_h` are device pointers except `out`, which this routine assigns to
+// private 16-byte aligned slots.  Leaves DeflateOut[n] in d_outs and per-item crc/adler in d_cks.
+static int deflate_device(nxgpu_ctx *c, DeflateJob *jobs_h, size_t n, int level, bool want_cksum)
+{
+	int rc;
+	if (level <= 0) level = 6;       // lib/nx_deflate.c:655-658 maps level 0 to 6 as well
+	if (level > 9) level = 9;
+	size_t slot_total = 0;
+	uint32_t max_len = 0;
+	for (size_t i = 0; i < n; i++) {
+		slot_total += align_up(nxgpu_deflate_bound(jobs_h[i].src_len) + 16, 16);
+		if (jobs_h[i].src_len > max_len) max_len = jobs_h[i].src_len;
+	}
+	const int grid = (int)(n < (size_t)kNumSMs ? n : (size_t)kNumSMs);
+	const uint32_t tok_stride = (uint32_t)align_up((size_t)max_len + 64, 64);
+	if ((rc = c->d_slots.reserve(slot_total + 64))) return rc;
+	if ((rc = c->d_tok.reserve((size_t)grid * tok_stride * 4))) return rc;
+	if ((rc = c->d_jobs.reserve(n * sizeof(DeflateJob)))) return rc;
+	if ((rc = c->d_outs.reserve(n * sizeof(DeflateOut)))) return rc;
+	size_t o = 0;
+	for (size_t i = 0; i < n; i++) {
+		jobs_h[i].out = static_cast<uint8_t *>(c->d_slots.p) + o;
+		jobs_h[i].out_cap = nxgpu_deflate_bound(jobs_h[i].src_len);
+		o += align_up(jobs_h[i].out_cap + 16, 16);
+	}
+	NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_jobs.p, jobs_h, n * sizeof(DeflateJob), cudaMemcpyHostToDevice, c->stream));
+	timer_begin(c, 0);
+	NXGPU_CUDA_OK(launch_deflate(static_cast<const DeflateJob *>(c->d_jobs.p), static_cast<DeflateOut *>(c->d_outs.p),
+				     (uint32_t)n, level, static_cast<uint32_t *>(c->d_tok.p), tok_stride, grid, c->stream));
+	timer_end(c, 0);
+	if (want_cksum) {
+		std::vector<nxgpu_cksum_item> it(n);
+		for (size_t i = 0; i < n; i++) { it[i].src = jobs_h[i].src; it[i].len = jobs_h[i].src_len; it[i].crc_seed = 0; it[i].adler_seed = 1; }
+		if ((rc = checksum_device(c, it.data(), n, 3))) return rc;
+	}
+	return 0;
+}
+
+int nxgpu_deflate_batch(nxgpu_ctx *c, const nxgpu_deflate_item *items, size_t n, nxgpu_deflate_result *results,
+			int level, int mem)
+{
+	if (!c || (!items && n) || (!results && n)) return NXGPU_E_ARG;
+	if (n == 0) return 0;
+	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
+	int rc;
+	if ((rc = c->h_jobs.reserve(n * sizeof(DeflateJob)))) return rc;
+	DeflateJob *jh = static_cast<DeflateJob *>(c->h_jobs.p);
+	memset(jh, 0, n * sizeof(DeflateJob));
+	if (mem == NXGPU_MEM_HOST) {
+		// upload [src - hist_len, src + src_len) of every item; contiguous items share one copy
+		uint64_t total = 0;
+		for (size_t i = 0; i < n; i++) total += align_up((uint64_t)items[i].hist_len + items[i].src_len, 16) + 16;
+		if ((rc = c->d_in.reserve(total))) return rc;
+		uint64_t o = 0;
+		const uint8_t *span_lo = nullptr, *span_hi = nullptr;   // host span already uploaded
+		uint8_t *span_dev = nullptr;
+		for (size_t i = 0; i < n; i++) {
+			const uint8_t *lo = static_cast<const uint8_t *>(items[i].src) - items[i].hist_len;
+			const uint8_t *hi = static_cast<const uint8_t *>(items[i].src) + items[i].src_len;
+			if (items[i].hist_len > 32768) return NXGPU_E_ARG;
+			if (span_lo && lo >= span_lo && lo <= span_hi && hi >= span_hi) {
+				// continues the previous span: upload only the new tail
+				const size_t add = hi - span_hi;
+				if (add)
+					NXGPU_CUDA_OK(cudaMemcpyAsync(span_dev + (span_hi - span_lo), span_hi, add, cudaMemcpyHostToDevice, c->stream));
+				span_hi = hi;
+				o = (span_dev - static_cast<uint8_t *>(c->d_in.p)) + (span_hi - span_lo);
+			} else {
+				o = align_up(o, 16);
+				span_dev = static_cast<uint8_t *>(c->d_in.p) + o;
+				span_lo = lo; span_hi = hi;
+				if (hi > lo)
+					NXGPU_CUDA_OK(cudaMemcpyAsync(span_dev, lo, hi - lo, cudaMemcpyHostToDevice, c->stream));
+				o += hi - lo;
+			}
+			jh[i].src = span_dev + (static_cast<const uint8_t *>(items[i].src) - span_lo);
+			jh[i].src_len = items[i].src_len; jh[i].hist_len = items[i].hist_len; jh[i].flags = items[i].flags;
+		}
+	} else {
+		for (size_t i = 0; i < n; i++) {
+			if (items[i].hist_len > 32768) return NXGPU_E_ARG;
+			jh[i].src = static_cast<const uint8_t *>(items[i].src);
+			jh[i].src_len = items[i].src_len; jh[i].hist_len = items[i].hist_len; jh[i].flags = items[i].flags;
+		}
+	}
+	if ((rc = deflate_device(c, jh, n, level, true))) return rc;
+	// results
+	if ((rc = c->h_outs.reserve(n * sizeof(DeflateOut) + n * 8))) return rc;
+	DeflateOut *oh = static_cast<DeflateOut *>(c->h_outs.p);
+	uint32_t *ck = reinterpret_cast<uint32_t *>(oh + n);
+	NXGPU_CUDA_OK(cudaMemcpyAsync(oh, c->d_outs.p, n * sizeof(DeflateOut), cudaMemcpyDeviceToHost, c->stream));
+	NXGPU_CUDA_OK(cudaMemcpyAsync(ck, c->d_cks.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+	if (mem == NXGPU_MEM_DEVICE) {
+		// device copy of slot -> caller's dst
+		if ((rc = c->d_dst_ptrs.reserve(n * 12))) return rc;
+		if ((rc = c->h_stage.reserve(n * 12))) return rc;
+		uint8_t **dp = static_cast<uint8_t **>(c->h_stage.p);
+		uint32_t *caps = reinterpret_cast<uint32_t *>(dp + n);
+		for (size_t i = 0; i < n; i++) { dp[i] = static_cast<uint8_t *>(items[i].dst); caps[i] = items[i].dst_cap; }
+		NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_dst_ptrs.p, dp, n * 12, cudaMemcpyHostToDevice, c->stream));
+		const uint32_t grid = (uint32_t)(n < (size_t)(kNumSMs * 8) ? n : (size_t)(kNumSMs * 8));
+		scatter_outputs_kernel<<<grid, 256, 0, c->stream>>>(static_cast<const DeflateJob *>(c->d_jobs.p),
+			static_cast<const DeflateOut *>(c->d_outs.p), static_cast<uint8_t *const *>(c->d_dst_ptrs.p),
+			reinterpret_cast<const uint32_t *>(static_cast<uint8_t **>(c->d_dst_ptrs.p) + n), (uint32_t)n);
+		NXGPU_CUDA_OK(cudaGetLastError());
+		c->launches++;
+	}
+	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	for (size_t i = 0; i < n; i++) {
+		results[i].rc = oh[i].rc;
+		results[i].out_len = oh[i].out_len;
+		results[i].tebc = oh[i].tebc;
+		results[i].crc32 = ck[i];
+		results[i].adler32 = ck[n + i];
+		results[i].n_tokens = oh[i].n_tokens;
+		if (oh[i].rc == 0 && oh[i].out_len > items[i].dst_cap)
+			results[i].rc = NXGPU_E_BUF;
+	}
+	if (mem == NXGPU_MEM_HOST) {
+		for (size_t i = 0; i < n; i++)
+			if (results[i].rc == 0 && results[i].out_len)
+				NXGPU_CUDA_OK(cudaMemcpyAsync(items[i].dst, jh[i].out, results[i].out_len, cudaMemcpyDeviceToHost, c->stream));
+		NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	}
+	return 0;
+}
+
+int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *dst, uint64_t dst_cap,
+			 int level, int wrap, uint32_t chunk, uint64_t *chunk_offsets, nxgpu_stream_result *res, int mem)
+{
+	if (!c || (!src && src_len) || !dst || !res) return NXGPU_E_ARG;
+	if (wrap != NXGPU_WRAP_RAW && wrap != NXGPU_WRAP_ZLIB && wrap != NXGPU_WRAP_GZIP) return NXGPU_E_ARG;
+	if (chunk == 0) chunk = 262144;
+	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
+	int rc;
+	const size_t n = src_len ? (size_t)((src_len + chunk - 1) / chunk) : 1;
+	const uint8_t *dsrc = static_cast<const uint8_t *>(src);
+	uint8_t *ddst = static_cast<uint8_t *>(dst);
+	if (mem == NXGPU_MEM_HOST) {
+		if ((rc = c->d_in.reserve(src_len + 16))) return rc;
+		if ((rc = c->d_out.reserve(dst_cap + 16))) return rc;
+		if (src_len)
+			NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_in.p, src, src_len, cudaMemcpyHostToDevice, c->stream));
+		dsrc = static_cast<const uint8_t *>(c->d_in.p);
+		ddst = static_cast<uint8_t *>(c->d_out.p);
+	}
+	if ((rc = c->h_jobs.reserve(n * sizeof(DeflateJob)))) return rc;
+	DeflateJob *jh = static_cast<DeflateJob *>(c->h_jobs.p);
+	memset(jh, 0, n * sizeof(DeflateJob));
+	for (size_t i = 0; i < n; i++) {
+		const uint64_t o = (uint64_t)i * chunk;
+		jh[i].src = dsrc + o;
+		jh[i].src_len = (uint32_t)(src_len - o < chunk ? src_len - o : chunk);
+		jh[i].hist_len = (uint32_t)(o < 32768 ? o : 32768);
+		jh[i].flags = (i + 1 == n) ? NXGPU_F_FINAL : 0;
+	}
+	if ((rc = deflate_device(c, jh, n, level, false))) return rc;
+	// whole-stream checksums: chunks are the ranges of one job
+	nxgpu_cksum_item whole = { dsrc, src_len, 0, 1 };
+	if ((rc = checksum_device(c, &whole, 1, 3))) return rc;
+	// header
+	uint64_t hdr = 0; int hdr_len = 0;
+	if (wrap == NXGPU_WRAP_GZIP) {
+		// 1f 8b 08 00 mtime=0 xfl=0 os=3, the blank header of lib/nx_deflate.c:473-489
+		hdr = 0x1full | 0x8bull << 8 | 0x08ull << 16; hdr_len = 8;
+	} else if (wrap == NXGPU_WRAP_ZLIB) {
+		const int lv = level <= 0 ? 6 : level;
+		const uint32_t flevel = lv < 2 ? 0 : lv < 6 ? 1 : lv == 6 ? 2 : 3;
+		uint32_t h = (0x78u << 8) | (flevel << 6);
+		h += 31 - (h % 31);
+		hdr = (h >> 8) | ((h & 0xff) << 8); hdr_len = 2;
+	}
+	const uint64_t hdr_total = wrap == NXGPU_WRAP_GZIP ? 10 : hdr_len;
+	if (dst_cap < hdr_total) return NXGPU_E_BUF;
+	if (hdr_len) {
+		write_bytes_kernel<<<1, 1, 0, c->stream>>>(ddst, hdr, hdr_len);
+		if (wrap == NXGPU_WRAP_GZIP)
+			write_bytes_kernel<<<1, 1, 0, c->stream>>>(ddst + 8, 0x0300ull, 2);
+		c->launches += 1;
+	}
+	if ((rc = c->d_offsets.reserve((n + 2) * 8))) return rc;
+	uint64_t *d_off = static_cast<uint64_t *>(c->d_offsets.p);
+	const DeflateJob *dj = static_cast<const DeflateJob *>(c->d_jobs.p);
+	const DeflateOut *dout = static_cast<const DeflateOut *>(c->d_outs.p);
+	NXGPU_CUDA_OK(launch_scan_offsets(dout, (uint32_t)n, hdr_total, d_off, c->stream));
+	NXGPU_CUDA_OK(launch_gather(dj, dout, d_off, (uint32_t)n, ddst, dst_cap, c->stream));
+	const uint32_t *d_crc = static_cast<const uint32_t *>(c->d_cks.p);
+	NXGPU_CUDA_OK(launch_finish_stream(dout, d_off, (uint32_t)n, ddst, dst_cap, wrap, d_crc, d_crc + 1, src_len, d_off + n + 1, c->stream));
+	c->launches += 3;
+	// results back
+	if ((rc = c->h_outs.reserve(n * sizeof(DeflateOut) + (n + 2) * 8 + 16))) return rc;
+	DeflateOut *oh = static_cast<DeflateOut *>(c->h_outs.p);
+	uint64_t *offh = reinterpret_cast<uint64_t *>(oh + n);
+	uint32_t *ckh = reinterpret_cast<uint32_t *>(offh + n + 2);
+	NXGPU_CUDA_OK(cudaMemcpyAsync(oh, c->d_outs.p, n * sizeof(DeflateOut), cudaMemcpyDeviceToHost, c->stream));
+	NXGPU_CUDA_OK(cudaMemcpyAsync(offh, d_off, (n + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
+	NXGPU_CUDA_OK(cudaMemcpyAsync(ckh, c->d_cks.p, 8, cudaMemcpyDeviceToHost, c->stream));
+	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	uint64_t ntok = 0;
+	for (size_t i = 0; i < n; i++) {
+		if (oh[i].rc) { set_error("chunk %zu failed rc=%d", i, oh[i].rc); return oh[i].rc < 0 ? oh[i].rc : NXGPU_E_DATA; }
+		ntok += oh[i].n_tokens;
+	}
+	const uint64_t total = offh[n + 1];
+	const uint64_t need = offh[n] + (wrap == NXGPU_WRAP_GZIP ? 8 : wrap == NXGPU_WRAP_ZLIB ? 4 : 0);
+	if (need > dst_cap) { set_error("output needs %llu bytes, capacity %llu", (unsigned long long)need, (unsigned long long)dst_cap); return NXGPU_E_BUF; }
+	if (mem == NXGPU_MEM_HOST) {
+		NXGPU_CUDA_OK(cudaMemcpyAsync(dst, ddst, total, cudaMemcpyDeviceToHost, c->stream));
+		NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	}
+	if (chunk_offsets)
+		for (size_t i = 0; i <= n; i++) chunk_offsets[i] = offh[i];
+	res->out_len = total;
+	res->crc32 = ckh[0];
+	res->adler32 = ckh[1];
+	res->n_chunks = (uint32_t)n;
+	res->n_tokens = ntok;
+	return 0;
+}
+
+/* ------------------------------- inflate ------------------------------- */
+
+int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n, nxgpu_inflate_result *results, int mem)
+{
+	if (!c || (!items && n) || (!results && n)) return NXGPU_E_ARG;
+	if (n == 0) return 0;
+	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
+	int rc;
+	if ((rc = c->h_jobs.reserve(n * sizeof(InflateJob)))) return rc;
+	InflateJob *jh = static_cast<InflateJob *>(c->h_jobs.p);
+	bool dst_contig = true;
+	if (mem == NXGPU_MEM_HOST) {
+		uint64_t in_total = 0, out_total = 0;
+		for (size_t i = 0; i < n; i++) {
+			in_total += align_up(items[i].src_len, 16);
+			out_total += align_up((uint64_t)items[i].hist_len + items[i].dst_cap, 16);
+			if (i && static_cast<uint8_t *>(items[i].dst) != static_cast<uint8_t *>(items[i - 1].dst) + items[i - 1].dst_cap)
+				dst_contig = false;
+			if (items[i].hist_len) dst_contig = false;
+		}
+		if ((rc = c->d_in.reserve(in_total + 16))) return rc;
+		if ((rc = c->d_out.reserve(out_total + 16))) return rc;
+		// pack sources through pinned staging: one H2D instead of n small ones
+		if ((rc = c->h_stage.reserve(in_total + 16))) return rc;
+		uint64_t io = 0, oo = 0;
+		uint8_t *hs = static_cast<uint8_t *>(c->h_stage.p);
+		for (size_t i = 0; i < n; i++) {
+			memcpy(hs + io, items[i].src, items[i].src_len);
+			jh[i].src = static_cast<uint8_t *>(c->d_in.p) + io;
+			jh[i].src_len = items[i].src_len; jh[i].wrap = items[i].wrap;
+			jh[i].hist_len = items[i].hist_len; jh[i].dst_cap = items[i].dst_cap;
+			if (dst_contig) {
+				jh[i].dst = static_cast<uint8_t *>(c->d_out.p) + (static_cast<uint8_t *>(items[i].dst) - static_cast<uint8_t *>(items[0].dst));
+			} else {
+				jh[i].dst = static_cast<uint8_t *>(c->d_out.p) + oo + items[i].hist_len;
+				if (items[i].hist_len)
+					NXGPU_CUDA_OK(cudaMemcpyAsync(jh[i].dst - items[i].hist_len, static_cast<uint8_t *>(items[i].dst) - items[i].hist_len,
+								      items[i].hist_len, cudaMemcpyHostToDevice, c->stream));
+			}
+			io += align_up(items[i].src_len, 16);
+			oo += align_up((uint64_t)items[i].hist_len + items[i].dst_cap, 16);
+		}
+		NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_in.p, hs, in_total, cudaMemcpyHostToDevice, c->stream));
+	} else {
+		for (size_t i = 0; i < n; i++) {
+			jh[i].src = static_cast<const uint8_t *>(items[i].src); jh[i].src_len = items[i].src_len; jh[i].wrap = items[i].wrap;
+			jh[i].dst = static_cast<uint8_t *>(items[i].dst); jh[i].dst_cap = items[i].dst_cap; jh[i].hist_len = items[i].hist_len;
+		}
+	}
+	if ((rc = c->d_jobs.reserve(n * sizeof(InflateJob)))) return rc;
+	if ((rc = c->d_outs.reserve(n * sizeof(InflateOut)))) return rc;
+	if ((rc = c->d_misc.reserve(64))) return rc;
+	const size_t rb = checksum_range_bytes(), pb = checksum_partial_bytes();
+	if ((rc = c->d_ranges.reserve(n * rb + (n + 1) * 4))) return rc;
+	if ((rc = c->d_parts.reserve(n * pb))) return rc;
+	if ((rc = c->d_cks.reserve(n * 8 + 16))) return rc;
+	NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_jobs.p, jh, n * sizeof(InflateJob), cudaMemcpyHostToDevice, c->stream));
+	const InflateJob *dj = static_cast<const InflateJob *>(c->d_jobs.p);
+	InflateOut *dout = static_cast<InflateOut *>(c->d_outs.p);
+	timer_begin(c, 1);
+	NXGPU_CUDA_OK(launch_inflate(dj, dout, (uint32_t)n, static_cast<uint32_t *>(c->d_misc.p), c->stream));
+	timer_end(c, 1);
+	// crc32 / adler32 of every output, lengths taken from the device results
+	uint32_t *d_rs = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(c->d_ranges.p) + n * rb);
+	NXGPU_CUDA_OK(launch_ranges_from_inflate(dj, dout, (uint32_t)n, c->d_ranges.p, d_rs, c->stream));
+	uint32_t *d_crc = static_cast<uint32_t *>(c->d_cks.p), *d_adler = d_crc + n;
+	timer_begin(c, 2);
+	NXGPU_CUDA_OK(launch_checksum_ranges(c->d_ranges.p, (uint32_t)n, c->d_parts.p, 3, c->stream));
+	timer_end(c, 2);
+	NXGPU_CUDA_OK(launch_checksum_combine(c->d_ranges.p, c->d_parts.p, d_rs, (uint32_t)n, nullptr, nullptr, d_crc, d_adler, c->stream));
+	c->launches += 2;
+	if ((rc = c->h_outs.reserve(n * sizeof(InflateOut) + n * 8))) return rc;
+	InflateOut *oh = static_cast<InflateOut *>(c->h_outs.p);
+	uint32_t *ck = reinterpret_cast<uint32_t *>(oh + n);
+	NXGPU_CUDA_OK(cudaMemcpyAsync(oh, dout, n * sizeof(InflateOut), cudaMemcpyDeviceToHost, c->stream));
+	NXGPU_CUDA_OK(cudaMemcpyAsync(ck, d_crc, n * 8, cudaMemcpyDeviceToHost, c->stream));
+	if (mem == NXGPU_MEM_HOST && dst_contig) {
+		const uint64_t span = (static_cast<uint8_t *>(items[n - 1].dst) - static_cast<uint8_t *>(items[0].dst)) + items[n - 1].dst_cap;
+		NXGPU_CUDA_OK(cudaMemcpyAsync(items[0].dst, c->d_out.p, span, cudaMemcpyDeviceToHost, c->stream));
+	}
+	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	for (size_t i = 0; i < n; i++) {
+		nxgpu_inflate_result &r = results[i];
+		r.rc = oh[i].rc; r.out_len = oh[i].out_len; r.in_used = oh[i].in_used;
+		r.crc32 = ck[i]; r.adler32 = ck[n + i];
+		r.flags = oh[i].flags & 1;
+		const uint32_t wrap = oh[i].flags >> 8;
+		if (r.rc == 0 && wrap == NXGPU_WRAP_GZIP) {
+			// the check lib/nx_inflate.c:763-848 does on the host
+			if (oh[i].trailer_crc != r.crc32 || oh[i].trailer_isize != r.out_len) r.rc = NXGPU_E_DATA; else r.flags |= 2;
+		} else if (r.rc == 0 && wrap == NXGPU_WRAP_ZLIB) {
+			if (oh[i].trailer_crc != r.adler32) r.rc = NXGPU_E_DATA; else r.flags |= 2;
+		}
+	}
+	if (mem == NXGPU_MEM_HOST && !dst_contig) {
+		for (size_t i = 0; i < n; i++)
+			if (results[i].out_len)
+				NXGPU_CUDA_OK(cudaMemcpyAsync(items[i].dst, jh[i].dst, results[i].out_len, cudaMemcpyDeviceToHost, c->stream));
+		NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	}
+	return 0;
+}
+
+/* ------------------------------ makedata ------------------------------- */
+
+// Same draw order as reference samples/makedata.c:35-70 (srand48/lrand48).  A draw of dist == 0
+// copies a byte onto itself there, i.e. keeps the fresh (zero) malloc page, hence the memset.
+uint64_t nxgpu_makedata(int seed, int log2size, const void *seedfile, uint64_t seedfile_len, void *out_, uint64_t out_cap)
+{
+	uint8_t *out = static_cast<uint8_t *>(out_);
+	uint64_t bufsz = 1ull << log2size;
+	srand48(seed);
+	const long a = lrand48() % 2;
+	const long b = lrand48() % (long)(bufsz / 10);
+	bufsz += (uint64_t)a * (uint64_t)b;
+	if (bufsz > out_cap)
+		return 0;
+	memset(out, 0, bufsz);
+	uint64_t idx = seedfile_len < bufsz / 2 ? seedfile_len : bufsz / 2;
+	memcpy(out, seedfile, idx);
+	const uint64_t len_max = (uint64_t)(lrand48() % 240) + 10;
+	const uint64_t dist_max = (uint64_t)(lrand48() % (1L << 16)) + 1;
+	while (idx < bufsz) {
+		uint64_t dist = (uint64_t)lrand48() % (idx > dist_max ? dist_max : idx);
+		uint64_t len = (uint64_t)lrand48() % len_max + 16;
+		if (dist > idx)
+			dist = idx;
+		while (len-- > 0 && idx < bufsz) {
+			out[idx] = out[idx - dist];
+			idx++;
+		}
+	}
+	return idx;
+}
+
+} // extern "C"

@@ -1,0 +1,321 @@
+"""GPU parity tests (run with -m gpu on a B200): every call goes through the C-ABI in
+include/nxgpu.h; the checker is the oracle (oracle/*.c) and system zlib — the library the
+reference's software path resolves to (lib/sw_zlib.c:283-327).
+
+Bars: crc32 / adler32 / inflate output are bit-exact; deflate output must be a valid
+RFC 1950/1951/1952 stream that zlib AND the oracle inflate decode bit-exactly to the input, with
+the compressed size within 5 % of zlib level 6 (BASELINE.json north_star) — compressed bytes are
+not pinned by the reference."""
+import ctypes as C
+import gzip
+import json
+import os
+import random
+import zlib
+
+import pytest
+
+from conftest import GOLDEN, oracle_inflate
+
+pytestmark = pytest.mark.gpu
+
+
+def _text(n, seed=1):
+    # test/test_utils.c:22-28,152-161: uniform draws from a 33-symbol alphabet (seeded here)
+    rnd = random.Random(seed)
+    alpha = b"abcdefghijklmnopqrstuvwxyz,.!?.{}"
+    return bytes(rnd.choice(alpha) for _ in range(n))
+
+
+# ---------------------------------------------------------------- checksums
+
+@pytest.mark.parametrize("name", ["crc32", "adler32"])
+def test_reference_kats_on_gpu(engine, name):
+    kats = json.load(open(os.path.join(GOLDEN, f"kat_{name}.json")))
+    items, keep, idx = [], [], []
+    for i, k in enumerate(kats):
+        if k["null"]:
+            continue          # NULL-buffer cases are host API behaviour (lib/nx_crc.c:218), not engine work
+        buf = C.create_string_buffer(bytes.fromhex(k["data_hex"]), max(k["len"], 1))
+        keep.append(buf)
+        items.append((C.addressof(buf), k["len"], k["seed"] if name == "crc32" else 0, k["seed"] if name == "adler32" else 1))
+        idx.append(i)
+    res = engine.checksum_batch(items, mem=0)
+    for i, (crc, adler) in zip(idx, res):
+        assert (crc if name == "crc32" else adler) == kats[i]["expect"], kats[i]
+
+
+def test_checksum_sizes_seeds_alignment(engine, oracle, alice):
+    rnd = random.Random(2)
+    big = (alice * 30)[: 4 * 1024 * 1024 + 7]
+    for n in [0, 1, 2, 15, 16, 17, 63, 64, 65, 4095, 4096, 32767, 32768, 32769, 65537, 262144, 1 << 20, len(big)]:
+        for off in (0, 1, 13):
+            d = big[off:off + n]
+            cs, as_ = rnd.getrandbits(32), rnd.randrange(65521) | rnd.randrange(65521) << 16
+            assert engine.crc32(d, cs) == oracle.oracle_crc32(cs, d, len(d)) == zlib.crc32(d, cs)
+            assert engine.adler32(d, as_) == oracle.oracle_adler32(as_, d, len(d))
+
+
+def test_crc32_vpmsum_boundary_symbol(pg, engine, oracle, alice):
+    # contract of lib/crc32_ppc.c:30 — raw update, 16-byte aligned, len % 16 == 0
+    lib = pg.load_library()
+    buf = (C.c_char * 65536).from_buffer_copy(alice[:65536])
+    for n in (16, 4096, 65536):
+        for seed in (0, 0xffffffff, 0x1234abcd):
+            assert lib.__crc32_vpmsum(seed, C.addressof(buf), n) == oracle.oracle_crc32_raw(seed, alice[:n], n)
+
+
+def test_checksum_combine_of_chunks_equals_whole(engine, alice):
+    # C4's merge step: per-chunk CRCs folded with crc32_combine (lib/nx_crc.c:374) == CRC of the stream
+    data = alice * 8
+    chunk = 262144
+    crc, adl = 0, 1
+    for o in range(0, len(data), chunk):
+        p = data[o:o + chunk]
+        crc = engine.crc32_combine(crc, engine.crc32(p), len(p))
+        adl = engine.adler32_combine(adl, engine.adler32(p), len(p))
+    assert crc == zlib.crc32(data) and adl == zlib.adler32(data)
+
+
+# ---------------------------------------------------------------- deflate
+
+def _decode(blob, wrap):
+    if wrap == 2:
+        return gzip.decompress(blob)
+    if wrap == 1:
+        return zlib.decompress(blob)
+    return zlib.decompress(blob, -15)
+
+
+CASES = ["empty", "one", "hello", "alice", "zeros", "same", "random", "text", "md20", "ragged"]
+
+
+def _case(name, alice, pg):
+    if name == "empty": return b""
+    if name == "one": return b"x"
+    if name == "hello": return b"hello, hello! hello, hello!"      # test/deflate/hello.c
+    if name == "alice": return alice
+    if name == "zeros": return bytes(1 << 20)                       # test/deflate/0.c
+    if name == "same": return b"\xa5" * 300001                      # test/test_utils.c:141
+    if name == "random": return random.Random(4).randbytes(300000)
+    if name == "text": return _text(200000)
+    if name == "md20": return pg.makedata(1, 20, alice)
+    if name == "ragged": return (alice * 3)[:262144 * 2 + 4097]     # last chunk not a multiple of anything
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_deflate_roundtrip_zlib_and_oracle(engine, oracle, pg, alice, name, level):
+    data = _case(name, alice, pg)
+    for wrap in (pg.WRAP_GZIP, pg.WRAP_ZLIB, pg.WRAP_RAW):
+        blob, index, res = engine.compress(data, level=level, wrap=wrap, with_index=True)
+        assert len(blob) <= engine.deflate_bound(len(data))          # test/test_utils.c:296
+        assert _decode(blob, wrap) == data                           # system zlib decodes it
+        rc, out, used, crc, adler = oracle_inflate(oracle, blob, len(data) + 8, wrap)
+        assert rc == 0 and out == data and used == len(blob)         # and so does the oracle
+        assert res.crc32 == zlib.crc32(data) and res.adler32 == zlib.adler32(data)
+        assert index[0] == (10 if wrap == 2 else 2 if wrap == 1 else 0)
+        assert list(index) == sorted(index)
+
+
+def test_deflate_ratio_within_5pct_of_zlib6(engine, pg, alice, vectors):
+    # BASELINE.json north_star: level-6-equivalent ratio within 5 % of zlib level 6
+    for key in ("s1_b20", "s4_b20", "s5_b20"):
+        seed = int(key[1])
+        data = pg.makedata(seed, 20, alice)
+        assert zlib.crc32(data) == vectors["makedata"][key]["crc32"]
+        got = len(engine.compress(data, level=6, wrap=pg.WRAP_ZLIB))
+        assert got <= 1.05 * vectors["makedata"][key]["zlib_L6"], (key, got)
+        got1 = len(engine.compress(data, level=1, wrap=pg.WRAP_ZLIB))
+        assert got1 <= 1.05 * vectors["makedata"][key]["zlib_L1"], (key, got1)
+    got = len(engine.compress(alice, level=6, wrap=pg.WRAP_ZLIB))
+    assert got <= 1.05 * vectors["alice29"]["compress2_L6"], got     # 54,404 B via the reference's compress2()
+
+
+def test_deflate_chunk_sizes_and_priming(engine, pg, alice):
+    data = pg.makedata(4, 20, alice)
+    sizes = {}
+    for chunk in (4096, 65536, 262144, 1 << 20):
+        blob, index, res = engine.compress(data, level=6, wrap=pg.WRAP_GZIP, chunk=chunk, with_index=True)
+        assert gzip.decompress(blob) == data
+        assert res.n_chunks == -(-len(data) // chunk)
+        sizes[chunk] = len(blob)
+        # every interior chunk ends with the byte-aligning empty stored block (lib/nx_deflate.c:220-243)
+        for off in index[1:-1]:
+            assert blob[off - 4:off] == b"\x00\x00\xff\xff"
+    assert sizes[262144] < sizes[4096]
+
+
+def test_deflate_batch_items_concatenate(engine, pg, alice):
+    # the NX job contract: each item primed with the 32 KiB before it, outputs join bytewise
+    data = (alice * 4)[:600000]
+    src = (C.c_char * len(data)).from_buffer_copy(data)
+    chunk = 100000
+    items, outs = [], []
+    for o in range(0, len(data), chunk):
+        n = min(chunk, len(data) - o)
+        cap = n + 1024
+        ob = (C.c_char * cap)()
+        outs.append(ob)
+        items.append(pg.DeflateItem(C.addressof(src) + o, n, min(o, 32768), C.addressof(ob), cap,
+                                    pg.F_FINAL if o + n == len(data) else 0))
+    res = engine.deflate_batch(items, level=6, mem=pg.MEM_HOST)
+    raw = b""
+    for r, ob, it in zip(res, outs, items):
+        assert r.rc == 0
+        piece = data[len(raw and b"") :]
+        raw += bytes(memoryview(ob)[: r.out_len])
+    assert zlib.decompress(raw, -15) == data
+    o = 0
+    for r, it in zip(res, items):
+        p = data[o:o + it.src_len]
+        assert r.crc32 == zlib.crc32(p) and r.adler32 == zlib.adler32(p)
+        o += it.src_len
+
+
+def test_deflate_fixed_and_small_capacity(engine, pg, alice):
+    data = alice[:50000]
+    src = (C.c_char * len(data)).from_buffer_copy(data)
+    ob = (C.c_char * 60000)()
+    r = engine.deflate_batch([pg.DeflateItem(C.addressof(src), len(data), 0, C.addressof(ob), 60000, pg.F_FINAL | pg.F_FIXED)], 6)[0]
+    assert r.rc == 0
+    blob = bytes(memoryview(ob)[: r.out_len])
+    assert (blob[0] >> 1) & 3 == 1                                   # BTYPE=01, Z_FIXED (lib/nx_deflate.c:1801-1831)
+    assert zlib.decompress(blob, -15) == data
+    r = engine.deflate_batch([pg.DeflateItem(C.addressof(src), len(data), 0, C.addressof(ob), 100, pg.F_FINAL)], 6)[0]
+    assert r.rc == pg.E_BUF                                          # the NX CC=13 case
+
+
+# ---------------------------------------------------------------- inflate
+
+def _streams(data):
+    yield gzip.compress(data, 6, mtime=0)
+    yield gzip.compress(data, 1, mtime=0)
+    yield zlib.compress(data, 9)
+    yield zlib.compress(data, 0)
+    c = zlib.compressobj(6, zlib.DEFLATED, -15, 8, zlib.Z_FIXED)
+    yield c.compress(data) + c.flush()
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)
+    parts = [c.compress(data[i:i + 7000]) + c.flush(zlib.Z_SYNC_FLUSH) for i in range(0, len(data), 7000)]
+    yield b"".join(parts) + c.flush()
+    c = zlib.compressobj(9, zlib.DEFLATED, -15, 9, zlib.Z_HUFFMAN_ONLY)
+    yield c.compress(data) + c.flush()
+
+
+def test_inflate_batch_bit_exact(engine, oracle, pg, alice):
+    rnd = random.Random(8)
+    datas = [b"", b"a", b"ab" * 5, alice, bytes(200000), rnd.randbytes(100000), _text(150000), pg.makedata(5, 20, alice)[:300000],
+             bytes(range(256)) * 300]
+    blobs, caps, want = [], [], []
+    for d in datas:
+        for b in _streams(d):
+            blobs.append(b); caps.append(len(d) + 32); want.append(d)
+    keep, items = [], []
+    for b, cap in zip(blobs, caps):
+        sb = C.create_string_buffer(b, len(b))
+        ob = (C.c_char * cap)()
+        keep.append((sb, ob))
+        items.append(pg.InflateItem(C.addressof(sb), len(b), C.addressof(ob), cap, pg.WRAP_AUTO, 0))
+    res = engine.inflate_batch(items, mem=pg.MEM_HOST)
+    for r, (sb, ob), b, d in zip(res, keep, blobs, want):
+        assert r.rc == 0, (len(d), r.rc)
+        assert bytes(memoryview(ob)[: r.out_len]) == d
+        assert r.in_used == len(b)
+        assert r.crc32 == zlib.crc32(d) and r.adler32 == zlib.adler32(d)
+        orc, oout, oused, ocrc, oadler = oracle_inflate(oracle, b, len(d) + 32, 3)
+        assert (orc, oused, ocrc, oadler) == (0, r.in_used, r.crc32, r.adler32)
+
+
+def test_inflate_every_small_length(engine):
+    # test/inflate/random_buffer.c:47-63 walks every length 1..100
+    blobs, caps, want = [], [], []
+    for n in range(0, 101):
+        d = _text(n, seed=n)
+        blobs.append(zlib.compress(d, 6)); caps.append(n + 4); want.append(d)
+    assert engine.uncompress_many(blobs, caps) == want
+
+
+def test_inflate_errors(engine, pg, alice):
+    good = zlib.compress(alice, 6)
+    bad_adler = bytearray(good); bad_adler[-1] ^= 0x55
+    trunc = good[: len(good) // 2]
+    garbage = bytes([0x78, 0x9c]) + bytes([0xff] * 100)
+    keep, items = [], []
+    for b, cap in ((bytes(bad_adler), len(alice)), (trunc, len(alice)), (garbage, 1000), (good, 1000), (good, len(alice))):
+        sb = C.create_string_buffer(b, len(b)); ob = (C.c_char * max(cap, 1))(); keep.append((sb, ob))
+        items.append(pg.InflateItem(C.addressof(sb), len(b), C.addressof(ob), cap, pg.WRAP_ZLIB, 0))
+    r = engine.inflate_batch(items, mem=pg.MEM_HOST)
+    assert [x.rc for x in r] == [pg.E_DATA, pg.E_DATA, pg.E_DATA, pg.E_BUF, 0]
+
+
+def test_inflate_reference_scp_stream(engine, pg):
+    # test/test_buf_error.c:107 — a sync-flushed prefix without a final block
+    blob = bytes.fromhex(json.load(open(os.path.join(GOLDEN, "scp_stream.json")))["zlib_stream_hex"])
+    want = zlib.decompressobj().decompress(blob)
+    sb = C.create_string_buffer(blob, len(blob)); ob = (C.c_char * 8192)()
+    r = engine.inflate_batch([pg.InflateItem(C.addressof(sb), len(blob), C.addressof(ob), 8192, pg.WRAP_ZLIB, 0)])[0]
+    assert r.rc == pg.E_DATA and not (r.flags & 1)                   # no BFINAL block in the capture
+    assert bytes(memoryview(ob)[: r.out_len]) == want                # but every decodable byte is out
+
+
+def test_own_deflate_own_inflate_segments(engine, pg, alice):
+    # C3 / §8b: the sync-point index lets one big member inflate as independent segments
+    data = pg.makedata(1, 20, alice) + alice
+    blob, index, res = engine.compress(data, level=6, wrap=pg.WRAP_RAW, chunk=65536, with_index=True)
+    assert engine.uncompress(blob, len(data), wrap=pg.WRAP_RAW) == data
+    src = (C.c_char * len(blob)).from_buffer_copy(blob)
+    out = (C.c_char * len(data))()
+    items = []
+    for i in range(res.n_chunks):
+        o = i * 65536
+        n = min(65536, len(data) - o)
+        items.append(pg.InflateItem(C.addressof(src) + index[i], index[i + 1] - index[i], C.addressof(out) + o, n, pg.WRAP_RAW, min(o, 32768)))
+    # segments need their window: run them in waves of independent (non-adjacent history) items
+    # here: sequential waves of one segment keep it simple and still exercise hist_len
+    for it in items:
+        r = engine.inflate_batch([it], mem=pg.MEM_HOST)
+    # host-mode copies only the new bytes back; rebuild via device buffers for the real parallel case
+    # (covered in test_inflate_segments_device)
+
+
+def test_inflate_segments_device(engine, pg, alice):
+    data = pg.makedata(4, 20, alice)
+    chunk = 65536
+    blob, index, res = engine.compress(data, level=6, wrap=pg.WRAP_RAW, chunk=chunk, with_index=True)
+    dsrc = engine.alloc(len(blob)); dsrc.upload(blob)
+    ddst = engine.alloc(len(data))
+    # wave 0: even segments need odd neighbours' bytes as window, so decode in order of dependency:
+    # all segments in ONE batch is only legal when hist_len == 0; with priming they chain, so run
+    # them as res.n_chunks single-item batches on the device-resident buffers
+    for i in range(res.n_chunks):
+        o = i * chunk
+        n = min(chunk, len(data) - o)
+        it = pg.InflateItem(dsrc.ptr + index[i], index[i + 1] - index[i], ddst.ptr + o, n, pg.WRAP_RAW, min(o, 32768))
+        r = engine.inflate_batch([it], mem=pg.MEM_DEVICE)[0]
+        want_final = 1 if i == res.n_chunks - 1 else 0
+        assert r.out_len == n and (r.flags & 1) == want_final, (i, r.rc, r.out_len)
+    assert ddst.download() == data
+    dsrc.free(); ddst.free()
+
+
+# ---------------------------------------------------------------- size-independent properties at scale
+
+def test_large_roundtrip_checksum_of_checksums(engine, pg, alice):
+    # 64 MiB of makedata text (crc32 pinned by BASELINE.md: ece3d95e), device resident end to end
+    data = pg.makedata(1, 26, alice)
+    assert zlib.crc32(data) == 0xece3d95e
+    n = len(data)
+    dsrc = engine.alloc(n); dsrc.upload(data)
+    cap = engine.deflate_bound(n)
+    ddst = engine.alloc(cap)
+    res = engine.deflate_stream_device(dsrc.ptr, n, ddst.ptr, cap, level=6, wrap=pg.WRAP_GZIP)
+    assert res.crc32 == 0xece3d95e and res.n_chunks == 256
+    blob = ddst.download(res.out_len)
+    assert len(blob) <= 1.05 * 10742124                              # zlib L6 whole-stream size, BASELINE.md §2
+    dback = engine.alloc(n)
+    r = engine.inflate_batch([pg.InflateItem(ddst.ptr, res.out_len, dback.ptr, n, pg.WRAP_GZIP, 0)], mem=pg.MEM_DEVICE)[0]
+    assert r.rc == 0 and r.out_len == n and r.crc32 == 0xece3d95e and (r.flags & 3) == 3
+    assert gzip.decompress(blob) == data
+    for b in (dsrc, ddst, dback):
+        b.free()
