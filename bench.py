@@ -1,0 +1,376 @@
+#!/usr/bin/env python3
+"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+
+Workload (configs[1]): 1 GiB of makedata.c-style synthetic text (seed 1, `-b 30`, seeded with
+alice29.txt) deflated at level 6 with dynamic Huffman in 256 KiB chunks primed with the previous
+32 KiB, stitched into one gzip member with crc32; one "step" = one pass over the 1 GiB that is
+already resident in HBM.  `value` = uncompressed GB/s (CUDA events on the engine's stream, max over
+ranks); `e2e` = the same metric through the host-pointer C-ABI call (pinned host buffer in,
+compressed host buffer out, copies inside the timed region).  Level 1 deflate and the batched
+inflate of 64 KiB gzip members (configs[2]) are measured in the same run and reported under
+`extra`.
+
+N > 1 (torchrun, one rank per GPU, NCCL): every rank deflates its own 1 GiB slice of an N GiB
+stream (weak scaling), sizes are all-gathered and exclusive-scanned, the compressed pieces are
+sent to rank 0 at their scanned offsets over NCCL P2P and the per-rank CRCs are folded with
+crc32_combine (configs[3]).
+
+`--impl reference` times the reference's own software path (lib/sw_zlib.c -> system zlib through
+oracle/_ref/libnxz_ref.so when it was built, else libz directly) on the host cores.
+"""
+import argparse
+import ctypes as C
+import gzip
+import importlib.util
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import zlib
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+GIB = 1 << 30
+CHUNK = 262144
+
+
+def load_pkg():
+    spec = importlib.util.spec_from_file_location(
+        "power_gzip_b200", os.path.join(ROOT, "power-gzip_b200", "__init__.py"),
+        submodule_search_locations=[os.path.join(ROOT, "power-gzip_b200")])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["power_gzip_b200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"          # /opt/skills/guides/B200_PROFILING.md
+
+
+class ClockSampler(threading.Thread):
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = []
+        for i, name in ((4, "hw_slowdown"), (5, "hw_thermal_slowdown"), (6, "sw_thermal_slowdown"), (7, "sw_power_cap")):
+            if any(len(r) > i and r[i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def oracle_lib():
+    p = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not os.path.exists(p):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], stdout=subprocess.DEVNULL)
+    lib = C.CDLL(p)
+    lib.oracle_cpu_baseline.restype = C.c_double
+    lib.oracle_cpu_baseline.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    return lib
+
+
+def cpu_baseline(data_addr, nbytes, level, threads, mode=0):
+    """Reference software path on `threads` host cores over `nbytes` of the workload (bounded sample)."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "libnxz_ref.so")
+    kind = "reference" if os.path.exists(ref) else "port"
+    lib_path = ref if kind == "reference" else "libz.so.1"
+    os.environ["NX_GZIP_TYPE_SELECTOR"] = "1"       # libnxz: software (sw_zlib.c) path
+    os.environ.setdefault("NX_GZIP_LOGFILE", "/tmp/nx.log")
+    out = C.c_uint64()
+    secs = oracle_lib().oracle_cpu_baseline(lib_path.encode(), data_addr, nbytes, CHUNK, level, mode, threads, C.byref(out))
+    if secs <= 0 and kind == "reference":
+        kind, lib_path = "port", "libz.so.1"
+        secs = oracle_lib().oracle_cpu_baseline(lib_path.encode(), data_addr, nbytes, CHUNK, level, mode, threads, C.byref(out))
+    return secs, out.value, kind
+
+
+def gen_input(pg, log2):
+    alice = gzip.decompress(open(os.path.join(ROOT, "tests", "golden", "alice29.txt.gz"), "rb").read())
+    lib = pg.load_library()
+    cap = (1 << log2) + 16
+    hptr = C.c_void_p()
+    rc = lib.nxgpu_host_alloc(cap, C.byref(hptr))       # pinned: the e2e leg copies from here
+    if rc != 0:
+        raise RuntimeError("pinned allocation failed: " + pg.last_error())
+    seed_buf = C.create_string_buffer(alice, len(alice))
+    n = lib.nxgpu_makedata(1, log2, C.addressof(seed_buf), len(alice), hptr, cap)
+    assert n == 1 << log2, n
+    return hptr.value, n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pg = load_pkg()
+    threads = os.cpu_count() or 1
+    sample = min(GIB, 8 * 1024 * 1024 * threads)     # about 10-30 s of level-6 zlib in total
+    sample = max(CHUNK * threads, sample // CHUNK * CHUNK)
+    log2 = 30 if sample > (1 << 28) else 28
+    alice = gzip.decompress(open(os.path.join(ROOT, "tests", "golden", "alice29.txt.gz"), "rb").read())
+    data = pg.makedata(1, log2, alice)
+    buf = C.create_string_buffer(data[:sample], sample)
+    addr = C.addressof(buf)
+    per = []
+    kind = "port"
+    for i in range(args.warmup + args.steps):
+        secs, outb, kind = cpu_baseline(addr, sample, 6, threads)
+        if i >= args.warmup:
+            per.append(secs)
+    t = sum(per) / len(per)
+    val = sample / t / 1e9
+    line = {"impl": "reference", "metric": "deflate uncompressed GB/s", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "1 GiB makedata text (seed 1), deflate level 6, dynamic Huffman, 256 KiB chunks", "chunk": CHUNK, "level": 6},
+            "cpu_baseline": {"value": val, "unit": "GB/s", "cores": threads, "kind": kind,
+                             "sample": f"first {sample >> 20} MiB of the workload, compress2(level 6) per 256 KiB piece, zlib {zlib.ZLIB_RUNTIME_VERSION}"},
+            "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--log2", type=int, default=30, help="log2 of the per-GPU input size (default 1 GiB)")
+    ap.add_argument("--skip-extra", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pg = load_pkg()
+    eng = pg.Engine(local)
+    lib = eng.lib
+    hbm_peak, peak_kind = peaks()
+
+    # ---- inputs: synthetic makedata text, resident in HBM before the timed region ----
+    hsrc, n = gen_input(pg, args.log2)
+    src = torch.empty(n, dtype=torch.uint8, device="cuda")
+    eng._check(lib.nxgpu_memcpy_h2d(eng.ctx, src.data_ptr(), hsrc, n), "h2d")
+    cap = eng.deflate_bound(n, CHUNK)
+    dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    hdst = C.c_void_p()
+    lib.nxgpu_host_alloc(cap, C.byref(hdst))
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def deflate_step(level, gather_to_rank0=True):
+        """one pass of the hot path; returns (device ms, StreamResult)"""
+        eng.timer_start()
+        if world == 1:
+            res = eng.deflate_stream_device(src.data_ptr(), n, dst.data_ptr(), cap, level=level, wrap=pg.WRAP_GZIP, chunk=CHUNK)
+            return eng.timer_stop(), res, res.out_len
+        # rank r owns bytes [r*n, (r+1)*n) of the N*n stream: raw deflate of its slice, joiner unless last
+        wrap = pg.WRAP_RAW
+        res = eng.deflate_stream_device(src.data_ptr(), n, dst.data_ptr(), cap, level=level, wrap=wrap, chunk=CHUNK)
+        ms = eng.timer_stop()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        meta = torch.tensor([res.out_len, res.crc32], dtype=torch.int64, device="cuda")
+        allm = [torch.empty_like(meta) for _ in range(world)]
+        dist.all_gather(allm, meta)                                  # sizes + crcs (8 numbers)
+        sizes = [int(m[0]) for m in allm]
+        offs = [10]
+        for s_ in sizes:
+            offs.append(offs[-1] + s_)                                 # exclusive scan behind the gzip header
+        total = offs[-1] + 8
+        if rank == 0:
+            if stitched[0] is None or stitched[0].numel() < total:
+                stitched[0] = torch.empty(total + (total >> 3), dtype=torch.uint8, device="cuda")
+            out = stitched[0]
+            out[offs[0]:offs[1]].copy_(dst[:sizes[0]])
+            reqs = [dist.irecv(out[offs[r]:offs[r + 1]], src=r) for r in range(1, world)]
+            for q in reqs:
+                q.wait()
+            crc = 0
+            for r in range(world):
+                crc = eng.crc32_combine(crc, int(allm[r][1]) & 0xffffffff, n)     # lib/nx_crc.c:374
+            last_crc[0] = crc
+        else:
+            dist.send(dst[:sizes[rank]], dst=0)
+        t1.record(); t1.synchronize()
+        return ms + t0.elapsed_time(t1), res, total
+
+    stitched, last_crc = [None], [0]
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        per = []
+        for _ in range(steps):
+            per.append(fn())
+        barrier()
+        return per
+
+    # ---- headline: deflate level 6, device resident ----
+    sampler = ClockSampler(local)
+    l0 = eng.launch_count()
+    eng.kernel_time_reset()
+    for _ in range(args.warmup):
+        deflate_step(6)
+    barrier()
+    eng.kernel_time_reset()
+    l0 = eng.launch_count()
+    sampler.start()
+    per = []
+    last = None
+    for _ in range(args.steps):
+        ms, res, total = deflate_step(6)
+        per.append(ms); last = (res, total)
+    barrier()
+    sampler.stop_flag.set()
+    launches = eng.launch_count() - l0
+    kms, kn = eng.kernel_time("deflate")
+    step_ms = sum(per) / len(per)
+    if world > 1:
+        t = torch.tensor([step_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = float(t[0])
+    value = world * n / step_ms / 1e6
+    res6, total6 = last
+    comp_bytes = res6.out_len
+    k_avg_ms = kms / max(kn, 1)
+    achieved = (n + comp_bytes) / k_avg_ms / 1e6                          # algorithmic U + C bytes per launch
+    extra = {"ratio_level6": n / comp_bytes, "tokens_level6": int(res6.n_tokens), "deflate_kernel_ms": k_avg_ms,
+             "deflate_kernel_GBps_uncompressed": n / k_avg_ms / 1e6}
+
+    # ---- end to end through the host-pointer C-ABI call (rank-local) ----
+    res_h = pg.StreamResult()
+
+    def e2e_step():
+        t = time.perf_counter()
+        eng._check(lib.nxgpu_deflate_stream(eng.ctx, hsrc, n, hdst, cap, 6, pg.WRAP_GZIP, CHUNK, None, C.byref(res_h), pg.MEM_HOST), "e2e deflate")
+        return (time.perf_counter() - t) * 1e3
+    e2e_per = timed(e2e_step, max(2, min(args.steps, 3)), 1)
+    e2e_ms = sum(e2e_per) / len(e2e_per)
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t[0])
+    e2e = {"value": world * n / e2e_ms / 1e6, "unit": "GB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": int(res_h.out_len)}
+
+    cpu = None
+    if rank == 0:
+        # ---- correctness of what was just timed: zlib must decode the stitched stream ----
+        check_n = min(n, 64 << 20)
+        if world == 1:
+            blob = bytes(C.string_at(hdst.value, int(res_h.out_len)))
+            d = zlib.decompressobj(31)
+            got = d.decompress(blob, check_n)
+            want = C.string_at(hsrc, check_n)
+            assert got == want, "zlib does not reproduce the input from the GPU stream"
+            assert res_h.crc32 == res6.crc32
+        extra["verified"] = f"zlib inflate of the e2e output reproduces the first {check_n >> 20} MiB; crc32 {res6.crc32:08x}"
+
+    if not args.skip_extra:
+        # ---- level 1 ----
+        eng.kernel_time_reset()
+        p1 = timed(lambda: deflate_step(1)[0], max(2, min(args.steps, 3)), 1)
+        k1, kn1 = eng.kernel_time("deflate")
+        r1 = eng.deflate_stream_device(src.data_ptr(), n, dst.data_ptr(), cap, level=1, wrap=pg.WRAP_GZIP, chunk=CHUNK)
+        extra["deflate_level1_GBps"] = world * n / (sum(p1) / len(p1)) / 1e6
+        extra["ratio_level1"] = n / r1.out_len
+        # ---- batched inflate of independent 64 KiB gzip members (configs[2], scaled to the input) ----
+        M = 65536
+        nm = n // M
+        sample_members = min(nm, 2048)
+        hb = C.string_at(hsrc, sample_members * M)
+        blobs = [zlib.compress(hb[i * M:(i + 1) * M], 6, wbits=31) for i in range(sample_members)]
+        packed = b"".join(blobs * (nm // sample_members))
+        lens = [len(b) for b in blobs] * (nm // sample_members)
+        nm = len(lens)
+        comp = torch.empty(len(packed), dtype=torch.uint8, device="cuda")
+        pk = C.create_string_buffer(packed, len(packed))
+        eng._check(lib.nxgpu_memcpy_h2d(eng.ctx, comp.data_ptr(), C.addressof(pk), len(packed)), "h2d")
+        out = torch.empty(nm * M, dtype=torch.uint8, device="cuda")
+        items = (pg.InflateItem * nm)()
+        o = 0
+        for i in range(nm):
+            items[i] = pg.InflateItem(comp.data_ptr() + o, lens[i], out.data_ptr() + i * M, M, pg.WRAP_GZIP, 0)
+            o += lens[i]
+        ires = (pg.InflateResult * nm)()
+
+        def inflate_step():
+            eng.timer_start()
+            eng._check(lib.nxgpu_inflate_batch(eng.ctx, items, nm, ires, pg.MEM_DEVICE), "inflate")
+            return eng.timer_stop()
+        eng.kernel_time_reset()
+        pi = timed(inflate_step, max(2, min(args.steps, 3)), 1)
+        ki, kni = eng.kernel_time("inflate")
+        assert all(r.rc == 0 and r.out_len == M for r in ires), "batched inflate failed"
+        assert ires[0].crc32 == zlib.crc32(hb[:M])
+        extra["inflate_members"] = nm
+        extra["inflate_64KiB_members_GBps"] = world * nm * M / (sum(pi) / len(pi)) / 1e6
+        extra["inflate_kernel_GBps"] = nm * M / (ki / max(kni, 1)) / 1e6
+        extra["inflate_roofline_frac"] = (nm * M + len(packed)) / (ki / max(kni, 1)) / 1e6 / hbm_peak
+
+    if rank == 0:
+        threads = os.cpu_count() or 1
+        sample = min(n, max(CHUNK * threads, 4 * 1024 * 1024 * threads))
+        secs, outb, kind = cpu_baseline(hsrc, sample, 6, threads)
+        cpu = {"value": sample / secs / 1e9, "unit": "GB/s", "cores": threads, "kind": kind,
+               "sample": f"first {sample >> 20} MiB of the workload, compress2(level 6) per 256 KiB piece on {threads} threads, zlib {zlib.ZLIB_RUNTIME_VERSION}",
+               "ratio": sample / max(outb, 1)}
+        line = {
+            "metric": "deflate uncompressed GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "1 GiB makedata text (seed 1) per GPU, deflate level 6, dynamic Huffman, 256 KiB chunks primed with 32 KiB, one gzip member + crc32",
+                       "bytes_per_gpu": n, "chunk": CHUNK, "level": 6, "l2": "inputs (1 GiB) larger than the 126 MB L2; no flush needed",
+                       "parallelism": f"chunk-range x{world}" if world > 1 else "1 GPU"},
+            "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": peak_kind, "kernel": "deflate_kernel",
+                         "note": "algorithmic bytes = U + C per launch (SURVEY.md §8d); LZ77 search is latency/issue bound, not HBM bound"},
+            "cpu_baseline": cpu, "clocks": sampler.summary(), "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -19,6 +19,9 @@
 // Tensor cores are not used: nothing here is a dense contraction.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
 #include "common.cuh"
 #include "../../include/nxgpu.h"
 
@@ -27,24 +30,30 @@ namespace nxgpu {
 namespace {
 
 constexpr int kThreads = 1024;
-constexpr int kStep = 1024;               // positions matched per CTA step
+constexpr int kWin = 30;                  // matcher warps = windows of 32 positions per step
+constexpr int kStep = kWin * 32;          // positions matched per CTA step
 constexpr uint32_t kRingMask = 0xFFFFu;   // 64 KiB data ring / 64 Ki-entry chain ring
-constexpr int kHashBits = 13;
+constexpr int kHashBits = 12;
 constexpr int kHashSize = 1 << kHashBits;
-constexpr uint32_t kMMask = 4095u;        // per-position match ring (4 steps)
-constexpr uint32_t kNoneAge = 40000u;     // "empty" head entries are kept at an age in (32768, 65536)
+constexpr uint32_t kNone = 0xFFFFFFFFu;    // empty hash head
 constexpr int kStageWords = 2048;
 
 struct __align__(16) Smem {
 	uint32_t ring32[16384];           // 64 KiB input ring (position & 0xFFFF)
 	uint16_t prev[65536];             // 128 KiB: distance to the previous position with the same hash
-	uint16_t head[kHashSize];         // 16 KiB: most recent position (low 16 bits) per hash
-	uint32_t M[4096];                 // 16 KiB: best match per position, len<<16 | dist
+	uint32_t head[kHashSize];         // 16 KiB: most recent position per hash (absolute, kNone = empty)
+	// matcher -> parser hand-off for the current step: per position, where the token stream leaves
+	// the window (low 10 bits) and how many tokens it emits on the way (high 6 bits)
+	uint16_t JC[kStep];
+	volatile uint32_t win_flag[32];   // == step + 1 once the window's JC entries are written
+	// parser -> matcher: per window the entry lane (>= 32: jumped over) and first token index
+	volatile uint32_t ent[2][32];
+	volatile uint32_t off[2][32];
 	uint32_t ll_freq[288];
 	uint32_t d_freq[32];
-	int grp_ctr;
+	int grp_ctr[2];
 	uint32_t n_tok;
-	uint32_t misc[14];
+	uint32_t misc[13];
 };
 static_assert(sizeof(Smem) <= 232448, "shared memory budget");
 
@@ -73,6 +82,11 @@ struct HuffScratch {                      // lives in Smem::prev
 static_assert(sizeof(HuffScratch) <= 65536 * 2, "huff scratch");
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// optional cycle accounting per CTA (NXGPU_DEBUG_CYCLES=1): [0] build, [1] parse, [2] match (warp 2),
+// [3] barrier wait (warp 2), [4] steps, [5] huffman+pack, [6] whole job
+__device__ unsigned long long *g_dbg = nullptr;
+#define DBG_ADD(slot, v) do { if (g_dbg && lane_id() == 0) atomicAdd(&g_dbg[blockIdx.x * 8 + (slot)], (unsigned long long)(v)); } while (0)
 
 __device__ __forceinline__ uint32_t load4(const uint32_t *ring32, uint32_t pos)
 {
@@ -106,39 +120,38 @@ __device__ void stage_input(Smem &S, const uint8_t *gbase, uint32_t lo, uint32_t
 __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;\n" ::); }
 
 // ---- warp 0: insert positions [lo, hi) into the hash chains, in stream order ----
-__device__ void build_chains(Smem &S, uint32_t lo, uint32_t hi, uint32_t &next_sweep)
+// One shared-memory atomic exchange per position: the returned value is the previous head, and
+// when several lanes of the warp hit the same bucket the hardware applies them one after the
+// other, so each lane receives the position of the lane applied just before it.  If that order
+// was ascending (checked below) the links are exactly those of a sequential insert; otherwise
+// the warp repairs the bucket with match.any (exact, just slower).
+__device__ void build_chains(Smem &S, uint32_t lo, uint32_t hi)
 {
 	const uint32_t lane = lane_id();
 	for (uint32_t p0 = lo; p0 < hi; p0 += 32) {
-		if (p0 >= next_sweep) {
-			// entries older than the window are parked at a fixed "empty" age so u16 positions never alias
-			for (uint32_t i = lane; i < kHashSize; i += 32) {
-				uint32_t age = (p0 - S.head[i]) & kRingMask;
-				if (age > kWindow)
-					S.head[i] = (uint16_t)(p0 - kNoneAge);
-			}
-			next_sweep += 16384;
-			__syncwarp();
-		}
 		const uint32_t pos = p0 + lane;
 		const bool valid = pos < hi;
 		const uint32_t h = hash4(load4(S.ring32, pos));
-		const uint32_t key = valid ? h : (0x80000000u | lane);
-		const uint32_t grp = __match_any_sync(0xffffffffu, key);
-		const uint32_t lower = grp & ((1u << lane) - 1);
-		if (valid) {
-			uint32_t d;
-			if (lower) {
-				d = lane - (31 - __clz(lower));
-			} else {
-				uint32_t age = (pos - S.head[h]) & kRingMask;
-				d = (age != 0 && age <= (uint32_t)kWindow) ? age : 0;
-			}
-			S.prev[pos & kRingMask] = (uint16_t)d;
+		uint32_t old = kNone;
+		if (valid)
+			old = atomicExch(&S.head[h], pos);
+		const bool same_iter = valid && old != kNone && old >= p0;
+		if (__ballot_sync(0xffffffffu, same_iter && old > pos)) {
+			// out-of-order application: rebuild this iteration's links exactly
+			const uint32_t key = valid ? h : (0x80000000u | lane);
+			const uint32_t grp = __match_any_sync(0xffffffffu, key);
+			const uint32_t outside = __ballot_sync(0xffffffffu, valid && !same_iter);
+			const int src = __ffs(grp & outside) - 1;            // the lane that saw the pre-iteration head
+			const uint32_t pre = __shfl_sync(0xffffffffu, old, src < 0 ? 0 : src);
+			const uint32_t lower = grp & ((1u << lane) - 1);
+			old = lower ? p0 + (31 - __clz(lower)) : (src < 0 ? kNone : pre);
+			if (valid && (grp >> lane) == 1u)
+				S.head[h] = pos;
 		}
-		__syncwarp();
-		if (valid && (grp >> lane) == 1u)       // last lane of its hash group
-			S.head[h] = (uint16_t)pos;
+		if (valid) {
+			const uint32_t d = pos - old;
+			S.prev[pos & kRingMask] = (uint16_t)((old != kNone && d <= (uint32_t)kWindow) ? d : 0);
+		}
 		__syncwarp();
 	}
 }
@@ -161,108 +174,222 @@ __device__ __forceinline__ uint32_t match_length(const uint32_t *ring32, uint32_
 	return l < maxl ? l : maxl;
 }
 
-// ---- all warps: best match for every position of [step_lo, step_hi) ----
-__device__ void match_step(Smem &S, uint32_t step_lo, uint32_t step_hi, uint32_t PE, uint32_t valid_lo,
-			   int depth, int nice)
+// ---- matcher warps: best match for each of the 32 positions of one window ----
+// Phase 1 (one lane per position): walk the hash chain, comparing at most kCap bytes per
+// candidate — a candidate that reaches kCap ends the first pass, like zlib's nice_length.
+// Phase 2 (whole warp): consecutive positions whose capped match has the SAME distance lie
+// inside one long repeat; only the first of them is extended (32 lanes x 4 bytes per pass) and
+// the followers derive their length from it.  Without this every position inside a 258-byte
+// repeat re-compares up to 258 bytes on a single lane.
+// Phase 3: positions inside such a repeat keep walking their chain, but only a candidate that
+// also matches at offset `bl` (beyond the inherited length) is compared in full.
+constexpr uint32_t kCap = 32;
+
+// bytes [0, capl) of p and q, capl <= 32; loads are issued in two independent batches so a
+// compare costs about two shared-memory round trips instead of one per word
+__device__ __forceinline__ uint32_t match_len_cap(const uint32_t *ring32, uint32_t p, uint32_t q, uint32_t capl)
+{
+	const uint32_t pa = p >> 2, qa = q >> 2;
+	const uint32_t ps = (p & 3) * 8, qs = (q & 3) * 8;
+	uint32_t pw[5], qw[5];
+#pragma unroll
+	for (int i = 0; i < 5; i++) {
+		pw[i] = ring32[(pa + i) & 0x3FFF];
+		qw[i] = ring32[(qa + i) & 0x3FFF];
+	}
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const uint32_t x = __funnelshift_r(pw[i], pw[i + 1], ps) ^ __funnelshift_r(qw[i], qw[i + 1], qs);
+		if (x)
+			return min(capl, 4u * i + ((uint32_t)(__ffs(x) - 1) >> 3));
+	}
+	if (capl <= 16)
+		return capl;
+	uint32_t pv[5], qv[5];
+	pv[0] = pw[4]; qv[0] = qw[4];
+#pragma unroll
+	for (int i = 1; i < 5; i++) {
+		pv[i] = ring32[(pa + 4 + i) & 0x3FFF];
+		qv[i] = ring32[(qa + 4 + i) & 0x3FFF];
+	}
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const uint32_t x = __funnelshift_r(pv[i], pv[i + 1], ps) ^ __funnelshift_r(qv[i], qv[i + 1], qs);
+		if (x)
+			return min(capl, 16u + 4u * i + ((uint32_t)(__ffs(x) - 1) >> 3));
+	}
+	return capl;
+}
+
+struct WinResult {       // what a matcher lane keeps in registers until its window is emitted
+	uint32_t token;      // literal byte or tok_match(len, dist)
+	uint32_t reach;      // positions of the window visited when the stream enters at this lane
+};
+
+__device__ WinResult match_window(Smem &S, uint32_t g, uint32_t p0, uint32_t step_hi, uint32_t PE, uint32_t valid_lo,
+				  uint32_t step_seq, int depth, int nice, int lazy)
 {
 	const uint32_t lane = lane_id();
-	for (;;) {
-		int g = 0;
-		if (lane == 0)
-			g = atomicAdd(&S.grp_ctr, 1);
-		g = __shfl_sync(0xffffffffu, g, 0);
-		const uint32_t p0 = step_lo + (uint32_t)g * 32;
-		if (p0 >= step_hi)
-			break;
-		const uint32_t pos = p0 + lane;
-		if (pos >= step_hi)
-			continue;
-		uint32_t res = 0;
-		const uint32_t maxl = min((uint32_t)kMaxMatch, PE - pos);
-		if (maxl >= (uint32_t)kMinMatch) {
-			const uint32_t maxdist = min((uint32_t)kWindow, pos - valid_lo);
-			uint32_t bl = kMinMatch - 1, bd = 0, acc = 0, q = pos;
-			uint32_t endb = ring_byte(S.ring32, pos + bl);
-			for (int hop = 0; hop < depth; hop++) {
-				uint32_t d = S.prev[q & kRingMask];
-				if (d == 0)
-					break;
-				acc += d;
-				if (acc > maxdist)
-					break;
-				q = pos - acc;
-				if (ring_byte(S.ring32, q + bl) != endb)
-					continue;
-				uint32_t len = match_length(S.ring32, pos, q, maxl);
-				if (len > bl) {
-					bl = len; bd = acc;
-					if (len >= (uint32_t)nice || len >= maxl)
-						break;
-					endb = ring_byte(S.ring32, pos + bl);
-				}
+	const uint32_t nice_eff = min((uint32_t)nice, kCap);
+	const uint32_t pos = p0 + lane;
+	const bool live = pos < step_hi;
+	const uint32_t maxl = live ? min((uint32_t)kMaxMatch, PE - pos) : 0;
+	uint32_t bl = kMinMatch - 1, bd = 0;
+	uint32_t acc = 0;
+	int hop = 0;
+	const uint32_t maxdist = min((uint32_t)kWindow, pos - valid_lo);
+	uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;   // next chain link (prefetched)
+	if (d) {
+		const uint32_t capl = min(maxl, kCap);
+		// filter: the 4 bytes ending at offset bl must match (for bl == 3 that is the 4-gram itself,
+		// which weeds out hash collisions; later it is the tail that a longer match needs)
+		uint32_t endw = load4(S.ring32, pos + bl - 3);
+		for (; hop < depth; hop++) {
+			if (d == 0) { hop = depth; break; }
+			acc += d;
+			if (acc > maxdist) { hop = depth; d = 0; break; }
+			const uint32_t q = pos - acc;
+			d = S.prev[q & kRingMask];                         // independent of the check below
+			if (load4(S.ring32, q + bl - 3) != endw)
+				continue;
+			const uint32_t len = match_len_cap(S.ring32, pos, q, capl);
+			if (len > bl) {
+				bl = len; bd = acc;
+				if (len >= nice_eff || len >= capl) { hop++; break; }
+				endw = load4(S.ring32, pos + bl - 3);
 			}
-			if (bl >= (uint32_t)kMinMatch)
-				res = (bl << 16) | bd;
 		}
-		S.M[pos & kMMask] = res;
+	}
+	// ---- phase 2 ----
+	const bool capped = (bl == kCap) && (maxl > kCap);
+	{
+		const uint32_t d_prev = __shfl_up_sync(0xffffffffu, bd, 1);
+		const bool c_prev = __shfl_up_sync(0xffffffffu, (int)capped, 1) != 0 && lane > 0;
+		const bool head = capped && !(c_prev && d_prev == bd);
+		const uint32_t heads_all = __ballot_sync(0xffffffffu, head);
+		uint32_t heads = heads_all;
+		const uint32_t myhead = capped ? 31 - __clz(heads_all & ((2u << lane) - 1)) : 32;
+		while (heads) {
+			const int h = __ffs(heads) - 1;
+			heads &= heads - 1;
+			const uint32_t hp = p0 + h;
+			const uint32_t hd = __shfl_sync(0xffffffffu, bd, h);
+			const uint32_t hmax = min((uint32_t)kMaxMatch + 31, PE - hp);
+			uint32_t L = kCap;
+			for (uint32_t base = kCap; base < hmax; base += 128) {
+				const uint32_t off = base + 4 * lane;
+				const uint32_t x = load4(S.ring32, hp + off) ^ load4(S.ring32, hp - hd + off);
+				uint32_t e = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4;
+				const uint32_t room = off < hmax ? min(4u, hmax - off) : 0;
+				e = min(e, room);
+				const uint32_t stop = __ballot_sync(0xffffffffu, e < 4);
+				if (stop == 0) { L = base + 128; continue; }
+				const int f = __ffs(stop) - 1;
+				L = base + 4 * f + __shfl_sync(0xffffffffu, e, f);
+				break;
+			}
+			if (myhead == (uint32_t)h)
+				bl = min(maxl, L - (lane - h));
+		}
+	}
+	// ---- phase 3 ----
+	if (capped && bl < maxl && bl < (uint32_t)nice) {
+		uint32_t endb = ring_byte(S.ring32, pos + bl);
+		for (; hop < depth; hop++) {
+			if (d == 0)
+				break;
+			acc += d;
+			if (acc > maxdist)
+				break;
+			const uint32_t q = pos - acc;
+			d = S.prev[q & kRingMask];
+			if (ring_byte(S.ring32, q + bl) != endb)
+				continue;
+			const uint32_t len = match_length(S.ring32, pos, q, maxl);
+			if (len > bl) {
+				bl = len; bd = acc;
+				if (len >= (uint32_t)nice || len >= maxl)
+					break;
+				endb = ring_byte(S.ring32, pos + bl);
+			}
+		}
+	}
+
+	// ---- greedy / lazy choice per position, then reach sets by pointer jumping ----
+	const uint32_t len = (bl >= (uint32_t)kMinMatch) ? bl : 0;
+	uint32_t nlen = __shfl_down_sync(0xffffffffu, len, 1);
+	if (lane == 31)
+		nlen = 0;                                  // no look-ahead across windows
+	bool take = len != 0;
+	if (take && lazy && len < (uint32_t)lazy && nlen > len)
+		take = false;
+	uint32_t J = live ? lane + (take ? len : 1) : 64;       // next token start relative to p0 (>= 32: leaves the window)
+	uint32_t Rl = live ? (1u << lane) : 0;
+#pragma unroll
+	for (int k = 0; k < 5; k++) {
+		const uint32_t tJ = __shfl_sync(0xffffffffu, J, J & 31);
+		const uint32_t tR = __shfl_sync(0xffffffffu, Rl, J & 31);
+		if (J < 32) { Rl |= tR; J = tJ; }
+	}
+	// the parser warp only needs, per possible entry lane, the exit and the token count
+	S.JC[g * 32 + lane] = (uint16_t)(J | ((uint32_t)__popc(Rl) << 10));
+	__threadfence_block();
+	__syncwarp();
+	if (lane == 0)
+		S.win_flag[g] = step_seq;
+	WinResult r;
+	r.token = take ? tok_match(len, bd) : ring_byte(S.ring32, pos);
+	r.reach = Rl;
+	return r;
+}
+
+// a matcher warp writes out the tokens of the window it matched in the PREVIOUS step: by now the
+// parser has published where the stream entered that window (lane, or >= 32 if it was jumped over)
+// and the index of its first token
+__device__ __forceinline__ void emit_window(Smem &S, const WinResult &r, uint32_t entry, uint32_t off, uint32_t *tok)
+{
+	if (entry >= 32)
+		return;
+	const uint32_t lane = lane_id();
+	const uint32_t R = __shfl_sync(0xffffffffu, r.reach, entry);
+	if ((R >> lane) & 1) {
+		const uint32_t t = r.token;
+		if (tok_is_match(t)) {
+			uint32_t lc, le, lx, dc, de, dx;
+			len_code(tok_len(t), lc, le, lx);
+			dist_code(tok_dist(t), dc, de, dx);
+			atomicAdd(&S.ll_freq[257 + lc], 1u);
+			atomicAdd(&S.d_freq[dc], 1u);
+		} else {
+			atomicAdd(&S.ll_freq[t], 1u);
+		}
+		tok[off + __popc(R & ((1u << lane) - 1))] = t;
 	}
 }
 
-// ---- warp 1: positions [lo, hi) -> tokens; `cur` is the next token start, carried across calls.
-//      M[pos+1] must be valid for pos+1 < avail. ----
-__device__ void parse_range(Smem &S, uint32_t lo, uint32_t hi, uint32_t avail, uint32_t &cur, uint32_t &ntok,
-			    uint32_t *tok, int lazy)
+// ---- warp 1: follow the token stream through the windows of one step as the matchers finish them;
+//      publishes per window the entry lane and the index of its first token ----
+__device__ void parse_step(Smem &S, uint32_t step_lo, uint32_t step_hi, uint32_t step_seq, uint32_t &cur, uint32_t &ntok)
 {
-	const uint32_t lane = lane_id();
-	const uint32_t lt = (1u << lane) - 1;
-	for (uint32_t w = lo; w < hi; w += 32) {
-		if (cur >= w + 32 || cur >= hi)
-			continue;
-		const uint32_t pos = w + lane;
-		const bool in = pos < hi;
-		const uint32_t m = (pos < avail) ? S.M[pos & kMMask] : 0;
-		uint32_t nm = __shfl_down_sync(0xffffffffu, m, 1);
-		if (lane == 31)
-			nm = (pos + 1 < avail) ? S.M[(pos + 1) & kMMask] : 0;
-		const uint32_t len = m >> 16, nlen = nm >> 16;
-		bool take = len >= (uint32_t)kMinMatch;
-		if (take && lazy && len < (uint32_t)lazy && nlen > len)
-			take = false;
-		const uint32_t nxt = lane + (take ? len : 1);     // relative to w, may be >= 32
-		// reachability from cur by pointer jumping: after round k, R holds next^j(cur) for j < 2^(k+1)
-		uint32_t R = 1u << (cur - w);
-		uint32_t J = in ? nxt : 64;
-		if (!in)
-			J = 64;
-#pragma unroll
-		for (int k = 0; k < 5; k++) {
-			uint32_t c = (((R >> lane) & 1) && J < 32) ? (1u << J) : 0;
-			R |= __reduce_or_sync(0xffffffffu, c);
-			uint32_t Jn = __shfl_sync(0xffffffffu, J, J & 31);
-			J = (J < 32) ? Jn : J;
+	const uint32_t nwin = (step_hi - step_lo + 31) / 32;
+	const uint32_t par = step_seq & 1;
+	for (uint32_t g = 0; g < nwin; g++) {
+		const uint32_t p0 = step_lo + g * 32;
+		while (S.win_flag[g] != step_seq)
+			;
+		__threadfence_block();
+		uint32_t entry = 64;
+		const uint32_t off = ntok;
+		if (cur < p0 + 32 && cur < step_hi) {
+			entry = cur - p0;
+			const uint32_t jc = S.JC[g * 32 + entry];
+			cur = p0 + (jc & 1023);
+			ntok += jc >> 10;
 		}
-		// drop lanes beyond hi (they are not in this range)
-		if (hi - w < 32)
-			R &= (1u << (hi - w)) - 1;
-		const uint32_t last = 31 - __clz(R);
-		cur = w + __shfl_sync(0xffffffffu, nxt, last);
-		if ((R >> lane) & 1) {
-			uint32_t t;
-			if (take) {
-				const uint32_t dist = m & 0xFFFF;
-				t = tok_match(len, dist);
-				uint32_t lc, le, lx, dc, de, dx;
-				len_code(len, lc, le, lx);
-				dist_code(dist, dc, de, dx);
-				atomicAdd(&S.ll_freq[257 + lc], 1u);
-				atomicAdd(&S.d_freq[dc], 1u);
-			} else {
-				t = ring_byte(S.ring32, pos);
-				atomicAdd(&S.ll_freq[t], 1u);
-			}
-			tok[ntok + __popc(R & lt)] = t;
+		if (lane_id() == 0) {
+			S.ent[par][g] = entry;
+			S.off[par][g] = off;
 		}
-		ntok += __popc(R);
 	}
 }
 
@@ -662,6 +789,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 	uint32_t *tok = tok_scratch + (size_t)blockIdx.x * tok_stride;
 
 	for (uint32_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+		const long long tjob0 = clock64();
 		const DeflateJob J = jobs[job];
 		const uintptr_t first = reinterpret_cast<uintptr_t>(J.src) - J.hist_len;
 		const uint8_t *gbase = reinterpret_cast<const uint8_t *>(first & ~(uintptr_t)15);
@@ -674,54 +802,65 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 
 		// ---- init ----
 		for (int i = threadIdx.x; i < kHashSize; i += kThreads)
-			S.head[i] = (uint16_t)(P0 - kNoneAge);
+			S.head[i] = kNone;
 		for (int i = threadIdx.x; i < 288; i += kThreads)
 			S.ll_freq[i] = 0;
 		if (threadIdx.x < 32)
 			S.d_freq[threadIdx.x] = 0;
-		if (threadIdx.x == 0) { S.grp_ctr = 0; S.n_tok = 0; }
+		if (threadIdx.x < 32)
+			S.win_flag[threadIdx.x] = 0;
+		if (threadIdx.x == 0) { S.grp_ctr[0] = 0; S.grp_ctr[1] = 0; S.n_tok = 0; }
 		uint32_t DF = min(PEa, (PS + 3 * kStep + 15) & ~15u);   // data staged through here
 		stage_input(S, gbase, 0, DF, P0, PE);
 		stage_wait();
 		__syncthreads();
-		uint32_t BF = P0, next_sweep = P0 + 16384;               // warp-0 state
-		uint32_t cur = PS, ntok = 0, parse_lo = PS;              // warp-1 state
+		uint32_t BF = P0;                                        // warp-0 state: chains built up to here
+		uint32_t cur = PS, ntok = 0;                             // warp-1 state: next token start, tokens so far
+		WinResult held = { 0, 0 };                               // matcher state: last step's window, not yet emitted
+		bool have_held = false;
+		const uint32_t g = warp - 2;                             // matcher warps 2..31 own window g of every step
 		if (warp == 0) {
 			uint32_t hi = min(PS + kStep, hash_hi);
-			if (hi > BF) { build_chains(S, BF, hi, next_sweep); BF = hi; }
+			if (hi > BF) { build_chains(S, BF, hi); BF = hi; }
 		}
 		__syncthreads();
 
-		// ---- LZ77 pipeline: build(s+1) | match(s) | parse(s-1) | stage(s+3) ----
-		for (uint32_t s = 0; s <= nsteps; s++) {
+		// ---- LZ77 pipeline: warp 0 build(s+1) | warp 1 parse(s) | warps 2.. emit(s-1), match(s) | stage(s+3) ----
+		for (uint32_t s = 0; s < nsteps; s++) {
 			const uint32_t step_lo = PS + s * kStep;
 			const uint32_t step_hi = min(step_lo + kStep, PE);
 			const uint32_t want = min(PEa, (PS + (s + 4) * kStep + 15) & ~15u);
 			if (want > DF) { stage_input(S, gbase, DF, want, P0, PE); DF = want; }
+			long long tc1 = clock64();
 			if (warp == 0) {
 				uint32_t hi = min(PS + (s + 2) * kStep, hash_hi);
-				if (hi > BF) { build_chains(S, BF, hi, next_sweep); BF = hi; }
-			} else if (warp == 1 && s > 0) {
-				const bool last = (s == nsteps);
-				const uint32_t prev_hi = min(PS + s * kStep, PE);
-				const uint32_t hi = last ? PE : prev_hi - 1;
-				const uint32_t avail = last ? PE : prev_hi;
-				if (hi > parse_lo) { parse_range(S, parse_lo, hi, avail, cur, ntok, tok, lazy); parse_lo = hi; }
+				if (hi > BF) { build_chains(S, BF, hi); BF = hi; }
+				DBG_ADD(0, clock64() - tc1);
+			} else if (warp == 1) {
+				parse_step(S, step_lo, step_hi, s + 1, cur, ntok);
+				DBG_ADD(1, clock64() - tc1);
+			} else {
+				if (have_held)
+					emit_window(S, held, S.ent[s & 1][g], S.off[s & 1][g], tok);
+				const uint32_t p0 = step_lo + g * 32;
+				have_held = p0 < step_hi;
+				if (have_held)
+					held = match_window(S, g, p0, step_hi, PE, P0, s + 1, depth, nice, lazy);
 			}
-			if (s < nsteps)
-				match_step(S, step_lo, step_hi, PE, P0, depth, nice);
+			long long tc2 = clock64();
 			stage_wait();
 			__syncthreads();
-			if (threadIdx.x == 0)
-				S.grp_ctr = 0;
-			__syncthreads();
+			if (warp == 2) { DBG_ADD(2, tc2 - tc1); DBG_ADD(3, clock64() - tc2); DBG_ADD(4, 1); }
 		}
+		if (warp >= 2 && have_held)
+			emit_window(S, held, S.ent[nsteps & 1][g], S.off[nsteps & 1][g], tok);
 		if (threadIdx.x == 32)
 			S.n_tok = ntok;
 		if (threadIdx.x == 0)
 			S.ll_freq[256] = 1;                               // EOB
 		__syncthreads();
 		ntok = S.n_tok;
+		const long long thuf0 = clock64();
 
 		// ---- Huffman tables, block type decision ----
 		const bool is_final = (J.flags & NXGPU_F_FINAL) != 0;
@@ -856,6 +995,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 					J.out[P.words_out * 4 + b] = (uint8_t)(v >> (8 * b));
 			}
 		}
+		if (warp == 2) { DBG_ADD(5, clock64() - thuf0); DBG_ADD(6, clock64() - tjob0); }
 		if (threadIdx.x == 0) {
 			DeflateOut o = {};
 			o.rc = 0;
@@ -884,8 +1024,28 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 		configured = true;
 	}
 	const LevelParams lp = level_params(level);
+	static const bool dbg = getenv("NXGPU_DEBUG_CYCLES") != nullptr;
+	unsigned long long *d_dbg = nullptr;
+	if (dbg) {
+		cudaMalloc(&d_dbg, (size_t)grid * 64);
+		cudaMemsetAsync(d_dbg, 0, (size_t)grid * 64, s);
+		cudaMemcpyToSymbolAsync(g_dbg, &d_dbg, sizeof(d_dbg), 0, cudaMemcpyHostToDevice, s);
+	}
 	deflate_kernel<<<grid, kThreads, sizeof(Smem), s>>>(jobs, outs, n_jobs, lp.depth, lp.lazy, lp.nice, tok_scratch, tok_stride);
-	return cudaGetLastError();
+	cudaError_t e = cudaGetLastError();
+	if (dbg) {
+		std::vector<unsigned long long> h((size_t)grid * 8);
+		cudaStreamSynchronize(s);
+		cudaMemcpy(h.data(), d_dbg, (size_t)grid * 64, cudaMemcpyDeviceToHost);
+		unsigned long long t[8] = { 0 };
+		for (int b = 0; b < grid; b++) for (int k = 0; k < 8; k++) t[k] += h[(size_t)b * 8 + k];
+		const double st = t[4] ? (double)t[4] : 1.0;
+		fprintf(stderr, "[nxgpu cycles/step] level %d: build %.0f parse %.0f match(w2) %.0f barrier-wait(w2) %.0f | per job: huff+pack %.0f total %.0f (steps/job %.1f)\n",
+			level, t[0] / st, t[1] / st, t[2] / st, t[3] / st, (double)t[5] / n_jobs, (double)t[6] / n_jobs, st / n_jobs);
+		d_dbg = nullptr;
+		cudaMemcpyToSymbol(g_dbg, &d_dbg, sizeof(d_dbg));
+	}
+	return e;
 }
 
 } // namespace nxgpu
