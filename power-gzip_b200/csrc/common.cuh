@@ -7,7 +7,7 @@ namespace nxgpu {
 
 constexpr int kNumSMs = 148;             // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 constexpr int kWindow = 32768;           // RFC 1951 maximum match distance
-constexpr int kMinMatch = 4;             // shortest match the LZ77 stage emits
+constexpr int kMinMatch = 5;             // shortest match the LZ77 stage emits: the chains hash 5 bytes
 constexpr int kMaxMatch = 258;
 
 // LZ77 token, one u32: literal = byte value; match = 1<<31 | (len-3)<<15 | (dist-1)
@@ -95,17 +95,17 @@ struct CksumJob {
 struct LevelParams { int depth; int lazy; int nice; };
 __host__ __device__ inline LevelParams level_params(int level)
 {
-	switch (level) {
-	case 1: return { 4, 0, 32 };
-	case 2: return { 6, 0, 64 };
-	case 3: return { 8, 0, 128 };
-	case 4: return { 12, 16, 128 };
-	case 5: return { 20, 32, 258 };
-	case 6: return { 32, 32, 258 };
-	case 7: return { 48, 64, 258 };
-	case 8: return { 96, 258, 258 };
-	case 9: return { 200, 258, 258 };
-	default: return { 32, 32, 258 };
+	switch (level) {          // chain depth (5-byte hash chains), lazy threshold (0 = greedy), nice length
+	case 1: return { 2, 0, 32 };
+	case 2: return { 3, 0, 64 };
+	case 3: return { 4, 0, 128 };
+	case 4: return { 4, 16, 128 };
+	case 5: return { 6, 32, 258 };
+	case 6: return { 8, 32, 258 };
+	case 7: return { 16, 64, 258 };
+	case 8: return { 32, 258, 258 };
+	case 9: return { 64, 258, 258 };
+	default: return { 8, 32, 258 };
 	}
 }
 
@@ -114,6 +114,7 @@ void set_error(const char *fmt, ...);
 
 // kernel launchers (defined in the .cu files)
 size_t deflate_smem_bytes();
+size_t deflate_scratch_words(uint32_t tok_stride);   // per-CTA token scratch (u32 words)
 cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_jobs, int level,
 			   uint32_t *tok_scratch, uint32_t tok_stride, int grid, cudaStream_t s);
 cudaError_t launch_inflate(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s);

@@ -30,30 +30,27 @@ namespace nxgpu {
 namespace {
 
 constexpr int kThreads = 1024;
-constexpr int kWin = 30;                  // matcher warps = windows of 32 positions per step
-constexpr int kStep = kWin * 32;          // positions matched per CTA step
 constexpr uint32_t kRingMask = 0xFFFFu;   // 64 KiB data ring / 64 Ki-entry chain ring
-constexpr int kHashBits = 12;
+constexpr int kHashBits = 13;
 constexpr int kHashSize = 1 << kHashBits;
 constexpr uint32_t kNone = 0xFFFFFFFFu;    // empty hash head
 constexpr int kStageWords = 2048;
+constexpr uint32_t kSub = 512;            // bytes per sub-block (one parser warp at a time)
+constexpr uint32_t kBlk = 4096;           // bytes per TMA staging block
+constexpr int kSlots = 4;                 // staging mbarriers (block b uses slot b % kSlots)
+constexpr int kParsers = kThreads / 32 - 1;   // warps 1..31 parse, warp 0 produces
 
 struct __align__(16) Smem {
 	uint32_t ring32[16384];           // 64 KiB input ring (position & 0xFFFF)
 	uint16_t prev[65536];             // 128 KiB: distance to the previous position with the same hash
-	uint32_t head[kHashSize];         // 16 KiB: most recent position per hash (absolute, kNone = empty)
-	// matcher -> parser hand-off for the current step: per position, where the token stream leaves
-	// the window (low 10 bits) and how many tokens it emits on the way (high 6 bits)
-	uint16_t JC[kStep];
-	volatile uint32_t win_flag[32];   // == step + 1 once the window's JC entries are written
-	// parser -> matcher: per window the entry lane (>= 32: jumped over) and first token index
-	volatile uint32_t ent[2][32];
-	volatile uint32_t off[2][32];
+	uint32_t head[kHashSize];         // 32 KiB: most recent position per hash (kNone = empty)
+	uint64_t mbar[kSlots];            // TMA completion barriers of the staging blocks
+	volatile uint32_t parse_pos[32];  // per parser warp: first position of the sub-block in flight
+	volatile uint32_t built;          // chains exist (and data is staged) for every position below this
 	uint32_t ll_freq[288];
 	uint32_t d_freq[32];
-	int grp_ctr[2];
 	uint32_t n_tok;
-	uint32_t misc[13];
+	uint32_t misc[8];
 };
 static_assert(sizeof(Smem) <= 232448, "shared memory budget");
 
@@ -83,8 +80,9 @@ static_assert(sizeof(HuffScratch) <= 65536 * 2, "huff scratch");
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
-// optional cycle accounting per CTA (NXGPU_DEBUG_CYCLES=1): [0] build, [1] parse, [2] match (warp 2),
-// [3] barrier wait (warp 2), [4] steps, [5] huffman+pack, [6] whole job
+// optional cycle accounting per CTA (NXGPU_DEBUG_CYCLES=1): [0] chain build, [1] producer waits for data,
+// [2] producer waits for ring space, [3] parser busy (warp 1), [4] parser waits for chains (warp 1),
+// [5] huffman+pack, [6] whole job, [7] windows (warp 1)
 __device__ unsigned long long *g_dbg = nullptr;
 #define DBG_ADD(slot, v) do { if (g_dbg && lane_id() == 0) atomicAdd(&g_dbg[blockIdx.x * 8 + (slot)], (unsigned long long)(v)); } while (0)
 
@@ -93,69 +91,144 @@ __device__ __forceinline__ uint32_t load4(const uint32_t *ring32, uint32_t pos)
 	uint32_t a = (pos >> 2) & 0x3FFF, b = (a + 1) & 0x3FFF;
 	return __funnelshift_r(ring32[a], ring32[b], (pos & 3) * 8);
 }
-__device__ __forceinline__ uint32_t hash4(uint32_t v) { return (v * 0x9E3779B1u) >> (32 - kHashBits); }
+// hash of the 5 bytes at pos (the chains only ever propose matches of 5 or more bytes)
+__device__ __forceinline__ uint32_t hash5(const uint32_t *ring32, uint32_t pos)
+{
+	const uint32_t a = (pos >> 2) & 0x3FFF;
+	const uint32_t w0 = ring32[a], w1 = ring32[(a + 1) & 0x3FFF], w2 = ring32[(a + 2) & 0x3FFF];
+	const uint32_t sh = (pos & 3) * 8;
+	const uint32_t lo = __funnelshift_r(w0, w1, sh);
+	const uint32_t b4 = __funnelshift_r(w1, w2, sh) & 0xffu;
+	return ((lo * 0x9E3779B1u) ^ (b4 * 0x85EBCA6Bu + (lo >> 15))) * 0x2545F491u >> (32 - kHashBits);
+}
 __device__ __forceinline__ uint32_t ring_byte(const uint32_t *ring32, uint32_t pos)
 {
 	return reinterpret_cast<const uint8_t *>(ring32)[pos & kRingMask];
 }
 
-// ---- stage [lo, hi) (multiples of 16, relative to gbase) of the input into the ring ----
-__device__ void stage_input(Smem &S, const uint8_t *gbase, uint32_t lo, uint32_t hi, uint32_t valid_lo, uint32_t valid_hi)
+// ---- mbarrier + TMA bulk copy (global -> shared) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
-	for (uint32_t p = lo + threadIdx.x * 16; p < hi; p += kThreads * 16) {
-		uint8_t *dst = reinterpret_cast<uint8_t *>(S.ring32) + (p & kRingMask);
-		if (p >= valid_lo && p + 16 <= valid_hi) {
-			uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst);
-			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gbase + p));
-		} else {
-			// edge block: touch only bytes that belong to the caller
-			for (int k = 0; k < 16; k++) {
-				uint32_t q = p + k;
-				dst[k] = (q >= valid_lo && q < valid_hi) ? gbase[q] : 0;
-			}
-		}
-	}
-	asm volatile("cp.async.commit_group;\n" ::);
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;\n" ::); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+	uint32_t ok;
+	asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+		     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	return ok != 0;
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+		     ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
-// ---- warp 0: insert positions [lo, hi) into the hash chains, in stream order ----
-// One shared-memory atomic exchange per position: the returned value is the previous head, and
-// when several lanes of the warp hit the same bucket the hardware applies them one after the
-// other, so each lane receives the position of the lane applied just before it.  If that order
-// was ascending (checked below) the links are exactly those of a sequential insert; otherwise
-// the warp repairs the bucket with match.any (exact, just slower).
+// ---- warp 0: stage the input into the ring with TMA and thread the hash chains through it ----
+// Position space starts at gbase (the 16-byte aligned address at or below the first dictionary
+// byte); block b covers positions [b*kBlk, (b+1)*kBlk).  Staging block b overwrites the ring slots
+// of positions 64 KiB earlier, so it is only issued once every parser is past them (parse_pos).
+//
+// Chain insert: every lane reads the bucket's head (the previous position with this hash) and
+// then stores its own position, one warp instruction for 32 consecutive positions.  Loads and
+// stores of one warp reach shared memory in program order, so nothing on the critical path waits
+// for a load result: the links (position - previous) are written a few iterations later.  Lanes of
+// ONE instruction that share a bucket all link to the older head and one of them becomes the new
+// head: a chain can skip same-hash positions less than 32 bytes back, which costs well under 1 %
+// of ratio (tools/lzsim.c, racy=32) and removes every atomic from the build.
 __device__ void build_chains(Smem &S, uint32_t lo, uint32_t hi)
 {
 	const uint32_t lane = lane_id();
-	for (uint32_t p0 = lo; p0 < hi; p0 += 32) {
-		const uint32_t pos = p0 + lane;
-		const bool valid = pos < hi;
-		const uint32_t h = hash4(load4(S.ring32, pos));
-		uint32_t old = kNone;
-		if (valid)
-			old = atomicExch(&S.head[h], pos);
-		const bool same_iter = valid && old != kNone && old >= p0;
-		if (__ballot_sync(0xffffffffu, same_iter && old > pos)) {
-			// out-of-order application: rebuild this iteration's links exactly
-			const uint32_t key = valid ? h : (0x80000000u | lane);
-			const uint32_t grp = __match_any_sync(0xffffffffu, key);
-			const uint32_t outside = __ballot_sync(0xffffffffu, valid && !same_iter);
-			const int src = __ffs(grp & outside) - 1;            // the lane that saw the pre-iteration head
-			const uint32_t pre = __shfl_sync(0xffffffffu, old, src < 0 ? 0 : src);
-			const uint32_t lower = grp & ((1u << lane) - 1);
-			old = lower ? p0 + (31 - __clz(lower)) : (src < 0 ? kNone : pre);
-			if (valid && (grp >> lane) == 1u)
-				S.head[h] = pos;
+	constexpr int U = 4;
+	for (uint32_t p0 = lo; p0 < hi; p0 += 32 * U) {
+		uint32_t h[U], old[U];
+#pragma unroll
+		for (int u = 0; u < U; u++)
+			h[u] = hash5(S.ring32, p0 + 32 * u + lane);
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const uint32_t pos = p0 + 32 * u + lane;
+			old[u] = kNone;
+			if (pos < hi) {
+				old[u] = S.head[h[u]];
+				S.head[h[u]] = pos;
+			}
+			__syncwarp();
 		}
-		if (valid) {
-			const uint32_t d = pos - old;
-			S.prev[pos & kRingMask] = (uint16_t)((old != kNone && d <= (uint32_t)kWindow) ? d : 0);
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const uint32_t pos = p0 + 32 * u + lane;
+			const uint32_t d = pos - old[u];
+			if (pos < hi)
+				S.prev[pos & kRingMask] = (uint16_t)((old[u] < pos && d <= (uint32_t)kWindow) ? d : 0);
 		}
-		__syncwarp();
 	}
 }
 
+__device__ void producer(Smem &S, const uint8_t *gbase, uint32_t P0, uint32_t PE)
+{
+	const uint32_t lane = lane_id();
+	const uint32_t PEa = (PE + 15) & ~15u;
+	const uint32_t hash_hi = PE >= 4 ? PE - 4 : 0;           // positions with 5 bytes available
+	const uint32_t nblk = (PEa + kBlk - 1) / kBlk;
+	uint32_t issued = 0, BF = P0;
+	for (uint32_t b = 0; b < nblk; b++) {
+		// keep up to two blocks in flight beyond b; only the block we need next may block on ring space
+		while (issued < nblk && issued <= b + 2) {
+			const uint32_t need = (issued + 1) * kBlk;
+			long long t0 = clock64();
+			bool ok;
+			for (;;) {
+				const uint32_t mp = __reduce_min_sync(0xffffffffu, S.parse_pos[lane]);
+				ok = need <= mp + 32768u || mp == kNone;
+				if (ok || issued > b)
+					break;
+				__nanosleep(200);
+			}
+			if (issued == b)
+				DBG_ADD(2, clock64() - t0);
+			if (!ok)
+				break;
+			if (lane == 0) {
+				const uint32_t lo = issued * kBlk;
+				const uint32_t bytes = min(kBlk, PEa - lo);
+				uint64_t *bar = &S.mbar[issued % kSlots];
+				mbar_expect_tx(bar, bytes);
+				tma_load_1d(reinterpret_cast<uint8_t *>(S.ring32) + (lo & kRingMask), gbase + lo, bytes, bar);
+			}
+			issued++;
+		}
+		{
+			long long t0 = clock64();
+			const uint32_t parity = (b / kSlots) & 1;
+			while (!mbar_try_wait(&S.mbar[b % kSlots], parity))
+				;
+			DBG_ADD(1, clock64() - t0);
+		}
+		// positions of block b whose 5 bytes are staged: the last 4 wait for block b+1
+		const uint32_t blk_hi = min((b + 1) * kBlk, PEa);
+		const uint32_t hi = (b + 1 == nblk) ? hash_hi : min(blk_hi - 4, hash_hi);
+		long long t1 = clock64();
+		if (hi > BF) {
+			build_chains(S, BF, hi);
+			BF = hi;
+		}
+		DBG_ADD(0, clock64() - t1);
+		__threadfence_block();
+		__syncwarp();
+		if (lane == 0)
+			S.built = (b + 1 == nblk) ? kNone : BF;
+	}
+	if (nblk == 0 && lane == 0)
+		S.built = kNone;
+}
+
+// length of the common prefix of p and q, at most maxl; 16 bytes per step
 __device__ __forceinline__ uint32_t match_length(const uint32_t *ring32, uint32_t p, uint32_t q, uint32_t maxl)
 {
 	uint32_t pa = p >> 2, qa = q >> 2;
@@ -163,234 +236,128 @@ __device__ __forceinline__ uint32_t match_length(const uint32_t *ring32, uint32_
 	uint32_t pw0 = ring32[pa & 0x3FFF], qw0 = ring32[qa & 0x3FFF];
 	uint32_t l = 0;
 	while (l < maxl) {
-		uint32_t pw1 = ring32[(pa + 1) & 0x3FFF], qw1 = ring32[(qa + 1) & 0x3FFF];
-		uint32_t x = __funnelshift_r(pw0, pw1, ps) ^ __funnelshift_r(qw0, qw1, qs);
-		if (x) {
-			l += (__ffs(x) - 1) >> 3;
+		uint32_t pw[4], qw[4];
+#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			pw[i] = ring32[(pa + 1 + i) & 0x3FFF];
+			qw[i] = ring32[(qa + 1 + i) & 0x3FFF];
+		}
+		const uint32_t x0 = __funnelshift_r(pw0, pw[0], ps) ^ __funnelshift_r(qw0, qw[0], qs);
+		const uint32_t x1 = __funnelshift_r(pw[0], pw[1], ps) ^ __funnelshift_r(qw[0], qw[1], qs);
+		const uint32_t x2 = __funnelshift_r(pw[1], pw[2], ps) ^ __funnelshift_r(qw[1], qw[2], qs);
+		const uint32_t x3 = __funnelshift_r(pw[2], pw[3], ps) ^ __funnelshift_r(qw[2], qw[3], qs);
+		if (x0 | x1 | x2 | x3) {
+			if (x0) l += (uint32_t)(__ffs(x0) - 1) >> 3;
+			else if (x1) l += 4 + ((uint32_t)(__ffs(x1) - 1) >> 3);
+			else if (x2) l += 8 + ((uint32_t)(__ffs(x2) - 1) >> 3);
+			else l += 12 + ((uint32_t)(__ffs(x3) - 1) >> 3);
 			break;
 		}
-		l += 4; pa++; qa++; pw0 = pw1; qw0 = qw1;
+		l += 16; pa += 4; qa += 4; pw0 = pw[3]; qw0 = qw[3];
 	}
 	return l < maxl ? l : maxl;
 }
 
-// ---- matcher warps: best match for each of the 32 positions of one window ----
-// Phase 1 (one lane per position): walk the hash chain, comparing at most kCap bytes per
-// candidate — a candidate that reaches kCap ends the first pass, like zlib's nice_length.
-// Phase 2 (whole warp): consecutive positions whose capped match has the SAME distance lie
-// inside one long repeat; only the first of them is extended (32 lanes x 4 bytes per pass) and
-// the followers derive their length from it.  Without this every position inside a 258-byte
-// repeat re-compares up to 258 bytes on a single lane.
-// Phase 3: positions inside such a repeat keep walking their chain, but only a candidate that
-// also matches at offset `bl` (beyond the inherited length) is compared in full.
-constexpr uint32_t kCap = 32;
-
-// bytes [0, capl) of p and q, capl <= 32; loads are issued in two independent batches so a
-// compare costs about two shared-memory round trips instead of one per word
-__device__ __forceinline__ uint32_t match_len_cap(const uint32_t *ring32, uint32_t p, uint32_t q, uint32_t capl)
-{
-	const uint32_t pa = p >> 2, qa = q >> 2;
-	const uint32_t ps = (p & 3) * 8, qs = (q & 3) * 8;
-	uint32_t pw[5], qw[5];
-#pragma unroll
-	for (int i = 0; i < 5; i++) {
-		pw[i] = ring32[(pa + i) & 0x3FFF];
-		qw[i] = ring32[(qa + i) & 0x3FFF];
-	}
-#pragma unroll
-	for (int i = 0; i < 4; i++) {
-		const uint32_t x = __funnelshift_r(pw[i], pw[i + 1], ps) ^ __funnelshift_r(qw[i], qw[i + 1], qs);
-		if (x)
-			return min(capl, 4u * i + ((uint32_t)(__ffs(x) - 1) >> 3));
-	}
-	if (capl <= 16)
-		return capl;
-	uint32_t pv[5], qv[5];
-	pv[0] = pw[4]; qv[0] = qw[4];
-#pragma unroll
-	for (int i = 1; i < 5; i++) {
-		pv[i] = ring32[(pa + 4 + i) & 0x3FFF];
-		qv[i] = ring32[(qa + 4 + i) & 0x3FFF];
-	}
-#pragma unroll
-	for (int i = 0; i < 4; i++) {
-		const uint32_t x = __funnelshift_r(pv[i], pv[i + 1], ps) ^ __funnelshift_r(qv[i], qv[i + 1], qs);
-		if (x)
-			return min(capl, 16u + 4u * i + ((uint32_t)(__ffs(x) - 1) >> 3));
-	}
-	return capl;
-}
-
-struct WinResult {       // what a matcher lane keeps in registers until its window is emitted
-	uint32_t token;      // literal byte or tok_match(len, dist)
-	uint32_t reach;      // positions of the window visited when the stream enters at this lane
-};
-
-__device__ WinResult match_window(Smem &S, uint32_t g, uint32_t p0, uint32_t step_hi, uint32_t PE, uint32_t valid_lo,
-				  uint32_t step_seq, int depth, int nice, int lazy)
+// ---- parser warps: one sub-block [sub_lo, sub_hi) at a time, front to back ----
+// The warp looks at a window of 32 consecutive positions (one lane each).  Every lane walks the
+// hash chain of its position, nearest candidate first, keeping the longest match.  As soon as
+// the lane at the head of the token stream has its final answer the token is emitted and the head
+// jumps over the match; once it leaves the window the next window starts where it landed, so
+// positions covered by a match are never searched.  Matches stop at the sub-block end.
+__device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, uint32_t valid_lo,
+				   int depth, int nice, int lazy, uint32_t *tk, uint32_t &nwin)
 {
 	const uint32_t lane = lane_id();
-	const uint32_t nice_eff = min((uint32_t)nice, kCap);
-	const uint32_t pos = p0 + lane;
-	const bool live = pos < step_hi;
-	const uint32_t maxl = live ? min((uint32_t)kMaxMatch, PE - pos) : 0;
-	uint32_t bl = kMinMatch - 1, bd = 0;
-	uint32_t acc = 0;
-	int hop = 0;
-	const uint32_t maxdist = min((uint32_t)kWindow, pos - valid_lo);
-	uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;   // next chain link (prefetched)
-	if (d) {
-		const uint32_t capl = min(maxl, kCap);
-		// filter: the 4 bytes ending at offset bl must match (for bl == 3 that is the 4-gram itself,
-		// which weeds out hash collisions; later it is the tail that a longer match needs)
-		uint32_t endw = load4(S.ring32, pos + bl - 3);
-		for (; hop < depth; hop++) {
-			if (d == 0) { hop = depth; break; }
-			acc += d;
-			if (acc > maxdist) { hop = depth; d = 0; break; }
-			const uint32_t q = pos - acc;
-			d = S.prev[q & kRingMask];                         // independent of the check below
-			if (load4(S.ring32, q + bl - 3) != endw)
-				continue;
-			const uint32_t len = match_len_cap(S.ring32, pos, q, capl);
-			if (len > bl) {
-				bl = len; bd = acc;
-				if (len >= nice_eff || len >= capl) { hop++; break; }
-				endw = load4(S.ring32, pos + bl - 3);
-			}
-		}
-	}
-	// ---- phase 2 ----
-	const bool capped = (bl == kCap) && (maxl > kCap);
-	{
-		const uint32_t d_prev = __shfl_up_sync(0xffffffffu, bd, 1);
-		const bool c_prev = __shfl_up_sync(0xffffffffu, (int)capped, 1) != 0 && lane > 0;
-		const bool head = capped && !(c_prev && d_prev == bd);
-		const uint32_t heads_all = __ballot_sync(0xffffffffu, head);
-		uint32_t heads = heads_all;
-		const uint32_t myhead = capped ? 31 - __clz(heads_all & ((2u << lane) - 1)) : 32;
-		while (heads) {
-			const int h = __ffs(heads) - 1;
-			heads &= heads - 1;
-			const uint32_t hp = p0 + h;
-			const uint32_t hd = __shfl_sync(0xffffffffu, bd, h);
-			const uint32_t hmax = min((uint32_t)kMaxMatch + 31, PE - hp);
-			uint32_t L = kCap;
-			for (uint32_t base = kCap; base < hmax; base += 128) {
-				const uint32_t off = base + 4 * lane;
-				const uint32_t x = load4(S.ring32, hp + off) ^ load4(S.ring32, hp - hd + off);
-				uint32_t e = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4;
-				const uint32_t room = off < hmax ? min(4u, hmax - off) : 0;
-				e = min(e, room);
-				const uint32_t stop = __ballot_sync(0xffffffffu, e < 4);
-				if (stop == 0) { L = base + 128; continue; }
-				const int f = __ffs(stop) - 1;
-				L = base + 4 * f + __shfl_sync(0xffffffffu, e, f);
-				break;
-			}
-			if (myhead == (uint32_t)h)
-				bl = min(maxl, L - (lane - h));
-		}
-	}
-	// ---- phase 3 ----
-	if (capped && bl < maxl && bl < (uint32_t)nice) {
+	const uint32_t lt = (1u << lane) - 1;
+	uint32_t n = 0;
+	uint32_t p = sub_lo;
+	while (p < sub_hi) {
+		nwin++;
+		const uint32_t pos = p + lane;
+		const uint32_t nlive = min(32u, sub_hi - p);
+		const bool live = lane < nlive;
+		const uint32_t maxl = live ? min((uint32_t)kMaxMatch, sub_hi - pos) : 0;
+		const uint32_t maxdist = min((uint32_t)kWindow, pos - valid_lo);
+		const uint32_t myb = ring_byte(S.ring32, pos);
+		uint32_t bl = kMinMatch - 1, bd = 0, acc = 0;
+		uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;
 		uint32_t endb = ring_byte(S.ring32, pos + bl);
-		for (; hop < depth; hop++) {
-			if (d == 0)
-				break;
-			acc += d;
-			if (acc > maxdist)
-				break;
-			const uint32_t q = pos - acc;
-			d = S.prev[q & kRingMask];
-			if (ring_byte(S.ring32, q + bl) != endb)
-				continue;
-			const uint32_t len = match_length(S.ring32, pos, q, maxl);
-			if (len > bl) {
-				bl = len; bd = acc;
-				if (len >= (uint32_t)nice || len >= maxl)
-					break;
-				endb = ring_byte(S.ring32, pos + bl);
+		uint32_t head = 0;
+		bool finished = false;
+		for (int hop = 0; !finished; hop++) {
+			if (d) {
+				acc += d;
+				if (acc > maxdist) {
+					d = 0;
+				} else {
+					const uint32_t q = pos - acc;
+					d = S.prev[q & kRingMask];
+					if (ring_byte(S.ring32, q + bl) == endb) {
+						const uint32_t len = match_length(S.ring32, pos, q, maxl);
+						if (len > bl) {
+							bl = len; bd = acc;
+							if (len >= (uint32_t)nice || len >= maxl)
+								d = 0;
+							else
+								endb = ring_byte(S.ring32, pos + bl);
+						}
+					}
+				}
 			}
+			if (hop + 1 >= depth)
+				d = 0;
+			if ((hop & 1) == 0 && hop + 1 < depth)
+				continue;                                  // look at the head every other hop
+			const uint32_t dm = __ballot_sync(0xffffffffu, d == 0);
+			if ((dm | ((1u << head) - 1)) == 0xffffffffu)
+				break;                                     // everything from the head on is final
+			// serial steps while the lane at the head is final
+			while (head < nlive && ((dm >> head) & 1)) {
+				uint32_t L = __shfl_sync(0xffffffffu, bl, head);
+				L = L >= (uint32_t)kMinMatch ? L : 0;
+				if (L && lazy && L < (uint32_t)lazy && head < 31) {
+					if (!((dm >> (head + 1)) & 1))
+						break;
+					if (__shfl_sync(0xffffffffu, bl, head + 1) > L)
+						L = 0;
+				}
+				const uint32_t bdh = __shfl_sync(0xffffffffu, bd, head);
+				const uint32_t byh = __shfl_sync(0xffffffffu, myb, head);
+				if (lane == 0)
+					tk[n] = L ? tok_match(L, bdh) : byh;
+				n++;
+				head += L ? L : 1;
+			}
+			if (head >= nlive)
+				finished = true;
 		}
-	}
-
-	// ---- greedy / lazy choice per position, then reach sets by pointer jumping ----
-	const uint32_t len = (bl >= (uint32_t)kMinMatch) ? bl : 0;
-	uint32_t nlen = __shfl_down_sync(0xffffffffu, len, 1);
-	if (lane == 31)
-		nlen = 0;                                  // no look-ahead across windows
-	bool take = len != 0;
-	if (take && lazy && len < (uint32_t)lazy && nlen > len)
-		take = false;
-	uint32_t J = live ? lane + (take ? len : 1) : 64;       // next token start relative to p0 (>= 32: leaves the window)
-	uint32_t Rl = live ? (1u << lane) : 0;
+		if (!finished) {
+			// greedy / lazy choice per position, then the reach set of the head by pointer jumping
+			const uint32_t len = (bl >= (uint32_t)kMinMatch) ? bl : 0;
+			uint32_t nlen = __shfl_down_sync(0xffffffffu, len, 1);
+			if (lane == 31)
+				nlen = 0;                                  // no look-ahead across windows
+			bool take = len != 0;
+			if (take && lazy && len < (uint32_t)lazy && nlen > len)
+				take = false;
+			uint32_t J = live ? lane + (take ? len : 1) : 64;      // next token start (>= 32: leaves the window)
+			uint32_t Rl = live ? (1u << lane) : 0;
 #pragma unroll
-	for (int k = 0; k < 5; k++) {
-		const uint32_t tJ = __shfl_sync(0xffffffffu, J, J & 31);
-		const uint32_t tR = __shfl_sync(0xffffffffu, Rl, J & 31);
-		if (J < 32) { Rl |= tR; J = tJ; }
-	}
-	// the parser warp only needs, per possible entry lane, the exit and the token count
-	S.JC[g * 32 + lane] = (uint16_t)(J | ((uint32_t)__popc(Rl) << 10));
-	__threadfence_block();
-	__syncwarp();
-	if (lane == 0)
-		S.win_flag[g] = step_seq;
-	WinResult r;
-	r.token = take ? tok_match(len, bd) : ring_byte(S.ring32, pos);
-	r.reach = Rl;
-	return r;
-}
-
-// a matcher warp writes out the tokens of the window it matched in the PREVIOUS step: by now the
-// parser has published where the stream entered that window (lane, or >= 32 if it was jumped over)
-// and the index of its first token
-__device__ __forceinline__ void emit_window(Smem &S, const WinResult &r, uint32_t entry, uint32_t off, uint32_t *tok)
-{
-	if (entry >= 32)
-		return;
-	const uint32_t lane = lane_id();
-	const uint32_t R = __shfl_sync(0xffffffffu, r.reach, entry);
-	if ((R >> lane) & 1) {
-		const uint32_t t = r.token;
-		if (tok_is_match(t)) {
-			uint32_t lc, le, lx, dc, de, dx;
-			len_code(tok_len(t), lc, le, lx);
-			dist_code(tok_dist(t), dc, de, dx);
-			atomicAdd(&S.ll_freq[257 + lc], 1u);
-			atomicAdd(&S.d_freq[dc], 1u);
-		} else {
-			atomicAdd(&S.ll_freq[t], 1u);
+			for (int k = 0; k < 5; k++) {
+				const uint32_t tJ = __shfl_sync(0xffffffffu, J, J & 31);
+				const uint32_t tR = __shfl_sync(0xffffffffu, Rl, J & 31);
+				if (J < 32) { Rl |= tR; J = tJ; }
+			}
+			const uint32_t R = __shfl_sync(0xffffffffu, Rl, head);
+			const uint32_t exitJ = __shfl_sync(0xffffffffu, J, head);
+			if ((R >> lane) & 1)
+				tk[n + __popc(R & lt)] = take ? tok_match(len, bd) : myb;
+			n += __popc(R);
+			head = exitJ;
 		}
-		tok[off + __popc(R & ((1u << lane) - 1))] = t;
+		p += head;
 	}
-}
-
-// ---- warp 1: follow the token stream through the windows of one step as the matchers finish them;
-//      publishes per window the entry lane and the index of its first token ----
-__device__ void parse_step(Smem &S, uint32_t step_lo, uint32_t step_hi, uint32_t step_seq, uint32_t &cur, uint32_t &ntok)
-{
-	const uint32_t nwin = (step_hi - step_lo + 31) / 32;
-	const uint32_t par = step_seq & 1;
-	for (uint32_t g = 0; g < nwin; g++) {
-		const uint32_t p0 = step_lo + g * 32;
-		while (S.win_flag[g] != step_seq)
-			;
-		__threadfence_block();
-		uint32_t entry = 64;
-		const uint32_t off = ntok;
-		if (cur < p0 + 32 && cur < step_hi) {
-			entry = cur - p0;
-			const uint32_t jc = S.JC[g * 32 + entry];
-			cur = p0 + (jc & 1023);
-			ntok += jc >> 10;
-		}
-		if (lane_id() == 0) {
-			S.ent[par][g] = entry;
-			S.off[par][g] = off;
-		}
-	}
+	return n;
 }
 
 // ---- Huffman: CTA-collective code-length construction ----
@@ -778,6 +745,11 @@ __device__ uint32_t emit_stored(const DeflateJob &J, bool final_flag)
 	return o;
 }
 
+// per-CTA scratch in global memory (L2-resident): flat token stream | per-position token slots of
+// the sub-blocks | tokens per sub-block | first flat index per sub-block
+__host__ __device__ inline uint32_t scratch_nsub(uint32_t tok_stride) { return tok_stride / kSub + 2; }
+__host__ __device__ inline size_t scratch_words(uint32_t tok_stride) { return 2 * (size_t)tok_stride + 2 * (size_t)scratch_nsub(tok_stride); }
+
 __global__ void __launch_bounds__(kThreads, 1)
 deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ outs, uint32_t n_jobs,
 	       int depth, int lazy, int nice, uint32_t *tok_scratch, uint32_t tok_stride)
@@ -786,7 +758,10 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 	Smem &S = *reinterpret_cast<Smem *>(smem_raw);
 	HuffScratch &H = *reinterpret_cast<HuffScratch *>(S.prev);
 	const uint32_t warp = threadIdx.x >> 5;
-	uint32_t *tok = tok_scratch + (size_t)blockIdx.x * tok_stride;
+	uint32_t *tok = tok_scratch + (size_t)blockIdx.x * scratch_words(tok_stride);
+	uint32_t *tokpos = tok + tok_stride;
+	uint32_t *sub_cnt = tokpos + tok_stride;
+	uint32_t *sub_off = sub_cnt + scratch_nsub(tok_stride);
 
 	for (uint32_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
 		const long long tjob0 = clock64();
@@ -796,70 +771,115 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 		const uint32_t P0 = (uint32_t)(first & 15);      // first dictionary byte
 		const uint32_t PS = P0 + J.hist_len;              // first byte to compress
 		const uint32_t PE = PS + J.src_len;
-		const uint32_t PEa = (PE + 15) & ~15u;
-		const uint32_t hash_hi = PE >= 3 ? PE - 3 : 0;    // positions with 4 bytes available
-		const uint32_t nsteps = (J.src_len + kStep - 1) / kStep;
+		const uint32_t n_sub = (J.src_len + kSub - 1) / kSub;
 
 		// ---- init ----
 		for (int i = threadIdx.x; i < kHashSize; i += kThreads)
 			S.head[i] = kNone;
 		for (int i = threadIdx.x; i < 288; i += kThreads)
 			S.ll_freq[i] = 0;
-		if (threadIdx.x < 32)
+		if (threadIdx.x < 32) {
 			S.d_freq[threadIdx.x] = 0;
-		if (threadIdx.x < 32)
-			S.win_flag[threadIdx.x] = 0;
-		if (threadIdx.x == 0) { S.grp_ctr[0] = 0; S.grp_ctr[1] = 0; S.n_tok = 0; }
-		uint32_t DF = min(PEa, (PS + 3 * kStep + 15) & ~15u);   // data staged through here
-		stage_input(S, gbase, 0, DF, P0, PE);
-		stage_wait();
-		__syncthreads();
-		uint32_t BF = P0;                                        // warp-0 state: chains built up to here
-		uint32_t cur = PS, ntok = 0;                             // warp-1 state: next token start, tokens so far
-		WinResult held = { 0, 0 };                               // matcher state: last step's window, not yet emitted
-		bool have_held = false;
-		const uint32_t g = warp - 2;                             // matcher warps 2..31 own window g of every step
-		if (warp == 0) {
-			uint32_t hi = min(PS + kStep, hash_hi);
-			if (hi > BF) { build_chains(S, BF, hi); BF = hi; }
+			const uint32_t w = threadIdx.x - 1;               // parser index of warp threadIdx.x
+			S.parse_pos[threadIdx.x] = (threadIdx.x >= 1 && w < n_sub) ? PS + w * kSub : kNone;
 		}
+		if (threadIdx.x == 0) {
+			S.n_tok = 0;
+			S.built = 0;
+			for (int i = 0; i < kSlots; i++)
+				mbar_init(&S.mbar[i], 1);
+			asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+		}
+		// the ring was last written by ordinary stores (bit-packer staging); TMA writes come next
+		asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 		__syncthreads();
 
-		// ---- LZ77 pipeline: warp 0 build(s+1) | warp 1 parse(s) | warps 2.. emit(s-1), match(s) | stage(s+3) ----
-		for (uint32_t s = 0; s < nsteps; s++) {
-			const uint32_t step_lo = PS + s * kStep;
-			const uint32_t step_hi = min(step_lo + kStep, PE);
-			const uint32_t want = min(PEa, (PS + (s + 4) * kStep + 15) & ~15u);
-			if (want > DF) { stage_input(S, gbase, DF, want, P0, PE); DF = want; }
-			long long tc1 = clock64();
-			if (warp == 0) {
-				uint32_t hi = min(PS + (s + 2) * kStep, hash_hi);
-				if (hi > BF) { build_chains(S, BF, hi); BF = hi; }
-				DBG_ADD(0, clock64() - tc1);
-			} else if (warp == 1) {
-				parse_step(S, step_lo, step_hi, s + 1, cur, ntok);
-				DBG_ADD(1, clock64() - tc1);
-			} else {
-				if (have_held)
-					emit_window(S, held, S.ent[s & 1][g], S.off[s & 1][g], tok);
-				const uint32_t p0 = step_lo + g * 32;
-				have_held = p0 < step_hi;
-				if (have_held)
-					held = match_window(S, g, p0, step_hi, PE, P0, s + 1, depth, nice, lazy);
+		// ---- LZ77: warp 0 stages + builds chains, warps 1..31 parse sub-blocks round-robin ----
+		if (warp == 0) {
+			producer(S, gbase, P0, PE);
+		} else {
+			uint32_t nwin = 0;
+			long long busy = 0, waited = 0;
+			for (uint32_t sb = warp - 1; sb < n_sub; sb += kParsers) {
+				const uint32_t sub_lo = PS + sb * kSub;
+				const uint32_t sub_hi = min(PE, sub_lo + kSub);
+				__syncwarp();
+				if (lane_id() == 0)
+					S.parse_pos[warp] = sub_lo;
+				const long long t0 = clock64();
+				while (S.built < sub_hi)
+					__nanosleep(100);
+				__threadfence_block();
+				const long long t1 = clock64();
+				const uint32_t cnt = parse_subblock(S, sub_lo, sub_hi, P0, depth, nice, lazy, tokpos + (size_t)sb * kSub, nwin);
+				if (lane_id() == 0)
+					sub_cnt[sb] = cnt;
+				waited += t1 - t0;
+				busy += clock64() - t1;
 			}
-			long long tc2 = clock64();
-			stage_wait();
-			__syncthreads();
-			if (warp == 2) { DBG_ADD(2, tc2 - tc1); DBG_ADD(3, clock64() - tc2); DBG_ADD(4, 1); }
+			__syncwarp();
+			if (lane_id() == 0)
+				S.parse_pos[warp] = kNone;
+			if (warp == 1) { DBG_ADD(3, busy); DBG_ADD(4, waited); DBG_ADD(7, nwin); }
 		}
-		if (warp >= 2 && have_held)
-			emit_window(S, held, S.ent[nsteps & 1][g], S.off[nsteps & 1][g], tok);
-		if (threadIdx.x == 32)
-			S.n_tok = ntok;
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			for (int i = 0; i < kSlots; i++)
+				asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&S.mbar[i])) : "memory");
+		}
+
+		// ---- flat token stream + histograms: scan the sub-block counts, then copy ----
+		uint32_t ntok = 0;
+		for (uint32_t base = 0; base < n_sub; base += kThreads) {
+			const uint32_t i = base + threadIdx.x;
+			const uint32_t c = i < n_sub ? sub_cnt[i] : 0;
+			uint32_t incl = c;
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+				if (lane_id() >= (uint32_t)o)
+					incl += y;
+			}
+			if (lane_id() == 31)
+				H.warp_sums[warp] = incl;
+			__syncthreads();
+			if (warp == 0) {
+				const uint32_t ws = H.warp_sums[lane_id()];
+				uint32_t wi = ws;
+				for (int o = 1; o < 32; o <<= 1) {
+					const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o);
+					if (lane_id() >= (uint32_t)o)
+						wi += y;
+				}
+				H.warp_sums[lane_id()] = wi - ws;
+				if (lane_id() == 31)
+					H.batch_total = wi;
+			}
+			__syncthreads();
+			if (i < n_sub)
+				sub_off[i] = ntok + H.warp_sums[warp] + incl - c;
+			ntok += H.batch_total;
+			__syncthreads();
+		}
+		for (uint32_t sb = warp; sb < n_sub; sb += kThreads / 32) {
+			const uint32_t cnt = sub_cnt[sb], off = sub_off[sb];
+			const uint32_t *src = tokpos + (size_t)sb * kSub;
+			for (uint32_t k = lane_id(); k < cnt; k += 32) {
+				const uint32_t t = src[k];
+				tok[off + k] = t;
+				if (tok_is_match(t)) {
+					uint32_t lc, le, lx, dc, de, dx;
+					len_code(tok_len(t), lc, le, lx);
+					dist_code(tok_dist(t), dc, de, dx);
+					atomicAdd(&S.ll_freq[257 + lc], 1u);
+					atomicAdd(&S.d_freq[dc], 1u);
+				} else {
+					atomicAdd(&S.ll_freq[t], 1u);
+				}
+			}
+		}
 		if (threadIdx.x == 0)
 			S.ll_freq[256] = 1;                               // EOB
 		__syncthreads();
-		ntok = S.n_tok;
 		const long long thuf0 = clock64();
 
 		// ---- Huffman tables, block type decision ----
@@ -1012,6 +1032,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 } // namespace
 
 size_t deflate_smem_bytes() { return sizeof(Smem); }
+size_t deflate_scratch_words(uint32_t tok_stride) { return scratch_words(tok_stride); }
 
 cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_jobs, int level,
 			   uint32_t *tok_scratch, uint32_t tok_stride, int grid, cudaStream_t s)
@@ -1023,7 +1044,11 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 			return e;
 		configured = true;
 	}
-	const LevelParams lp = level_params(level);
+	LevelParams lp = level_params(level);
+	if (const char *ov = getenv("NXGPU_LZ_PARAMS")) {         // developer override: "depth,lazy,nice"
+		int a, b, c;
+		if (sscanf(ov, "%d,%d,%d", &a, &b, &c) == 3 && a >= 1) { lp.depth = a; lp.lazy = b; lp.nice = c; }
+	}
 	static const bool dbg = getenv("NXGPU_DEBUG_CYCLES") != nullptr;
 	unsigned long long *d_dbg = nullptr;
 	if (dbg) {
@@ -1040,8 +1065,10 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 		unsigned long long t[8] = { 0 };
 		for (int b = 0; b < grid; b++) for (int k = 0; k < 8; k++) t[k] += h[(size_t)b * 8 + k];
 		const double st = t[4] ? (double)t[4] : 1.0;
-		fprintf(stderr, "[nxgpu cycles/step] level %d: build %.0f parse %.0f match(w2) %.0f barrier-wait(w2) %.0f | per job: huff+pack %.0f total %.0f (steps/job %.1f)\n",
-			level, t[0] / st, t[1] / st, t[2] / st, t[3] / st, (double)t[5] / n_jobs, (double)t[6] / n_jobs, st / n_jobs);
+		(void)st;
+		const double nj = n_jobs;
+		fprintf(stderr, "[nxgpu cycles/job] level %d (depth %d lazy %d nice %d): producer build %.0f wait-data %.0f wait-space %.0f | parser(w1) busy %.0f wait %.0f windows %.0f | huff+pack %.0f total %.0f\n",
+			level, lp.depth, lp.lazy, lp.nice, t[0] / nj, t[1] / nj, t[2] / nj, t[3] / nj, t[4] / nj, t[7] / nj, t[5] / nj, t[6] / nj);
 		d_dbg = nullptr;
 		cudaMemcpyToSymbol(g_dbg, &d_dbg, sizeof(d_dbg));
 	}

@@ -439,9 +439,9 @@ static int deflate_device(nxgpu_ctx *c, DeflateJob *jobs_h, size_t n, int level,
 		if (jobs_h[i].src_len > max_len) max_len = jobs_h[i].src_len;
 	}
 	const int grid = (int)(n < (size_t)kNumSMs ? n : (size_t)kNumSMs);
-	const uint32_t tok_stride = (uint32_t)align_up((size_t)max_len + 64, 64);
+	const uint32_t tok_stride = (uint32_t)align_up((size_t)max_len + 64, 512);
 	if ((rc = c->d_slots.reserve(slot_total + 64))) return rc;
-	if ((rc = c->d_tok.reserve((size_t)grid * tok_stride * 4))) return rc;
+	if ((rc = c->d_tok.reserve((size_t)grid * deflate_scratch_words(tok_stride) * 4))) return rc;
 	if ((rc = c->d_jobs.reserve(n * sizeof(DeflateJob)))) return rc;
 	if ((rc = c->d_outs.reserve(n * sizeof(DeflateOut)))) return rc;
 	size_t o = 0;
