@@ -95,17 +95,17 @@ struct CksumJob {
 struct LevelParams { int depth; int lazy; int nice; };
 __host__ __device__ inline LevelParams level_params(int level)
 {
-	switch (level) {          // chain depth (5-byte hash chains), lazy threshold (0 = greedy), nice length
+	switch (level) {          // base chain depth (x1..x4 with the data, see parse_subblock), lazy threshold (0 = greedy), nice length
 	case 1: return { 2, 0, 32 };
 	case 2: return { 3, 0, 64 };
 	case 3: return { 4, 0, 128 };
 	case 4: return { 4, 16, 128 };
-	case 5: return { 6, 32, 258 };
-	case 6: return { 8, 32, 258 };
+	case 5: return { 8, 32, 258 };
+	case 6: return { 12, 32, 258 };
 	case 7: return { 16, 64, 258 };
-	case 8: return { 32, 258, 258 };
-	case 9: return { 64, 258, 258 };
-	default: return { 8, 32, 258 };
+	case 8: return { 24, 258, 258 };
+	case 9: return { 48, 258, 258 };
+	default: return { 12, 32, 258 };
 	}
 }
 

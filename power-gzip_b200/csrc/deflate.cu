@@ -38,15 +38,18 @@ constexpr int kStageWords = 2048;
 constexpr uint32_t kSub = 512;            // bytes per sub-block (one parser warp at a time)
 constexpr uint32_t kBlk = 4096;           // bytes per TMA staging block
 constexpr int kSlots = 4;                 // staging mbarriers (block b uses slot b % kSlots)
-constexpr int kParsers = kThreads / 32 - 1;   // warps 1..31 parse, warp 0 produces
+constexpr int kDoneSlots = 16;            // "chains of block b are built" mbarriers (slot b % kDoneSlots)
+constexpr int kMirrorWords = 80;          // ring bytes [0, 320) are mirrored behind the ring
 
 struct __align__(16) Smem {
-	uint32_t ring32[16384];           // 64 KiB input ring (position & 0xFFFF)
+	uint32_t ring32[16384 + kMirrorWords];   // 64 KiB input ring (position & 0xFFFF) + copy of its first bytes,
+	                                  // so that reads of up to 320 bytes never have to wrap
 	uint16_t prev[65536];             // 128 KiB: distance to the previous position with the same hash
 	uint32_t head[kHashSize];         // 32 KiB: most recent position per hash (kNone = empty)
 	uint64_t mbar[kSlots];            // TMA completion barriers of the staging blocks
+	uint64_t done_bar[kDoneSlots];    // producer arrives once block b's chains are built; parsers sleep on it
 	volatile uint32_t parse_pos[32];  // per parser warp: first position of the sub-block in flight
-	volatile uint32_t built;          // chains exist (and data is staged) for every position below this
+	uint32_t next_sub;                // next sub-block to hand out
 	uint32_t ll_freq[288];
 	uint32_t d_freq[32];
 	uint32_t n_tok;
@@ -86,24 +89,30 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 __device__ unsigned long long *g_dbg = nullptr;
 #define DBG_ADD(slot, v) do { if (g_dbg && lane_id() == 0) atomicAdd(&g_dbg[blockIdx.x * 8 + (slot)], (unsigned long long)(v)); } while (0)
 
-__device__ __forceinline__ uint32_t load4(const uint32_t *ring32, uint32_t pos)
+// The ring is addressed by byte offset (position & 0xFFFF); thanks to the mirror behind it a read
+// may run up to 320 bytes past the offset without masking.
+__device__ __forceinline__ uint32_t ld32(const uint8_t *ring8, uint32_t aligned_off)
 {
-	uint32_t a = (pos >> 2) & 0x3FFF, b = (a + 1) & 0x3FFF;
-	return __funnelshift_r(ring32[a], ring32[b], (pos & 3) * 8);
+	return *reinterpret_cast<const uint32_t *>(ring8 + aligned_off);
+}
+__device__ __forceinline__ uint32_t load4(const uint8_t *ring8, uint32_t pos)
+{
+	const uint32_t o = pos & kRingMask, a = o & ~3u;
+	return __funnelshift_r(ld32(ring8, a), ld32(ring8, a + 4), (o & 3) * 8);
 }
 // hash of the 5 bytes at pos (the chains only ever propose matches of 5 or more bytes)
-__device__ __forceinline__ uint32_t hash5(const uint32_t *ring32, uint32_t pos)
+__device__ __forceinline__ uint32_t hash5(const uint8_t *ring8, uint32_t pos)
 {
-	const uint32_t a = (pos >> 2) & 0x3FFF;
-	const uint32_t w0 = ring32[a], w1 = ring32[(a + 1) & 0x3FFF], w2 = ring32[(a + 2) & 0x3FFF];
-	const uint32_t sh = (pos & 3) * 8;
+	const uint32_t o = pos & kRingMask, a = o & ~3u;
+	const uint32_t w0 = ld32(ring8, a), w1 = ld32(ring8, a + 4), w2 = ld32(ring8, a + 8);
+	const uint32_t sh = (o & 3) * 8;
 	const uint32_t lo = __funnelshift_r(w0, w1, sh);
 	const uint32_t b4 = __funnelshift_r(w1, w2, sh) & 0xffu;
 	return ((lo * 0x9E3779B1u) ^ (b4 * 0x85EBCA6Bu + (lo >> 15))) * 0x2545F491u >> (32 - kHashBits);
 }
-__device__ __forceinline__ uint32_t ring_byte(const uint32_t *ring32, uint32_t pos)
+__device__ __forceinline__ uint32_t ring_byte(const uint8_t *ring8, uint32_t pos)
 {
-	return reinterpret_cast<const uint8_t *>(ring32)[pos & kRingMask];
+	return ring8[pos & kRingMask];
 }
 
 // ---- mbarrier + TMA bulk copy (global -> shared) ----
@@ -116,11 +125,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// try_wait suspends the warp in hardware until the phase completes or the time hint (ns) runs out;
+// without the hint it returns after a few cycles and the retry loop eats issue slots
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
 	uint32_t ok;
-	asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-		     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+		     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(100000u) : "memory");
 	return ok != 0;
 }
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
@@ -144,12 +159,13 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
 __device__ void build_chains(Smem &S, uint32_t lo, uint32_t hi)
 {
 	const uint32_t lane = lane_id();
+	const uint8_t *ring8 = reinterpret_cast<const uint8_t *>(S.ring32);
 	constexpr int U = 4;
 	for (uint32_t p0 = lo; p0 < hi; p0 += 32 * U) {
 		uint32_t h[U], old[U];
 #pragma unroll
 		for (int u = 0; u < U; u++)
-			h[u] = hash5(S.ring32, p0 + 32 * u + lane);
+			h[u] = hash5(ring8, p0 + 32 * u + lane);
 #pragma unroll
 		for (int u = 0; u < U; u++) {
 			const uint32_t pos = p0 + 32 * u + lane;
@@ -188,7 +204,7 @@ __device__ void producer(Smem &S, const uint8_t *gbase, uint32_t P0, uint32_t PE
 				ok = need <= mp + 32768u || mp == kNone;
 				if (ok || issued > b)
 					break;
-				__nanosleep(200);
+				__nanosleep(500);
 			}
 			if (issued == b)
 				DBG_ADD(2, clock64() - t0);
@@ -210,6 +226,11 @@ __device__ void producer(Smem &S, const uint8_t *gbase, uint32_t P0, uint32_t PE
 				;
 			DBG_ADD(1, clock64() - t0);
 		}
+		if (((b * kBlk) & kRingMask) == 0) {
+			for (int i = lane; i < kMirrorWords; i += 32)
+				S.ring32[16384 + i] = S.ring32[i];
+			__syncwarp();
+		}
 		// positions of block b whose 5 bytes are staged: the last 4 wait for block b+1
 		const uint32_t blk_hi = min((b + 1) * kBlk, PEa);
 		const uint32_t hi = (b + 1 == nblk) ? hash_hi : min(blk_hi - 4, hash_hi);
@@ -219,72 +240,100 @@ __device__ void producer(Smem &S, const uint8_t *gbase, uint32_t P0, uint32_t PE
 			BF = hi;
 		}
 		DBG_ADD(0, clock64() - t1);
+		// block b done: chains exist for every position below (b+1)*kBlk - 4 (everything, for the last block)
 		__threadfence_block();
 		__syncwarp();
 		if (lane == 0)
-			S.built = (b + 1 == nblk) ? kNone : BF;
+			mbar_arrive(&S.done_bar[b % kDoneSlots]);
 	}
-	if (nblk == 0 && lane == 0)
-		S.built = kNone;
 }
 
-// length of the common prefix of p and q, at most maxl; 16 bytes per step
-__device__ __forceinline__ uint32_t match_length(const uint32_t *ring32, uint32_t p, uint32_t q, uint32_t maxl)
+// length of the common prefix of p and q, at most maxl.  P0..P3 are the first 16 bytes at p
+// (the caller keeps them in registers for the whole window); 16 bytes per step after that.
+__device__ __forceinline__ uint32_t first_diff(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3)
 {
-	uint32_t pa = p >> 2, qa = q >> 2;
-	const uint32_t ps = (p & 3) * 8, qs = (q & 3) * 8;
-	uint32_t pw0 = ring32[pa & 0x3FFF], qw0 = ring32[qa & 0x3FFF];
-	uint32_t l = 0;
-	while (l < maxl) {
-		uint32_t pw[4], qw[4];
-#pragma unroll
-		for (int i = 0; i < 4; i++) {
-			pw[i] = ring32[(pa + 1 + i) & 0x3FFF];
-			qw[i] = ring32[(qa + 1 + i) & 0x3FFF];
+	if (x0) return (uint32_t)(__ffs(x0) - 1) >> 3;
+	if (x1) return 4 + ((uint32_t)(__ffs(x1) - 1) >> 3);
+	if (x2) return 8 + ((uint32_t)(__ffs(x2) - 1) >> 3);
+	return 12 + ((uint32_t)(__ffs(x3) - 1) >> 3);
+}
+__device__ __forceinline__ uint32_t match_length(const uint8_t *ring8, uint32_t p, uint32_t q, uint32_t maxl,
+						 uint32_t P0, uint32_t P1, uint32_t P2, uint32_t P3)
+{
+	const uint32_t qo = q & kRingMask, qa = qo & ~3u, qs = (qo & 3) * 8;
+	const uint32_t w0 = ld32(ring8, qa), w1 = ld32(ring8, qa + 4), w2 = ld32(ring8, qa + 8), w3 = ld32(ring8, qa + 12);
+	uint32_t qw0 = ld32(ring8, qa + 16);
+	uint32_t x0 = P0 ^ __funnelshift_r(w0, w1, qs), x1 = P1 ^ __funnelshift_r(w1, w2, qs);
+	uint32_t x2 = P2 ^ __funnelshift_r(w2, w3, qs), x3 = P3 ^ __funnelshift_r(w3, qw0, qs);
+	uint32_t l;
+	if (x0 | x1 | x2 | x3) {
+		l = first_diff(x0, x1, x2, x3);
+	} else {
+		const uint32_t po = p & kRingMask, ps = (po & 3) * 8;
+		uint32_t pa = (po & ~3u) + 16, qb = qa + 16;
+		uint32_t pw0 = ld32(ring8, pa);
+		l = 16;
+		while (l < maxl) {
+			const uint32_t pw1 = ld32(ring8, pa + 4), pw2 = ld32(ring8, pa + 8), pw3 = ld32(ring8, pa + 12), pw4 = ld32(ring8, pa + 16);
+			const uint32_t qw1 = ld32(ring8, qb + 4), qw2 = ld32(ring8, qb + 8), qw3 = ld32(ring8, qb + 12), qw4 = ld32(ring8, qb + 16);
+			x0 = __funnelshift_r(pw0, pw1, ps) ^ __funnelshift_r(qw0, qw1, qs);
+			x1 = __funnelshift_r(pw1, pw2, ps) ^ __funnelshift_r(qw1, qw2, qs);
+			x2 = __funnelshift_r(pw2, pw3, ps) ^ __funnelshift_r(qw2, qw3, qs);
+			x3 = __funnelshift_r(pw3, pw4, ps) ^ __funnelshift_r(qw3, qw4, qs);
+			if (x0 | x1 | x2 | x3) {
+				l += first_diff(x0, x1, x2, x3);
+				break;
+			}
+			l += 16; pa += 16; qb += 16; pw0 = pw4; qw0 = qw4;
 		}
-		const uint32_t x0 = __funnelshift_r(pw0, pw[0], ps) ^ __funnelshift_r(qw0, qw[0], qs);
-		const uint32_t x1 = __funnelshift_r(pw[0], pw[1], ps) ^ __funnelshift_r(qw[0], qw[1], qs);
-		const uint32_t x2 = __funnelshift_r(pw[1], pw[2], ps) ^ __funnelshift_r(qw[1], qw[2], qs);
-		const uint32_t x3 = __funnelshift_r(pw[2], pw[3], ps) ^ __funnelshift_r(qw[2], qw[3], qs);
-		if (x0 | x1 | x2 | x3) {
-			if (x0) l += (uint32_t)(__ffs(x0) - 1) >> 3;
-			else if (x1) l += 4 + ((uint32_t)(__ffs(x1) - 1) >> 3);
-			else if (x2) l += 8 + ((uint32_t)(__ffs(x2) - 1) >> 3);
-			else l += 12 + ((uint32_t)(__ffs(x3) - 1) >> 3);
-			break;
-		}
-		l += 16; pa += 4; qa += 4; pw0 = pw[3]; qw0 = qw[3];
 	}
 	return l < maxl ? l : maxl;
 }
 
 // ---- parser warps: one sub-block [sub_lo, sub_hi) at a time, front to back ----
 // The warp looks at a window of 32 consecutive positions (one lane each).  Every lane walks the
-// hash chain of its position, nearest candidate first, keeping the longest match.  As soon as
-// the lane at the head of the token stream has its final answer the token is emitted and the head
-// jumps over the match; once it leaves the window the next window starts where it landed, so
-// positions covered by a match are never searched.  Matches stop at the sub-block end.
-__device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, uint32_t valid_lo,
-				   int depth, int nice, int lazy, uint32_t *tk, uint32_t &nwin)
+// hash chain of its position, nearest candidate first, keeping the longest match; a candidate is
+// only compared in full when the 4 bytes that would make it longer than the best so far agree.
+// As soon as the lane at the head of the token stream has its final answer the token is emitted
+// and the head jumps over the match; once it leaves the window the next window starts where it
+// landed, so positions covered by a match are never searched.  Tokens START inside the sub-block;
+// the last match may run past its end (end_pos), and the stitch pass trims it to a token boundary
+// of the next sub-block.
+__device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, uint32_t valid_lo, uint32_t PE,
+				   int depth, int nice, int lazy, uint32_t *tk, uint32_t &nwin, uint32_t &end_pos)
 {
 	const uint32_t lane = lane_id();
 	const uint32_t lt = (1u << lane) - 1;
+	const uint8_t *ring8 = reinterpret_cast<const uint8_t *>(S.ring32);
 	uint32_t n = 0;
 	uint32_t p = sub_lo;
+	// Chain depth follows the data: a window costs about the same however far it advances, so the
+	// budget of hops per byte stays level when the depth grows with the bytes the recent windows
+	// advanced (long matches = many equally good candidates = the case where deeper chains pay).
+	const int base_depth = depth;
+	uint32_t adv = 32;                                        // running average of the advance per window
 	while (p < sub_hi) {
 		nwin++;
+		depth = min(4 * base_depth, max(base_depth, (int)(base_depth * adv) >> 5));
 		const uint32_t pos = p + lane;
 		const uint32_t nlive = min(32u, sub_hi - p);
 		const bool live = lane < nlive;
-		const uint32_t maxl = live ? min((uint32_t)kMaxMatch, sub_hi - pos) : 0;
+		const uint32_t maxl = live ? min((uint32_t)kMaxMatch, PE - pos) : 0;
 		const uint32_t maxdist = min((uint32_t)kWindow, pos - valid_lo);
-		const uint32_t myb = ring_byte(S.ring32, pos);
+		uint32_t P0, P1, P2, P3;
+		{
+			const uint32_t o = pos & kRingMask, a = o & ~3u, sh = (o & 3) * 8;
+			const uint32_t w0 = ld32(ring8, a), w1 = ld32(ring8, a + 4), w2 = ld32(ring8, a + 8), w3 = ld32(ring8, a + 12), w4 = ld32(ring8, a + 16);
+			P0 = __funnelshift_r(w0, w1, sh); P1 = __funnelshift_r(w1, w2, sh);
+			P2 = __funnelshift_r(w2, w3, sh); P3 = __funnelshift_r(w3, w4, sh);
+		}
+		const uint32_t myb = P0 & 0xffu;
 		uint32_t bl = kMinMatch - 1, bd = 0, acc = 0;
 		uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;
-		uint32_t endb = ring_byte(S.ring32, pos + bl);
+		uint32_t endw = __funnelshift_r(P0, P1, 8);              // the 4 bytes ending at offset bl = 4
 		uint32_t head = 0;
 		bool finished = false;
-		for (int hop = 0; !finished; hop++) {
+		for (int hop = 1; !finished; hop++) {
 			if (d) {
 				acc += d;
 				if (acc > maxdist) {
@@ -292,22 +341,24 @@ __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, ui
 				} else {
 					const uint32_t q = pos - acc;
 					d = S.prev[q & kRingMask];
-					if (ring_byte(S.ring32, q + bl) == endb) {
-						const uint32_t len = match_length(S.ring32, pos, q, maxl);
+					if (load4(ring8, q + bl - 3) == endw) {
+						const uint32_t len = match_length(ring8, pos, q, maxl, P0, P1, P2, P3);
 						if (len > bl) {
 							bl = len; bd = acc;
 							if (len >= (uint32_t)nice || len >= maxl)
 								d = 0;
 							else
-								endb = ring_byte(S.ring32, pos + bl);
+								endw = load4(ring8, pos + bl - 3);
 						}
 					}
 				}
 			}
-			if (hop + 1 >= depth)
+			if (hop < depth) {
+				if (hop & 1)
+					continue;                              // look at the head every other hop
+			} else {
 				d = 0;
-			if ((hop & 1) == 0 && hop + 1 < depth)
-				continue;                                  // look at the head every other hop
+			}
 			const uint32_t dm = __ballot_sync(0xffffffffu, d == 0);
 			if ((dm | ((1u << head) - 1)) == 0xffffffffu)
 				break;                                     // everything from the head on is final
@@ -340,13 +391,13 @@ __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, ui
 			bool take = len != 0;
 			if (take && lazy && len < (uint32_t)lazy && nlen > len)
 				take = false;
-			uint32_t J = live ? lane + (take ? len : 1) : 64;      // next token start (>= 32: leaves the window)
+			uint32_t J = live ? lane + (take ? len : 1) : 64;      // next token start (>= nlive: leaves the window)
 			uint32_t Rl = live ? (1u << lane) : 0;
 #pragma unroll
 			for (int k = 0; k < 5; k++) {
 				const uint32_t tJ = __shfl_sync(0xffffffffu, J, J & 31);
 				const uint32_t tR = __shfl_sync(0xffffffffu, Rl, J & 31);
-				if (J < 32) { Rl |= tR; J = tJ; }
+				if (J < nlive) { Rl |= tR; J = tJ; }
 			}
 			const uint32_t R = __shfl_sync(0xffffffffu, Rl, head);
 			const uint32_t exitJ = __shfl_sync(0xffffffffu, J, head);
@@ -356,8 +407,49 @@ __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, ui
 			head = exitJ;
 		}
 		p += head;
+		adv = (3 * adv + min(head, 256u) + 2) >> 2;
 	}
+	end_pos = p;
 	return n;
+}
+
+// ---- stitch helpers (after the parse): sub-block sb+1 was parsed from its nominal start although
+// the last match of sub-block sb may cover its first bytes.  The match is cut back to the latest
+// token start of sb+1 it reaches, and sb+1 drops the tokens in front of that start.
+__device__ __forceinline__ uint32_t tok_span(uint32_t t) { return tok_is_match(t) ? tok_len(t) : 1; }
+
+// tokens tk[0..cnt) start at `start` and end at `end`; returns the largest j (0..cnt, cnt = "end")
+// whose start s_j <= e, and s_j itself
+__device__ uint32_t scan_head(const uint32_t *tk, uint32_t cnt, uint32_t start, uint32_t end, uint32_t e, uint32_t &s_best)
+{
+	const uint32_t lane = lane_id();
+	uint32_t j_best = 0;
+	s_best = start;
+	for (uint32_t base = 0; base < cnt; base += 32) {
+		const uint32_t i = base + lane;
+		const uint32_t span = i < cnt ? tok_span(tk[i]) : 0;
+		uint32_t incl = span;
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= (uint32_t)o)
+				incl += y;
+		}
+		const uint32_t s_i = start + incl - span;
+		const uint32_t q = __ballot_sync(0xffffffffu, i < cnt && s_i <= e);
+		const uint32_t nq = __popc(q);
+		if (nq) {
+			j_best = base + nq - 1;
+			s_best = __shfl_sync(0xffffffffu, s_i, nq - 1);
+		}
+		start += __shfl_sync(0xffffffffu, incl, 31);
+		if (nq < 32)
+			return j_best;
+	}
+	if (end <= e) {
+		j_best = cnt;
+		s_best = end;
+	}
+	return j_best;
 }
 
 // ---- Huffman: CTA-collective code-length construction ----
@@ -748,11 +840,13 @@ __device__ uint32_t emit_stored(const DeflateJob &J, bool final_flag)
 // per-CTA scratch in global memory (L2-resident): flat token stream | per-position token slots of
 // the sub-blocks | tokens per sub-block | first flat index per sub-block
 __host__ __device__ inline uint32_t scratch_nsub(uint32_t tok_stride) { return tok_stride / kSub + 2; }
-__host__ __device__ inline size_t scratch_words(uint32_t tok_stride) { return 2 * (size_t)tok_stride + 2 * (size_t)scratch_nsub(tok_stride); }
+constexpr int kMeta = 8;     // per sub-block: tokens, end position, tokens dropped in front, kept tokens, flat offset, tail count, tail tokens[2]
+enum { M_CNT = 0, M_END = 1, M_SKIP = 2, M_NEW = 3, M_OFF = 4, M_TAILN = 5, M_TAIL0 = 6, M_TAIL1 = 7 };
+__host__ __device__ inline size_t scratch_words(uint32_t tok_stride) { return 2 * (size_t)tok_stride + kMeta * (size_t)scratch_nsub(tok_stride); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ outs, uint32_t n_jobs,
-	       int depth, int lazy, int nice, uint32_t *tok_scratch, uint32_t tok_stride)
+	       int depth, int lazy, int nice, uint32_t *tok_scratch, uint32_t tok_stride, uint32_t parser_mask)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -760,8 +854,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 	const uint32_t warp = threadIdx.x >> 5;
 	uint32_t *tok = tok_scratch + (size_t)blockIdx.x * scratch_words(tok_stride);
 	uint32_t *tokpos = tok + tok_stride;
-	uint32_t *sub_cnt = tokpos + tok_stride;
-	uint32_t *sub_off = sub_cnt + scratch_nsub(tok_stride);
+	uint32_t *meta = tokpos + tok_stride;
 
 	for (uint32_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
 		const long long tjob0 = clock64();
@@ -772,6 +865,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 		const uint32_t PS = P0 + J.hist_len;              // first byte to compress
 		const uint32_t PE = PS + J.src_len;
 		const uint32_t n_sub = (J.src_len + kSub - 1) / kSub;
+		const uint32_t nblk = (((PE + 15) & ~15u) + kBlk - 1) / kBlk;   // staging blocks, as in producer()
 
 		// ---- init ----
 		for (int i = threadIdx.x; i < kHashSize; i += kThreads)
@@ -780,40 +874,60 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 			S.ll_freq[i] = 0;
 		if (threadIdx.x < 32) {
 			S.d_freq[threadIdx.x] = 0;
-			const uint32_t w = threadIdx.x - 1;               // parser index of warp threadIdx.x
-			S.parse_pos[threadIdx.x] = (threadIdx.x >= 1 && w < n_sub) ? PS + w * kSub : kNone;
+			S.parse_pos[threadIdx.x] = (((parser_mask >> threadIdx.x) & 1) && n_sub) ? PS : kNone;
 		}
 		if (threadIdx.x == 0) {
 			S.n_tok = 0;
-			S.built = 0;
+			S.next_sub = 0;
 			for (int i = 0; i < kSlots; i++)
 				mbar_init(&S.mbar[i], 1);
+			for (int i = 0; i < kDoneSlots; i++)
+				mbar_init(&S.done_bar[i], 1);
 			asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 		}
 		// the ring was last written by ordinary stores (bit-packer staging); TMA writes come next
 		asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 		__syncthreads();
 
-		// ---- LZ77: warp 0 stages + builds chains, warps 1..31 parse sub-blocks round-robin ----
+		// ---- LZ77: warp 0 stages + builds chains, the parser warps take sub-blocks in order ----
 		if (warp == 0) {
 			producer(S, gbase, P0, PE);
-		} else {
+		} else if ((parser_mask >> warp) & 1) {
 			uint32_t nwin = 0;
 			long long busy = 0, waited = 0;
-			for (uint32_t sb = warp - 1; sb < n_sub; sb += kParsers) {
+			for (;;) {
+				uint32_t sb = 0;
+				if (lane_id() == 0)
+					sb = atomicAdd(&S.next_sub, 1u);
+				sb = __shfl_sync(0xffffffffu, sb, 0);
+				if (sb >= n_sub)
+					break;
 				const uint32_t sub_lo = PS + sb * kSub;
 				const uint32_t sub_hi = min(PE, sub_lo + kSub);
 				__syncwarp();
 				if (lane_id() == 0)
 					S.parse_pos[warp] = sub_lo;
 				const long long t0 = clock64();
-				while (S.built < sub_hi)
-					__nanosleep(100);
+				{
+					// chains for every position below sub_hi exist once block bw is done; the wait
+					// suspends the warp in hardware instead of polling (polling steals issue slots
+					// from the producer).  All unfinished sub-blocks lie within 16 KiB of each other,
+					// so the barrier slot cannot be more than one phase away.
+					// (data is needed a full match beyond sub_hi: the last match may run that far)
+					const uint32_t bw = min(nblk - 1, (min(PE, sub_hi + kMaxMatch) + 3) / kBlk);
+					uint64_t *bar = &S.done_bar[bw % kDoneSlots];
+					const uint32_t parity = (bw / kDoneSlots) & 1;
+					while (!mbar_try_wait(bar, parity))
+						;
+				}
 				__threadfence_block();
 				const long long t1 = clock64();
-				const uint32_t cnt = parse_subblock(S, sub_lo, sub_hi, P0, depth, nice, lazy, tokpos + (size_t)sb * kSub, nwin);
-				if (lane_id() == 0)
-					sub_cnt[sb] = cnt;
+				uint32_t end_pos;
+				const uint32_t cnt = parse_subblock(S, sub_lo, sub_hi, P0, PE, depth, nice, lazy, tokpos + (size_t)sb * kSub, nwin, end_pos);
+				if (lane_id() == 0) {
+					meta[sb * kMeta + M_CNT] = cnt;
+					meta[sb * kMeta + M_END] = end_pos;
+				}
 				waited += t1 - t0;
 				busy += clock64() - t1;
 			}
@@ -826,13 +940,51 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 		if (threadIdx.x == 0) {
 			for (int i = 0; i < kSlots; i++)
 				asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&S.mbar[i])) : "memory");
+			for (int i = 0; i < kDoneSlots; i++)
+				asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&S.done_bar[i])) : "memory");
 		}
 
-		// ---- flat token stream + histograms: scan the sub-block counts, then copy ----
+		// ---- stitch: per sub-block, tokens to drop in front and the cut-back last token ----
+		for (uint32_t sb = warp; sb < n_sub; sb += kThreads / 32) {
+			const uint32_t sub_lo = PS + sb * kSub;
+			const uint32_t cnt = meta[sb * kMeta + M_CNT], end = meta[sb * kMeta + M_END];
+			const uint32_t *tk = tokpos + (size_t)sb * kSub;
+			uint32_t s_keep = 0, skip = 0;
+			if (sb > 0)
+				skip = scan_head(tk, cnt, sub_lo, end, meta[(sb - 1) * kMeta + M_END], s_keep);
+			uint32_t tail_n = 0, tail0 = 0, tail1 = 0;
+			if (skip < cnt) {
+				// the last token: cut back to the latest token start of the next sub-block it reaches
+				uint32_t cut = end;
+				if (sb + 1 < n_sub)
+					scan_head(tokpos + (size_t)(sb + 1) * kSub, meta[(sb + 1) * kMeta + M_CNT], min(PE, sub_lo + kSub),
+						  meta[(sb + 1) * kMeta + M_END], end, cut);
+				const uint32_t last = tk[cnt - 1];
+				const uint32_t a = end - tok_span(last);              // where the last token starts
+				const uint32_t L = cut - a;
+				if (L == tok_span(last)) {
+					tail_n = 1; tail0 = last;
+				} else if (L >= 3) {
+					tail_n = 1; tail0 = tok_match(L, tok_dist(last));
+				} else {
+					tail_n = L; tail0 = J.src[a - PS]; tail1 = L == 2 ? J.src[a - PS + 1] : 0;   // 1 or 2 literals
+				}
+			}
+			if (lane_id() == 0) {
+				meta[sb * kMeta + M_SKIP] = skip;
+				meta[sb * kMeta + M_NEW] = skip < cnt ? cnt - skip - 1 + tail_n : 0;
+				meta[sb * kMeta + M_TAILN] = tail_n;
+				meta[sb * kMeta + M_TAIL0] = tail0;
+				meta[sb * kMeta + M_TAIL1] = tail1;
+			}
+		}
+		__syncthreads();
+
+		// ---- flat token stream + histograms: scan the kept counts, then copy ----
 		uint32_t ntok = 0;
 		for (uint32_t base = 0; base < n_sub; base += kThreads) {
 			const uint32_t i = base + threadIdx.x;
-			const uint32_t c = i < n_sub ? sub_cnt[i] : 0;
+			const uint32_t c = i < n_sub ? meta[i * kMeta + M_NEW] : 0;
 			uint32_t incl = c;
 			for (int o = 1; o < 32; o <<= 1) {
 				const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
@@ -856,15 +1008,18 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 			}
 			__syncthreads();
 			if (i < n_sub)
-				sub_off[i] = ntok + H.warp_sums[warp] + incl - c;
+				meta[i * kMeta + M_OFF] = ntok + H.warp_sums[warp] + incl - c;
 			ntok += H.batch_total;
 			__syncthreads();
 		}
 		for (uint32_t sb = warp; sb < n_sub; sb += kThreads / 32) {
-			const uint32_t cnt = sub_cnt[sb], off = sub_off[sb];
-			const uint32_t *src = tokpos + (size_t)sb * kSub;
-			for (uint32_t k = lane_id(); k < cnt; k += 32) {
-				const uint32_t t = src[k];
+			const uint32_t *m = meta + sb * kMeta;
+			const uint32_t cnt = m[M_CNT], skip = m[M_SKIP], nnew = m[M_NEW], off = m[M_OFF], tail_n = m[M_TAILN];
+			const uint32_t body = nnew - tail_n;                          // tokens copied unchanged
+			const uint32_t *src = tokpos + (size_t)sb * kSub + skip;
+			(void)cnt;
+			for (uint32_t k = lane_id(); k < nnew; k += 32) {
+				const uint32_t t = k < body ? src[k] : (k == body ? m[M_TAIL0] : m[M_TAIL1]);
 				tok[off + k] = t;
 				if (tok_is_match(t)) {
 					uint32_t lc, le, lx, dc, de, dx;
@@ -1056,7 +1211,12 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 		cudaMemsetAsync(d_dbg, 0, (size_t)grid * 64, s);
 		cudaMemcpyToSymbolAsync(g_dbg, &d_dbg, sizeof(d_dbg), 0, cudaMemcpyHostToDevice, s);
 	}
-	deflate_kernel<<<grid, kThreads, sizeof(Smem), s>>>(jobs, outs, n_jobs, lp.depth, lp.lazy, lp.nice, tok_scratch, tok_stride);
+	uint32_t parser_mask = 0xFFFFFFFEu;                       // warp 0 is the producer
+	if (const char *pm = getenv("NXGPU_PARSER_MASK"))
+		parser_mask = (uint32_t)strtoul(pm, nullptr, 0) & 0xFFFFFFFEu;
+	if (parser_mask == 0)
+		parser_mask = 2;
+	deflate_kernel<<<grid, kThreads, sizeof(Smem), s>>>(jobs, outs, n_jobs, lp.depth, lp.lazy, lp.nice, tok_scratch, tok_stride, parser_mask);
 	cudaError_t e = cudaGetLastError();
 	if (dbg) {
 		std::vector<unsigned long long> h((size_t)grid * 8);
