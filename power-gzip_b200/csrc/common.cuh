@@ -68,6 +68,7 @@ struct DeflateOut {
 	uint32_t reserved[3];
 };
 
+constexpr uint32_t kWrapJob = 4;         // InflateJob::wrap: NX decompress job semantics (nxu_run_job), raw deflate
 struct InflateJob {
 	const uint8_t *src;
 	uint32_t src_len;
@@ -75,14 +76,26 @@ struct InflateJob {
 	uint8_t *dst;           // dst[-hist_len..-1] window
 	uint32_t dst_cap;
 	uint32_t hist_len;
+	// --- NX job mode only (wrap == kWrapJob): resume state of inc_nx/nxu.h:296-400 ---
+	const uint8_t *dht;     // in_dht bits (from HLIT) when sfbt is 110x
+	uint8_t *out_dht;       // 288 bytes: dynamic header of the block the job stopped in
+	uint32_t dht_bits;
+	uint32_t start_bit;     // bits of src[0] already consumed (0..7)
+	uint32_t sfbt;          // 0xxx fresh block header; 100x stored, 101x fixed, 110x dynamic; bit0 = BFINAL
+	uint32_t rembytecnt;    // stored bytes still to copy (sfbt 100x)
 };
 struct InflateOut {
-	int32_t rc;
+	int32_t rc;             // job mode: NX completion code (0/3 ok, 13 target full, 66/67/68 data)
 	uint32_t out_len;
 	uint32_t in_used;
 	uint32_t flags;
 	uint32_t trailer_crc;   // from the stream (gzip) / adler (zlib)
 	uint32_t trailer_isize;
+	// --- NX job mode ---
+	uint32_t sfbt;          // manual Table 5-3 / 6-4
+	uint32_t subc;          // source bits supplied but not processed
+	uint32_t rembytecnt;
+	uint32_t dhtlen;        // valid bits in out_dht
 	uint32_t reserved[2];
 };
 

@@ -1,0 +1,87 @@
+// ctx.cuh — internal definitions shared by the host-side translation units (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+#include "common.cuh"
+#include "../../include/nxgpu.h"
+
+namespace nxgpu {
+
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	int reserve(size_t bytes)
+	{
+		if (bytes <= cap)
+			return 0;
+		if (p)
+			cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 8 + 4096;
+		if (cudaMalloc(&p, want) != cudaSuccess) {
+			cudaGetLastError();
+			want = bytes;
+			if (cudaMalloc(&p, want) != cudaSuccess) {
+				set_error("cudaMalloc(%zu) failed", want);
+				p = nullptr;
+				return NXGPU_E_MEM;
+			}
+		}
+		cap = want;
+		return 0;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	int reserve(size_t bytes)
+	{
+		if (bytes <= cap)
+			return 0;
+		if (p)
+			cudaFreeHost(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 8 + 4096;
+		if (cudaMallocHost(&p, want) != cudaSuccess) {
+			set_error("cudaMallocHost(%zu) failed", want);
+			cudaGetLastError();
+			return NXGPU_E_MEM;
+		}
+		cap = want;
+		return 0;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct KernelTimer {
+	std::vector<cudaEvent_t> ev;      // start/stop pairs
+	size_t used = 0;
+	double ms_total = 0;
+	uint64_t launches = 0;
+};
+
+} // namespace nxgpu
+
+using namespace nxgpu;
+
+struct nxgpu_ctx {
+	int dev = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t t0 = nullptr, t1 = nullptr;
+	uint64_t launches = 0;
+	DevBuf d_jobs, d_outs, d_tok, d_slots, d_ranges, d_parts, d_rs, d_seeds, d_cks, d_in, d_out, d_offsets, d_misc, d_dst_ptrs, d_dht, d_lz;
+	PinBuf h_jobs, h_outs, h_misc, h_stage;
+	KernelTimer timers[3];           // 0 deflate, 1 inflate, 2 checksum
+	bool timing = true;
+};
+
+
+namespace nxgpu {
+// nxgpu_api.cu: device-resident cores of the batch calls (pointers are device pointers)
+int deflate_device(nxgpu_ctx *c, DeflateJob *jobs_h, size_t n, int level, bool want_cksum);
+int checksum_device(nxgpu_ctx *c, const nxgpu_cksum_item *items, size_t n, int which);
+void timer_begin(nxgpu_ctx *c, int fam);
+void timer_end(nxgpu_ctx *c, int fam);
+}

@@ -169,15 +169,65 @@ __device__ bool build_table(const uint8_t *lens, int n, uint32_t *lut, int lut_b
 	return true;
 }
 
+// dynamic block header from HLIT on (RFC 1951 3.2.7), lane 0 only: code lengths into lens[0..hlit+hdist)
+__device__ int parse_dyn_header(BitReader &br, uint8_t *lens, int &hlit, int &hdist)
+{
+	int rc = 0;
+	br.refill();
+	const uint32_t v = br.get(14);
+	hlit = (int)(v & 31) + 257; hdist = (int)((v >> 5) & 31) + 1;
+	const int hclen = (int)(v >> 10) + 4;
+	if (hlit > 286 || hdist > 30) rc = NXGPU_E_DATA;
+	// code-length code: 19 symbols, <= 7 bits, decoded canonically
+	uint8_t cl[19];
+	for (int i = 0; i < 19; i++) cl[i] = 0;
+	for (int i = 0; i < hclen; i++) { br.refill(); cl[k_clorder[i]] = (uint8_t)br.get(3); }
+	uint16_t ccount[16], csorted[19], coffs[16];
+	for (int i = 0; i < 16; i++) ccount[i] = 0;
+	for (int i = 0; i < 19; i++) ccount[cl[i]]++;
+	ccount[0] = 0;
+	int left = 1;
+	for (int l = 1; l <= 7; l++) { left = (left << 1) - ccount[l]; if (left < 0) rc = NXGPU_E_DATA; }
+	coffs[1] = 0;
+	for (int l = 1; l < 15; l++) coffs[l + 1] = coffs[l] + ccount[l];
+	for (int i = 0; i < 19; i++) if (cl[i]) csorted[coffs[cl[i]]++] = (uint16_t)i;
+	int n = 0;
+	while (!rc && n < hlit + hdist) {
+		br.refill();
+		const int sym = slow_decode(br, ccount, csorted);
+		if (sym < 0) { rc = NXGPU_E_DATA; break; }
+		if (sym < 16) { lens[n++] = (uint8_t)sym; continue; }
+		int rep, val = 0;
+		if (sym == 16) { if (n == 0) { rc = NXGPU_E_DATA; break; } val = lens[n - 1]; rep = 3 + (int)br.get(2); }
+		else if (sym == 17) rep = 3 + (int)br.get(3);
+		else rep = 11 + (int)br.get(7);
+		if (n + rep > hlit + hdist) { rc = NXGPU_E_DATA; break; }
+		while (rep--) lens[n++] = (uint8_t)val;
+	}
+	if (!rc && lens[256] == 0) rc = NXGPU_E_DATA;
+	return rc;
+}
+
 __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 {
 	const uint32_t lane = threadIdx.x & 31;
-	const uint32_t lt = (1u << lane) - 1;
+	const bool job = J.wrap == kWrapJob;     // NX decompress-job semantics: stop at the source end and report where
+	const uint64_t total_bits = (uint64_t)J.src_len * 8;
 	BitReader br;
 	int rc = 0;                      // uniform after each broadcast
 	uint32_t out = 0;
 	uint32_t start = 0, wrap = J.wrap;
 	uint32_t tr_crc = 0, tr_isize = 0, flags = 0;
+	// job mode: set when the source ran out (or the final EOB was seen); lane 0 holds the details
+	bool suspended = false;
+	uint32_t o_sfbt = 0, o_subc = 0, o_rem = 0, o_dhtlen = 0;
+	uint64_t dht_from = 0;           // where the current dynamic header starts (bit offset in dht_src)
+	uint32_t dht_len = 0;
+	bool dht_saved = false;          // the current dynamic table came from J.dht, not from the stream
+	// resume state consumed by the first loop iteration
+	uint32_t resume = job ? (J.sfbt & 0xe) : 0;
+	if (resume != 0x8 && resume != 0xa && resume != 0xc)
+		resume = 0;
 
 	// ---- container header (lane 0), lib/nx_inflate.c:329-730 does this on the host ----
 	if (lane == 0) {
@@ -204,80 +254,106 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 			if (n < 6 || (s[0] & 0x0f) != 8 || (((uint32_t)s[0] << 8 | s[1]) % 31) || (s[1] & 0x20)) rc = NXGPU_E_DATA;
 			start = 2;
 		}
-		if (!rc)
+		if (!rc) {
 			br.init(J.src, J.src_len, start);
+			if (job && J.start_bit) {
+				br.refill();
+				br.drop(J.start_bit & 7);
+			}
+		}
 	}
 	rc = __shfl_sync(0xffffffffu, rc, 0);
 
 	bool final_block = false;
-	while (!rc && !final_block) {
+	while (!rc && !final_block && !suspended) {
 		// ---- block header (lane 0) ----
 		uint32_t btype = 0, stored_len = 0, stored_at = 0;
 		int hlit = 0, hdist = 0;
 		if (lane == 0) {
-			br.refill();
-			const uint32_t h = br.get(3);
-			final_block = h & 1;
-			btype = h >> 1;
-			if (btype == 0) {
-				br.drop(br.cnt & 7);
-				br.refill();
-				const uint32_t v = br.get(32);
-				if (((v ^ (v >> 16)) & 0xffff) != 0xffff) rc = NXGPU_E_DATA;
-				stored_len = v & 0xffff;
-				// give the buffered bytes back: stored data is copied straight from memory
-				stored_at = br.pos - (br.cnt >> 3);
-			} else if (btype == 2) {
-				const uint32_t v = br.get(14);
-				hlit = (int)(v & 31) + 257; hdist = (int)((v >> 5) & 31) + 1;
-				const int hclen = (int)(v >> 10) + 4;
-				if (hlit > 286 || hdist > 30) rc = NXGPU_E_DATA;
-				// code-length code: 19 symbols, <= 7 bits, decoded canonically
-				uint8_t cl[19];
-				for (int i = 0; i < 19; i++) cl[i] = 0;
-				for (int i = 0; i < hclen; i++) { br.refill(); cl[k_clorder[i]] = (uint8_t)br.get(3); }
-				uint16_t ccount[16], csorted[19], coffs[16];
-				for (int i = 0; i < 16; i++) ccount[i] = 0;
-				for (int i = 0; i < 19; i++) ccount[cl[i]]++;
-				ccount[0] = 0;
-				int left = 1;
-				for (int l = 1; l <= 7; l++) { left = (left << 1) - ccount[l]; if (left < 0) rc = NXGPU_E_DATA; }
-				coffs[1] = 0;
-				for (int l = 1; l < 15; l++) coffs[l + 1] = coffs[l] + ccount[l];
-				for (int i = 0; i < 19; i++) if (cl[i]) csorted[coffs[cl[i]]++] = (uint16_t)i;
-				int n = 0;
-				while (!rc && n < hlit + hdist) {
-					br.refill();
-					const int sym = slow_decode(br, ccount, csorted);
-					if (sym < 0) { rc = NXGPU_E_DATA; break; }
-					if (sym < 16) { T.lens[n++] = (uint8_t)sym; continue; }
-					int rep, val = 0;
-					if (sym == 16) { if (n == 0) { rc = NXGPU_E_DATA; break; } val = T.lens[n - 1]; rep = 3 + (int)br.get(2); }
-					else if (sym == 17) rep = 3 + (int)br.get(3);
-					else rep = 11 + (int)br.get(7);
-					if (n + rep > hlit + hdist) { rc = NXGPU_E_DATA; break; }
-					while (rep--) T.lens[n++] = (uint8_t)val;
+			if (resume) {
+				// continue inside the block the previous job stopped in (inc_nx/nxu.h:330-372)
+				final_block = J.sfbt & 1;
+				if (resume == 0x8) {
+					btype = 0;
+					stored_len = J.rembytecnt;
+					stored_at = (uint32_t)((br.bits_used() + 7) >> 3);
+				} else if (resume == 0xa) {
+					btype = 1;
+				} else {
+					btype = 2;
+					BitReader dr;
+					dr.init(J.dht, (J.dht_bits + 7) >> 3, 0);
+					rc = parse_dyn_header(dr, T.lens, hlit, hdist);
+					if (rc || dr.bits_used() > J.dht_bits) rc = 68;
+					dht_saved = true; dht_from = 0; dht_len = J.dht_bits;
 				}
-				if (!rc && T.lens[256] == 0) rc = NXGPU_E_DATA;
-				if (br.overrun()) rc = NXGPU_E_DATA;
-			} else if (btype == 3) {
-				rc = NXGPU_E_DATA;
+			} else {
+				const uint64_t blk = br.bits_used();
+				br.refill();
+				const uint32_t h = br.get(3);
+				final_block = h & 1;
+				btype = h >> 1;
+				if (btype == 0) {
+					br.drop(br.cnt & 7);
+					br.refill();
+					const uint32_t v = br.get(32);
+					if (((v ^ (v >> 16)) & 0xffff) != 0xffff) rc = NXGPU_E_DATA;
+					stored_len = v & 0xffff;
+					// give the buffered bytes back: stored data is copied straight from memory
+					stored_at = br.pos - (br.cnt >> 3);
+				} else if (btype == 2) {
+					dht_from = br.bits_used();
+					rc = parse_dyn_header(br, T.lens, hlit, hdist);
+					dht_len = (uint32_t)(br.bits_used() - dht_from);
+					dht_saved = false;
+				} else if (btype == 3) {
+					rc = NXGPU_E_DATA;
+				}
+				if (br.overrun()) {
+					if (job) {
+						// the header is incomplete: hand all of it back (manual Table 5-3, 111x)
+						const uint32_t f = blk < total_bits ? (J.src[blk >> 3] >> (blk & 7)) & 1 : 0;
+						o_sfbt = 0xe | f;
+						o_subc = (uint32_t)(total_bits - blk);
+						suspended = true;
+						final_block = false;
+						rc = 0;
+					} else {
+						rc = NXGPU_E_DATA;
+					}
+				} else if (rc && job) {
+					rc = 68;
+				}
 			}
 		}
+		resume = 0;
 		rc = __shfl_sync(0xffffffffu, rc, 0);
 		btype = __shfl_sync(0xffffffffu, btype, 0);
 		final_block = __shfl_sync(0xffffffffu, (int)final_block, 0) != 0;
-		if (rc)
+		suspended = __shfl_sync(0xffffffffu, (int)suspended, 0) != 0;
+		if (rc || suspended)
 			break;
 
 		if (btype == 0) {
 			stored_len = __shfl_sync(0xffffffffu, stored_len, 0);
 			stored_at = __shfl_sync(0xffffffffu, stored_at, 0);
-			if (stored_at + stored_len > J.src_len) { rc = NXGPU_E_DATA; break; }
-			if (out + stored_len > J.dst_cap) { rc = NXGPU_E_BUF; break; }
-			for (uint32_t i = lane; i < stored_len; i += 32)
+			uint32_t n = stored_len;
+			if (stored_at + stored_len > J.src_len) {
+				if (!job) { rc = NXGPU_E_DATA; break; }
+				n = J.src_len > stored_at ? J.src_len - stored_at : 0;   // copy what is there, resume later
+			}
+			if (n > J.dst_cap - out) { rc = job ? 13 : NXGPU_E_BUF; break; }
+			for (uint32_t i = lane; i < n; i += 32)
 				J.dst[out + i] = J.src[stored_at + i];
-			out += stored_len;
+			out += n;
+			if (n < stored_len) {
+				o_sfbt = 0x8 | (final_block ? 1u : 0u);
+				o_rem = stored_len - n;
+				o_subc = 0;
+				suspended = true;
+				final_block = false;
+				break;
+			}
 			if (lane == 0)
 				br.init(J.src, J.src_len, stored_at + stored_len);
 			__syncwarp();
@@ -297,14 +373,18 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 		__syncwarp();
 		bool ok = build_table(T.lens, hlit, T.lit, kLitBits, T.lit_count, T.lit_sorted, false);
 		ok = build_table(T.lens + hlit, hdist, T.dist, kDistBits, T.dist_count, T.dist_sorted, true) && ok;
-		if (!ok) { rc = NXGPU_E_DATA; break; }
+		if (!ok) { rc = job ? 68 : NXGPU_E_DATA; break; }
 
 		// ---- symbols ----
 		bool block_done = false;
-		while (!block_done && !rc) {
+		while (!block_done && !rc && !suspended) {
 			uint32_t qn = 0;
 			if (lane == 0) {
 				while (qn < 32) {
+					const uint64_t sym_at = br.bits_used();
+					int err = 0;
+					uint32_t tokv = 0;
+					int kind = 0;                            // 0 literal, 1 match, 2 end of block
 					br.refill();
 					uint32_t e = T.lit[br.peek(kLitBits)];
 					uint32_t type, value, nextra;
@@ -313,35 +393,50 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 						type = (e >> 4) & 3; nextra = (e >> 6) & 15; value = e >> 10;
 					} else {
 						const int sym = slow_decode(br, T.lit_count, T.lit_sorted);
-						if (sym < 0 || sym >= 286) { rc = NXGPU_E_DATA; break; }
-						if (sym < 256) { type = 0; value = sym; nextra = 0; }
+						if (sym < 0 || sym >= 286) { err = 66; type = 2; value = 0; nextra = 0; }
+						else if (sym < 256) { type = 0; value = sym; nextra = 0; }
 						else if (sym == 256) { type = 2; value = 0; nextra = 0; }
 						else { type = 1; value = k_len_base[sym - 257]; nextra = k_len_extra[sym - 257]; }
 					}
-					if (type == 0) { T.q[qn++] = value; continue; }
-					if (type == 2) { block_done = true; break; }
-					const uint32_t len = value + br.get(nextra);
-					br.refill();
-					uint32_t d = T.dist[br.peek(kDistBits)];
-					uint32_t dbase, dextra;
-					if (d & 15) {
-						br.drop(d & 15);
-						dextra = (d >> 4) & 15; dbase = d >> 8;
-					} else {
-						const int ds = slow_decode(br, T.dist_count, T.dist_sorted);
-						if (ds < 0 || ds >= 30) { rc = NXGPU_E_DATA; break; }
-						dbase = k_dist_base[ds]; dextra = k_dist_extra[ds];
+					if (!err && type == 0) { tokv = value; kind = 0; }
+					else if (!err && type == 2) { kind = 2; }
+					else if (!err) {
+						const uint32_t len = value + br.get(nextra);
+						br.refill();
+						uint32_t d = T.dist[br.peek(kDistBits)];
+						uint32_t dbase = 1, dextra = 0;
+						if (d & 15) {
+							br.drop(d & 15);
+							dextra = (d >> 4) & 15; dbase = d >> 8;
+						} else {
+							const int ds = slow_decode(br, T.dist_count, T.dist_sorted);
+							if (ds < 0 || ds >= 30) err = 66;
+							else { dbase = k_dist_base[ds]; dextra = k_dist_extra[ds]; }
+						}
+						const uint32_t dist = dbase + br.get(dextra);
+						tokv = tok_match(len, dist); kind = 1;
 					}
-					const uint32_t dist = dbase + br.get(dextra);
-					T.q[qn++] = tok_match(len, dist);
+					if (br.overrun()) {
+						// the symbol needs bits the source does not have
+						if (job) {
+							o_sfbt = (btype == 1 ? 0xau : 0xcu) | (final_block ? 1u : 0u);
+							o_subc = (uint32_t)(total_bits - sym_at);
+							suspended = true;
+						} else {
+							rc = NXGPU_E_DATA;
+						}
+						break;
+					}
+					if (err) { rc = job ? err : NXGPU_E_DATA; break; }
+					if (kind == 2) { block_done = true; break; }
+					T.q[qn++] = tokv;
 				}
-				if (br.overrun())
-					rc = NXGPU_E_DATA;
 			}
 			__syncwarp();
 			qn = __shfl_sync(0xffffffffu, qn, 0);
 			rc = __shfl_sync(0xffffffffu, rc, 0);
 			block_done = __shfl_sync(0xffffffffu, (int)block_done, 0) != 0;
+			suspended = __shfl_sync(0xffffffffu, (int)suspended, 0) != 0;
 			if (rc)
 				break;
 			// ---- materialise the queue ----
@@ -356,9 +451,9 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 			}
 			const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
 			const uint32_t my_out = out + incl - mylen;
-			if (out + total > J.dst_cap) { rc = NXGPU_E_BUF; break; }
+			if (total > J.dst_cap - out) { rc = job ? 13 : NXGPU_E_BUF; break; }
 			const bool bad = is_m && tok_dist(t) > my_out + J.hist_len;
-			if (__any_sync(0xffffffffu, bad)) { rc = NXGPU_E_DATA; break; }
+			if (__any_sync(0xffffffffu, bad)) { rc = job ? 67 : NXGPU_E_DATA; break; }
 			if (lane < qn && !is_m)
 				J.dst[my_out] = (uint8_t)t;
 			uint32_t mm = __ballot_sync(0xffffffffu, is_m);
@@ -385,9 +480,56 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 				}
 				__syncwarp();
 			}
-			(void)lt;
 			out += total;
 		}
+		if (suspended)
+			final_block = false;
+	}
+
+	if (job) {
+		// ---- NX completion state (lib/nx_inflate.c:1372-1609 reads these) ----
+		const bool in_dyn = suspended && (__shfl_sync(0xffffffffu, o_sfbt, 0) & 0xe) == 0xc;
+		dht_len = __shfl_sync(0xffffffffu, dht_len, 0);
+		const uint32_t from_lo = __shfl_sync(0xffffffffu, (uint32_t)dht_from, 0);
+		const bool saved = __shfl_sync(0xffffffffu, (int)dht_saved, 0) != 0;
+		if (in_dyn && J.out_dht) {
+			// hand the dynamic header back so that the next job can resume inside this block
+			const uint8_t *hs = saved ? J.dht : J.src;
+			const uint32_t hbytes = saved ? (J.dht_bits + 7) >> 3 : J.src_len;
+			const uint32_t nb = (dht_len + 7) >> 3;
+			for (uint32_t i = lane; i < 288; i += 32) {
+				uint32_t v = 0;
+				if (i < nb) {
+					const uint32_t bit = from_lo + 8 * i, by = bit >> 3, sh = bit & 7;
+					const uint32_t a = by < hbytes ? hs[by] : 0, b = by + 1 < hbytes ? hs[by + 1] : 0;
+					v = ((a | (b << 8)) >> sh) & 0xff;
+					if (i == nb - 1 && (dht_len & 7))
+						v &= (1u << (dht_len & 7)) - 1;
+				}
+				J.out_dht[i] = (uint8_t)v;
+			}
+			o_dhtlen = dht_len;
+		}
+		if (lane == 0) {
+			if (!rc && !suspended) {
+				// final EOB seen: sfbt 0000, subc = bits supplied behind it
+				o_sfbt = 0;
+				o_subc = (uint32_t)(total_bits - br.bits_used());
+				flags |= 1;
+			}
+			O.rc = rc;
+			O.out_len = out;
+			O.in_used = J.src_len;
+			O.flags = flags | (wrap << 8);
+			O.trailer_crc = 0;
+			O.trailer_isize = 0;
+			O.sfbt = o_sfbt;
+			O.subc = o_subc;
+			O.rembytecnt = o_rem;
+			O.dhtlen = in_dyn ? dht_len : 0;
+		}
+		(void)o_dhtlen;
+		return;
 	}
 
 	// ---- trailer (lane 0) ----

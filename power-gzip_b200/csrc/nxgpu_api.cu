@@ -24,74 +24,10 @@ void set_error(const char *fmt, ...)
 	va_end(ap);
 }
 
-struct DevBuf {
-	void *p = nullptr;
-	size_t cap = 0;
-	int reserve(size_t bytes)
-	{
-		if (bytes <= cap)
-			return 0;
-		if (p)
-			cudaFree(p);
-		p = nullptr; cap = 0;
-		size_t want = bytes + bytes / 8 + 4096;
-		if (cudaMalloc(&p, want) != cudaSuccess) {
-			cudaGetLastError();
-			want = bytes;
-			if (cudaMalloc(&p, want) != cudaSuccess) {
-				set_error("cudaMalloc(%zu) failed", want);
-				p = nullptr;
-				return NXGPU_E_MEM;
-			}
-		}
-		cap = want;
-		return 0;
-	}
-	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-struct PinBuf {
-	void *p = nullptr;
-	size_t cap = 0;
-	int reserve(size_t bytes)
-	{
-		if (bytes <= cap)
-			return 0;
-		if (p)
-			cudaFreeHost(p);
-		p = nullptr; cap = 0;
-		size_t want = bytes + bytes / 8 + 4096;
-		if (cudaMallocHost(&p, want) != cudaSuccess) {
-			set_error("cudaMallocHost(%zu) failed", want);
-			cudaGetLastError();
-			return NXGPU_E_MEM;
-		}
-		cap = want;
-		return 0;
-	}
-	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-};
-
-struct KernelTimer {
-	std::vector<cudaEvent_t> ev;      // start/stop pairs
-	size_t used = 0;
-	double ms_total = 0;
-	uint64_t launches = 0;
-};
-
 } // namespace nxgpu
 
+#include "ctx.cuh"
 using namespace nxgpu;
-
-struct nxgpu_ctx {
-	int dev = 0;
-	cudaStream_t stream = nullptr;
-	cudaEvent_t t0 = nullptr, t1 = nullptr;
-	uint64_t launches = 0;
-	DevBuf d_jobs, d_outs, d_tok, d_slots, d_ranges, d_parts, d_rs, d_seeds, d_cks, d_in, d_out, d_offsets, d_misc, d_dst_ptrs;
-	PinBuf h_jobs, h_outs, h_misc, h_stage;
-	KernelTimer timers[3];           // 0 deflate, 1 inflate, 2 checksum
-	bool timing = true;
-};
 
 namespace {
 
@@ -103,7 +39,8 @@ int fam_index(const char *f)
 	return -1;
 }
 
-void timer_begin(nxgpu_ctx *c, int fam)
+} // namespace
+void nxgpu::timer_begin(nxgpu_ctx *c, int fam)
 {
 	KernelTimer &t = c->timers[fam];
 	if (!c->timing)
@@ -115,7 +52,7 @@ void timer_begin(nxgpu_ctx *c, int fam)
 	}
 	cudaEventRecord(t.ev[t.used], c->stream);
 }
-void timer_end(nxgpu_ctx *c, int fam)
+void nxgpu::timer_end(nxgpu_ctx *c, int fam)
 {
 	KernelTimer &t = c->timers[fam];
 	c->launches++;
@@ -125,6 +62,7 @@ void timer_end(nxgpu_ctx *c, int fam)
 	t.used += 2;
 	t.launches++;
 }
+namespace {
 void timer_collect(nxgpu_ctx *c)
 {
 	for (int f = 0; f < 3; f++) {
@@ -209,7 +147,7 @@ void nxgpu_close(nxgpu_ctx *c)
 	cudaSetDevice(c->dev);
 	cudaStreamSynchronize(c->stream);
 	DevBuf *db[] = { &c->d_jobs, &c->d_outs, &c->d_tok, &c->d_slots, &c->d_ranges, &c->d_parts, &c->d_rs, &c->d_seeds,
-			 &c->d_cks, &c->d_in, &c->d_out, &c->d_offsets, &c->d_misc, &c->d_dst_ptrs };
+			 &c->d_cks, &c->d_in, &c->d_out, &c->d_offsets, &c->d_misc, &c->d_dst_ptrs, &c->d_dht, &c->d_lz };
 	for (DevBuf *b : db) b->release();
 	PinBuf *pb[] = { &c->h_jobs, &c->h_outs, &c->h_misc, &c->h_stage };
 	for (PinBuf *b : pb) b->release();
@@ -326,7 +264,7 @@ uint32_t nxgpu_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2)
 
 // Device-resident inputs: items[i].src are device pointers.  Cuts big items into ranges so that
 // the whole GPU works on one buffer; results land in d_cks (crc[n], adler[n]).
-static int checksum_device(nxgpu_ctx *c, const nxgpu_cksum_item *items, size_t n, int which)
+extern "C++" int nxgpu::checksum_device(nxgpu_ctx *c, const nxgpu_cksum_item *items, size_t n, int which)
 {
 	uint64_t total = 0;
 	for (size_t i = 0; i < n; i++) total += items[i].len;
@@ -427,15 +365,20 @@ int nxgpu_adler32(nxgpu_ctx *c, uint32_t seed, const void *src, uint64_t len, in
 
 // Core: all pointers in `jobs_h` are device pointers except `out`, which this routine assigns to
 // private 16-byte aligned slots.  Leaves DeflateOut[n] in d_outs and per-item crc/adler in d_cks.
-static int deflate_device(nxgpu_ctx *c, DeflateJob *jobs_h, size_t n, int level, bool want_cksum)
+extern "C++" int nxgpu::deflate_device(nxgpu_ctx *c, DeflateJob *jobs_h, size_t n, int level, bool want_cksum)
 {
 	int rc;
 	if (level <= 0) level = 6;       // lib/nx_deflate.c:655-658 maps level 0 to 6 as well
 	if (level > 9) level = 9;
 	size_t slot_total = 0;
 	uint32_t max_len = 0;
+	// worst case per item: stored blocks; an nxu_run_job item (no joiner, caller's table, no stored
+	// fallback) can come out at up to 15 bits per literal before the caller sees CC=64 and re-wraps it
+	auto slot_cap = [](const DeflateJob &j) -> uint32_t {
+		return (j.flags & NXGPU_F_NO_JOINER) ? 2 * j.src_len + 1024 : nxgpu_deflate_bound(j.src_len);
+	};
 	for (size_t i = 0; i < n; i++) {
-		slot_total += align_up(nxgpu_deflate_bound(jobs_h[i].src_len) + 16, 16);
+		slot_total += align_up(slot_cap(jobs_h[i]) + 16, 16);
 		if (jobs_h[i].src_len > max_len) max_len = jobs_h[i].src_len;
 	}
 	const int grid = (int)(n < (size_t)kNumSMs ? n : (size_t)kNumSMs);
@@ -447,7 +390,7 @@ static int deflate_device(nxgpu_ctx *c, DeflateJob *jobs_h, size_t n, int level,
 	size_t o = 0;
 	for (size_t i = 0; i < n; i++) {
 		jobs_h[i].out = static_cast<uint8_t *>(c->d_slots.p) + o;
-		jobs_h[i].out_cap = nxgpu_deflate_bound(jobs_h[i].src_len);
+		jobs_h[i].out_cap = slot_cap(jobs_h[i]);
 		o += align_up(jobs_h[i].out_cap + 16, 16);
 	}
 	NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_jobs.p, jobs_h, n * sizeof(DeflateJob), cudaMemcpyHostToDevice, c->stream));

@@ -1,0 +1,177 @@
+#!/usr/bin/env python3
+"""Drives the reference's UNMODIFIED zlib-compatible surface (libnxz.h:119-192: compress2 /
+uncompress / deflate / inflate / crc32 / adler32) in NX mode (NX_GZIP_TYPE_SELECTOR=2) through a
+build of its host code whose six boundary symbols come from either engine:
+
+    oracle/_ref/libnxz_ref.so   nxu_run_job = oracle/nxemu.c (CPU, the checker)
+    oracle/_ref/libnxz_gpu.so   nxu_run_job = power-gzip_b200/libnxgpu.so (the product)
+
+Run as a subprocess (the selector is read when the library is loaded).  Prints one JSON line.
+Mirrors the round trips of the reference's test/test_deflate.c and test/test_inflate.c: output of
+the nx deflate must inflate with system zlib, and streams made by system zlib must inflate through
+nx, in one shot and in small pieces.
+usage: nx_dropin_driver.py <libnxz .so> [size_log2]"""
+import ctypes as C
+import faulthandler
+import gzip
+import json
+import os
+import random
+import sys
+import zlib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ["NX_GZIP_TYPE_SELECTOR"] = "2"          # lib/nx_zlib.c: 2 = NX only, no software fallback
+os.environ.setdefault("NX_GZIP_LOGFILE", "/tmp/nx_dropin.log")
+if os.environ.get("NX_DRIVER_WATCHDOG"):
+    faulthandler.dump_traceback_later(int(os.environ["NX_DRIVER_WATCHDOG"]), exit=True)
+lib = C.CDLL(sys.argv[1], mode=C.RTLD_GLOBAL)
+log2 = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+
+
+class ZStream(C.Structure):
+    _fields_ = [("next_in", C.c_void_p), ("avail_in", C.c_uint), ("total_in", C.c_ulong),
+                ("next_out", C.c_void_p), ("avail_out", C.c_uint), ("total_out", C.c_ulong),
+                ("msg", C.c_char_p), ("state", C.c_void_p), ("zalloc", C.c_void_p), ("zfree", C.c_void_p),
+                ("opaque", C.c_void_p), ("data_type", C.c_int), ("adler", C.c_ulong), ("reserved", C.c_ulong)]
+
+
+lib.compress2.argtypes = [C.c_void_p, C.POINTER(C.c_ulong), C.c_void_p, C.c_ulong, C.c_int]
+lib.uncompress.argtypes = [C.c_void_p, C.POINTER(C.c_ulong), C.c_void_p, C.c_ulong]
+lib.compressBound.restype = C.c_ulong
+lib.compressBound.argtypes = [C.c_ulong]
+lib.crc32.restype = C.c_ulong
+lib.crc32.argtypes = [C.c_ulong, C.c_void_p, C.c_uint]
+lib.adler32.restype = C.c_ulong
+lib.adler32.argtypes = [C.c_ulong, C.c_void_p, C.c_uint]
+for f in ("deflateInit2_", "inflateInit2_"):
+    getattr(lib, f).restype = C.c_int
+lib.deflateInit2_.argtypes = [C.POINTER(ZStream), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+lib.inflateInit2_.argtypes = [C.POINTER(ZStream), C.c_int, C.c_char_p, C.c_int]
+for f in ("deflate", "inflate"):
+    getattr(lib, f).argtypes = [C.POINTER(ZStream), C.c_int]
+for f in ("deflateEnd", "inflateEnd"):
+    getattr(lib, f).argtypes = [C.POINTER(ZStream)]
+VER = b"1.2.11"
+Z_NO_FLUSH, Z_SYNC_FLUSH, Z_FULL_FLUSH, Z_FINISH, Z_OK, Z_STREAM_END, Z_BUF_ERROR = 0, 2, 3, 4, 0, 1, -5
+
+
+def nx_compress2(data, level):
+    cap = lib.compressBound(len(data)) + 64
+    out = C.create_string_buffer(cap)
+    n = C.c_ulong(cap)
+    rc = lib.compress2(out, C.byref(n), data, len(data), level)
+    assert rc == 0, f"compress2 rc={rc}"
+    return out.raw[: n.value]
+
+
+def nx_uncompress(blob, n_out):
+    out = C.create_string_buffer(max(n_out, 1))
+    n = C.c_ulong(n_out)
+    rc = lib.uncompress(out, C.byref(n), blob, len(blob))
+    assert rc == 0, f"uncompress rc={rc}"
+    return out.raw[: n.value]
+
+
+def nx_deflate_stream(data, wbits, in_piece, out_piece, flush_every=0):
+    """deflate() fed in_piece bytes at a time, drained out_piece bytes at a time"""
+    s = ZStream()
+    assert lib.deflateInit2_(C.byref(s), 6, 8, wbits, 8, 0, VER, C.sizeof(ZStream)) == 0
+    src = C.create_string_buffer(data, len(data))
+    obuf = C.create_string_buffer(out_piece)
+    out = bytearray()
+    pos, k = 0, 0
+    while True:
+        take = min(in_piece, len(data) - pos)
+        s.next_in = C.addressof(src) + pos
+        s.avail_in = take
+        pos += take
+        last = pos == len(data)
+        k += 1
+        flush = Z_FINISH if last else (Z_FULL_FLUSH if flush_every and k % flush_every == 0 else Z_NO_FLUSH)
+        while True:
+            s.next_out = C.addressof(obuf)
+            s.avail_out = out_piece
+            rc = lib.deflate(C.byref(s), flush)
+            assert rc in (Z_OK, Z_STREAM_END, Z_BUF_ERROR), f"deflate rc={rc}"
+            out += obuf.raw[: out_piece - s.avail_out]
+            if rc == Z_STREAM_END:
+                break
+            if s.avail_in == 0 and s.avail_out != 0 and flush != Z_FINISH:
+                break
+        if last:
+            assert rc == Z_STREAM_END
+            break
+    lib.deflateEnd(C.byref(s))
+    return bytes(out)
+
+
+def nx_inflate_stream(blob, wbits, in_piece, out_piece, expect_len):
+    s = ZStream()
+    assert lib.inflateInit2_(C.byref(s), wbits, VER, C.sizeof(ZStream)) == 0
+    src = C.create_string_buffer(blob, len(blob))
+    obuf = C.create_string_buffer(out_piece)
+    out = bytearray()
+    pos = 0
+    rc = Z_OK
+    guard = 0
+    while rc != Z_STREAM_END:
+        if s.avail_in == 0 and pos < len(blob):
+            take = min(in_piece, len(blob) - pos)
+            s.next_in = C.addressof(src) + pos
+            s.avail_in = take
+            pos += take
+        s.next_out = C.addressof(obuf)
+        s.avail_out = out_piece
+        rc = lib.inflate(C.byref(s), Z_NO_FLUSH)
+        assert rc in (Z_OK, Z_STREAM_END, Z_BUF_ERROR), f"inflate rc={rc} after {len(out)} bytes"
+        out += obuf.raw[: out_piece - s.avail_out]
+        guard += 1
+        assert guard < 10_000_000 and len(out) <= expect_len, "inflate does not terminate"
+        if rc == Z_BUF_ERROR and pos >= len(blob) and s.avail_out != 0:
+            raise AssertionError("inflate starved")
+    lib.inflateEnd(C.byref(s))
+    return bytes(out)
+
+
+alice = gzip.decompress(open(os.path.join(ROOT, "tests", "golden", "alice29.txt.gz"), "rb").read())
+rnd = random.Random(7)
+text = (alice * ((1 << log2) // len(alice) + 1))[: 1 << log2]
+cases = {
+    "alice": alice,
+    "text": text,
+    "zeros": bytes(300000),
+    "random": rnd.randbytes(100000),
+    "tiny": b"hello hello hello hello",
+}
+report = {"lib": os.path.basename(sys.argv[1]), "cases": {}}
+for name, data in cases.items():
+    r = {}
+    print("case", name, len(data), file=sys.stderr, flush=True)
+    # libnxz.h compress2 / uncompress (lib/nx_compress.c:82, lib/nx_uncompr.c:91)
+    z = nx_compress2(data, 6)
+    assert zlib.decompress(z) == data, f"{name}: zlib cannot decode nx compress2 output"
+    r["compress2"] = len(z)
+    assert nx_uncompress(zlib.compress(data, 6), len(data)) == data, f"{name}: nx uncompress(zlib -6) differs"
+    assert nx_uncompress(z, len(data)) == data, f"{name}: nx uncompress(nx compress2) differs"
+    # checksums through the exported crc32/adler32 (lib/nx_crc.c:437, lib/nx_adler32.c:182)
+    assert lib.crc32(0, data, len(data)) == zlib.crc32(data)
+    assert lib.adler32(1, data, len(data)) == zlib.adler32(data)
+    # streaming deflate: gzip wrapper, small pieces, full flushes in between
+    g = nx_deflate_stream(data, 31, 60000, 50000, flush_every=3)
+    assert gzip.decompress(g) == data, f"{name}: gzip cannot decode streamed nx deflate"
+    r["deflate_gzip_stream"] = len(g)
+    raw = nx_deflate_stream(data, -15, 1 << 20, 1 << 20)
+    assert zlib.decompress(raw, -15) == data
+    # streaming inflate of foreign streams, cut at awkward places (resume protocol, lib/nx_inflate.c:1447-1609)
+    for lvl, wb in ((6, 31), (1, 15), (9, -15), (0, 31)):
+        co = zlib.compressobj(lvl, zlib.DEFLATED, wb)
+        blob = co.compress(data) + co.flush()
+        for in_piece, out_piece in ((1 << 20, 1 << 20), (4099, 70001), (len(blob) // 3 + 1, 1 << 16)):
+            got = nx_inflate_stream(blob, wb, in_piece, out_piece, len(data))
+            assert got == data, f"{name}: nx inflate(level {lvl}, wbits {wb}, pieces {in_piece}/{out_piece}) differs"
+    fx = zlib.compressobj(6, zlib.DEFLATED, -15, 8, zlib.Z_FIXED)
+    blob = fx.compress(data) + fx.flush()
+    assert nx_inflate_stream(blob, -15, 5000, 9000, len(data)) == data
+    report["cases"][name] = r
+print(json.dumps(report))
