@@ -46,6 +46,17 @@ def load_pkg():
     return mod
 
 
+def ncu_traffic_per_input_byte():
+    """DRAM bytes (read + write) per uncompressed input byte of deflate_kernel, from the committed
+    `ncu --set full` capture summarised in profiles/ (None if absent)."""
+    p = os.path.join(ROOT, "profiles", "ncu_deflate_summary.json")
+    try:
+        j = json.load(open(p))
+        return (j["dram_bytes_read"] + j["dram_bytes_write"]) / j["input_bytes"]
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -175,6 +186,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pg = load_pkg()
+    from power_gzip_b200 import multi
     eng = pg.Engine(local)
     lib = eng.lib
     hbm_peak, peak_kind = peaks()
@@ -202,33 +214,18 @@ def main():
             res = eng.deflate_stream_device(src.data_ptr(), n, dst.data_ptr(), cap, level=level, wrap=pg.WRAP_GZIP, chunk=CHUNK)
             return eng.timer_stop(), res, res.out_len
         # rank r owns bytes [r*n, (r+1)*n) of the N*n stream: raw deflate of its slice, joiner unless last
-        wrap = pg.WRAP_RAW
+        wrap = pg.WRAP_RAW if rank == world - 1 else pg.WRAP_RAW_CONT
         res = eng.deflate_stream_device(src.data_ptr(), n, dst.data_ptr(), cap, level=level, wrap=wrap, chunk=CHUNK)
         ms = eng.timer_stop()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
-        meta = torch.tensor([res.out_len, res.crc32], dtype=torch.int64, device="cuda")
-        allm = [torch.empty_like(meta) for _ in range(world)]
-        dist.all_gather(allm, meta)                                  # sizes + crcs (8 numbers)
-        sizes = [int(m[0]) for m in allm]
-        offs = [10]
-        for s_ in sizes:
-            offs.append(offs[-1] + s_)                                 # exclusive scan behind the gzip header
-        total = offs[-1] + 8
+        # sizes + CRCs all-gathered, exclusive scan, ranges sent to rank 0 at their offsets, CRCs folded
+        # (power-gzip_b200/multi.py; same functions the gloo tests cover)
+        out, total, crc, _ = multi.stitch_to_rank0(dist, torch, dst, int(res.out_len), int(res.crc32), n,
+                                                   eng.crc32_combine, stitched[0])
         if rank == 0:
-            if stitched[0] is None or stitched[0].numel() < total:
-                stitched[0] = torch.empty(total + (total >> 3), dtype=torch.uint8, device="cuda")
-            out = stitched[0]
-            out[offs[0]:offs[1]].copy_(dst[:sizes[0]])
-            reqs = [dist.irecv(out[offs[r]:offs[r + 1]], src=r) for r in range(1, world)]
-            for q in reqs:
-                q.wait()
-            crc = 0
-            for r in range(world):
-                crc = eng.crc32_combine(crc, int(allm[r][1]) & 0xffffffff, n)     # lib/nx_crc.c:374
+            stitched[0] = out
             last_crc[0] = crc
-        else:
-            dist.send(dst[:sizes[rank]], dst=0)
         t1.record(); t1.synchronize()
         return ms + t0.elapsed_time(t1), res, total
 
@@ -303,6 +300,18 @@ def main():
             assert got == want, "zlib does not reproduce the input from the GPU stream"
             assert res_h.crc32 == res6.crc32
         extra["verified"] = f"zlib inflate of the e2e output reproduces the first {check_n >> 20} MiB; crc32 {res6.crc32:08x}"
+        if world > 1 and stitched[0] is not None:
+            # the stitched N-GPU stream is ONE gzip member: inflate all of it with zlib, compare crc32 + length
+            blob = stitched[0][:total6].cpu().numpy().tobytes()
+            d = zlib.decompressobj(31)
+            crc, length, pos = 0, 0, 0
+            while pos < len(blob):
+                piece = d.decompress(blob[pos:pos + (8 << 20)])
+                pos += 8 << 20
+                crc = zlib.crc32(piece, crc); length += len(piece)
+            tail = d.flush(); crc = zlib.crc32(tail, crc); length += len(tail)
+            assert d.eof and length == world * n and crc == last_crc[0], (d.eof, length, world * n, hex(crc), hex(last_crc[0]))
+            extra["verified_stitched"] = f"zlib inflates the {world}-GPU stream: {length} bytes, crc32 {crc:08x} == folded crc"
 
     if not args.skip_extra:
         # ---- level 1 ----
@@ -362,7 +371,8 @@ def main():
                        "parallelism": f"chunk-range x{world}" if world > 1 else "1 GPU"},
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_kind, "kernel": "deflate_kernel",
+                         "traffic": (ncu_traffic_per_input_byte() * n) if ncu_traffic_per_input_byte() else None,
+                         "peak_source": peak_kind, "kernel": "deflate_kernel",
                          "note": "algorithmic bytes = U + C per launch (SURVEY.md §8d); LZ77 search is latency/issue bound, not HBM bound"},
             "cpu_baseline": cpu, "clocks": sampler.summary(), "extra": extra,
         }

@@ -103,7 +103,10 @@ unsigned int __crc32_vpmsum(unsigned int crc, const void *p, unsigned long len);
 typedef struct nxgpu_ctx nxgpu_ctx;     /* one CUDA device + stream + scratch  */
 
 enum { NXGPU_MEM_HOST = 0, NXGPU_MEM_DEVICE = 1 };
-enum { NXGPU_WRAP_RAW = 0, NXGPU_WRAP_ZLIB = 1, NXGPU_WRAP_GZIP = 2, NXGPU_WRAP_AUTO = 3 };
+enum { NXGPU_WRAP_RAW = 0, NXGPU_WRAP_ZLIB = 1, NXGPU_WRAP_GZIP = 2, NXGPU_WRAP_AUTO = 3,
+       /* deflate_stream only: raw deflate that is NOT the end of the stream — every chunk, the last
+        * one too, ends on the joiner and none carries BFINAL (a GPU's range of a multi-GPU stream) */
+       NXGPU_WRAP_RAW_CONT = 5 };
 
 /* status codes: 0 and the zlib-style negatives, plus NX completion codes where
  * a caller wants them (inc_nx/nxu.h:823-857) */

@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnxgpu.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
-WRAP_RAW, WRAP_ZLIB, WRAP_GZIP, WRAP_AUTO = 0, 1, 2, 3
+WRAP_RAW, WRAP_ZLIB, WRAP_GZIP, WRAP_AUTO, WRAP_RAW_CONT = 0, 1, 2, 3, 5
 F_FINAL, F_FIXED, F_NO_JOINER = 1, 2, 4
 E_NODEV, E_ARG, E_DATA, E_MEM, E_BUF = -100, -2, -3, -4, -5
 

@@ -113,12 +113,12 @@ __host__ __device__ inline LevelParams level_params(int level)
 	case 2: return { 3, 0, 64 };
 	case 3: return { 4, 0, 128 };
 	case 4: return { 4, 16, 128 };
-	case 5: return { 8, 32, 258 };
-	case 6: return { 12, 32, 258 };
+	case 5: return { 10, 32, 258 };
+	case 6: return { 14, 32, 258 };
 	case 7: return { 16, 64, 258 };
 	case 8: return { 24, 258, 258 };
 	case 9: return { 48, 258, 258 };
-	default: return { 12, 32, 258 };
+	default: return { 14, 32, 258 };
 	}
 }
 
@@ -129,7 +129,8 @@ void set_error(const char *fmt, ...);
 size_t deflate_smem_bytes();
 size_t deflate_scratch_words(uint32_t tok_stride);   // per-CTA token scratch (u32 words)
 cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_jobs, int level,
-			   uint32_t *tok_scratch, uint32_t tok_stride, int grid, cudaStream_t s);
+			   uint32_t *tok_scratch, uint32_t tok_stride, int grid, cudaStream_t s,
+			   uint32_t *job_counter, const uint32_t *ready, uint32_t jobs_per_flag);
 cudaError_t launch_inflate(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s);
 // checksum.cu
 cudaError_t checksum_init_tables();

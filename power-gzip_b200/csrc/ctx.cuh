@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <utility>
 #include <vector>
 #include "common.cuh"
 #include "../../include/nxgpu.h"
@@ -69,10 +70,14 @@ using namespace nxgpu;
 struct nxgpu_ctx {
 	int dev = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t copy_stream = nullptr;      // uploads of host-pointer streams, overlapped with compute
+	cudaEvent_t ev_main = nullptr, ev_copy = nullptr;
+	const uint32_t *ready_flags = nullptr;   // set while a host-pointer stream is being uploaded slice by slice
+	uint32_t jobs_per_flag = 0;
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
 	uint64_t launches = 0;
-	DevBuf d_jobs, d_outs, d_tok, d_slots, d_ranges, d_parts, d_rs, d_seeds, d_cks, d_in, d_out, d_offsets, d_misc, d_dst_ptrs, d_dht, d_lz;
-	PinBuf h_jobs, h_outs, h_misc, h_stage;
+	DevBuf d_jobs, d_outs, d_tok, d_slots, d_ranges, d_parts, d_rs, d_seeds, d_cks, d_in, d_out, d_offsets, d_misc, d_dst_ptrs, d_dht, d_lz, d_ctr, d_flags;
+	PinBuf h_jobs, h_outs, h_misc, h_stage, h_ones;
 	KernelTimer timers[3];           // 0 deflate, 1 inflate, 2 checksum
 	bool timing = true;
 };

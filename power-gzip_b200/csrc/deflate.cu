@@ -846,7 +846,8 @@ __host__ __device__ inline size_t scratch_words(uint32_t tok_stride) { return 2 
 
 __global__ void __launch_bounds__(kThreads, 1)
 deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ outs, uint32_t n_jobs,
-	       int depth, int lazy, int nice, uint32_t *tok_scratch, uint32_t tok_stride, uint32_t parser_mask)
+	       int depth, int lazy, int nice, uint32_t *tok_scratch, uint32_t tok_stride, uint32_t parser_mask,
+	       uint32_t *job_counter, const volatile uint32_t *ready, uint32_t jobs_per_flag)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -856,7 +857,22 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 	uint32_t *tokpos = tok + tok_stride;
 	uint32_t *meta = tokpos + tok_stride;
 
-	for (uint32_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+	for (;;) {
+		// jobs are handed out in order; when the input is still being uploaded (host-pointer streams)
+		// ready[k] turns non-zero once the slice holding jobs [k*jobs_per_flag, (k+1)*jobs_per_flag) has landed
+		if (threadIdx.x == 0) {
+			const uint32_t j = atomicAdd(job_counter, 1u);
+			if (j < n_jobs && ready) {
+				while (ready[j / jobs_per_flag] == 0)
+					__nanosleep(1000);
+				__threadfence();
+			}
+			S.misc[7] = j;
+		}
+		__syncthreads();
+		const uint32_t job = S.misc[7];
+		if (job >= n_jobs)
+			break;
 		const long long tjob0 = clock64();
 		const DeflateJob J = jobs[job];
 		const uintptr_t first = reinterpret_cast<uintptr_t>(J.src) - J.hist_len;
@@ -1190,7 +1206,8 @@ size_t deflate_smem_bytes() { return sizeof(Smem); }
 size_t deflate_scratch_words(uint32_t tok_stride) { return scratch_words(tok_stride); }
 
 cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_jobs, int level,
-			   uint32_t *tok_scratch, uint32_t tok_stride, int grid, cudaStream_t s)
+			   uint32_t *tok_scratch, uint32_t tok_stride, int grid, cudaStream_t s,
+			   uint32_t *job_counter, const uint32_t *ready, uint32_t jobs_per_flag)
 {
 	static bool configured = false;
 	if (!configured) {
@@ -1216,7 +1233,11 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 		parser_mask = (uint32_t)strtoul(pm, nullptr, 0) & 0xFFFFFFFEu;
 	if (parser_mask == 0)
 		parser_mask = 2;
-	deflate_kernel<<<grid, kThreads, sizeof(Smem), s>>>(jobs, outs, n_jobs, lp.depth, lp.lazy, lp.nice, tok_scratch, tok_stride, parser_mask);
+	cudaError_t me = cudaMemsetAsync(job_counter, 0, sizeof(uint32_t), s);
+	if (me != cudaSuccess)
+		return me;
+	deflate_kernel<<<grid, kThreads, sizeof(Smem), s>>>(jobs, outs, n_jobs, lp.depth, lp.lazy, lp.nice, tok_scratch, tok_stride, parser_mask,
+							    job_counter, ready, jobs_per_flag ? jobs_per_flag : 1);
 	cudaError_t e = cudaGetLastError();
 	if (dbg) {
 		std::vector<unsigned long long> h((size_t)grid * 8);

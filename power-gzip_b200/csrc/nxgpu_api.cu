@@ -97,6 +97,7 @@ __global__ void write_bytes_kernel(uint8_t *dst, uint64_t v, int n)
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr size_t kSliceChunks = 2 * kNumSMs;   // host-pointer streams are uploaded and compressed in slices of this many chunks (whole waves of the persistent grid)
 
 } // namespace
 
@@ -133,6 +134,9 @@ int nxgpu_open(int dev, nxgpu_ctx **out)
 	nxgpu_ctx *c = new nxgpu_ctx();
 	c->dev = dev;
 	NXGPU_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	NXGPU_CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	NXGPU_CUDA_OK(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+	NXGPU_CUDA_OK(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
 	NXGPU_CUDA_OK(cudaEventCreate(&c->t0));
 	NXGPU_CUDA_OK(cudaEventCreate(&c->t1));
 	NXGPU_CUDA_OK(checksum_init_tables());
@@ -147,13 +151,16 @@ void nxgpu_close(nxgpu_ctx *c)
 	cudaSetDevice(c->dev);
 	cudaStreamSynchronize(c->stream);
 	DevBuf *db[] = { &c->d_jobs, &c->d_outs, &c->d_tok, &c->d_slots, &c->d_ranges, &c->d_parts, &c->d_rs, &c->d_seeds,
-			 &c->d_cks, &c->d_in, &c->d_out, &c->d_offsets, &c->d_misc, &c->d_dst_ptrs, &c->d_dht, &c->d_lz };
+			 &c->d_cks, &c->d_in, &c->d_out, &c->d_offsets, &c->d_misc, &c->d_dst_ptrs, &c->d_dht, &c->d_lz, &c->d_ctr, &c->d_flags };
 	for (DevBuf *b : db) b->release();
-	PinBuf *pb[] = { &c->h_jobs, &c->h_outs, &c->h_misc, &c->h_stage };
+	PinBuf *pb[] = { &c->h_jobs, &c->h_outs, &c->h_misc, &c->h_stage, &c->h_ones };
 	for (PinBuf *b : pb) b->release();
 	for (int f = 0; f < 3; f++)
 		for (cudaEvent_t e : c->timers[f].ev) cudaEventDestroy(e);
 	cudaEventDestroy(c->t0); cudaEventDestroy(c->t1);
+	cudaEventDestroy(c->ev_main);
+	cudaEventDestroy(c->ev_copy);
+	cudaStreamDestroy(c->copy_stream);
 	cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -394,9 +401,14 @@ extern "C++" int nxgpu::deflate_device(nxgpu_ctx *c, DeflateJob *jobs_h, size_t 
 		o += align_up(jobs_h[i].out_cap + 16, 16);
 	}
 	NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_jobs.p, jobs_h, n * sizeof(DeflateJob), cudaMemcpyHostToDevice, c->stream));
+	// one persistent launch; jobs are claimed in order.  For host-pointer streams the kernel is launched
+	// right away and each CTA waits for the ready flag of the slice its chunk lives in, so the uploads on
+	// the copy stream overlap the compression with no launch boundaries in between.
+	if ((rc = c->d_ctr.reserve(64))) return rc;
 	timer_begin(c, 0);
 	NXGPU_CUDA_OK(launch_deflate(static_cast<const DeflateJob *>(c->d_jobs.p), static_cast<DeflateOut *>(c->d_outs.p),
-				     (uint32_t)n, level, static_cast<uint32_t *>(c->d_tok.p), tok_stride, grid, c->stream));
+				     (uint32_t)n, level, static_cast<uint32_t *>(c->d_tok.p), tok_stride, grid, c->stream,
+				     static_cast<uint32_t *>(c->d_ctr.p), c->ready_flags, c->jobs_per_flag));
 	timer_end(c, 0);
 	if (want_cksum) {
 		std::vector<nxgpu_cksum_item> it(n);
@@ -499,6 +511,8 @@ int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *
 			 int level, int wrap, uint32_t chunk, uint64_t *chunk_offsets, nxgpu_stream_result *res, int mem)
 {
 	if (!c || (!src && src_len) || !dst || !res) return NXGPU_E_ARG;
+	const bool cont = wrap == NXGPU_WRAP_RAW_CONT;
+	if (cont) wrap = NXGPU_WRAP_RAW;
 	if (wrap != NXGPU_WRAP_RAW && wrap != NXGPU_WRAP_ZLIB && wrap != NXGPU_WRAP_GZIP) return NXGPU_E_ARG;
 	if (chunk == 0) chunk = 262144;
 	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
@@ -509,8 +523,28 @@ int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *
 	if (mem == NXGPU_MEM_HOST) {
 		if ((rc = c->d_in.reserve(src_len + 16))) return rc;
 		if ((rc = c->d_out.reserve(dst_cap + 16))) return rc;
-		if (src_len)
-			NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_in.p, src, src_len, cudaMemcpyHostToDevice, c->stream));
+		const size_t per_slice = kSliceChunks;
+		const size_t n_slices = (n + per_slice - 1) / per_slice;
+		if ((rc = c->d_flags.reserve((n_slices + 1) * 4))) return rc;
+		if ((rc = c->h_ones.reserve(16))) return rc;
+		*static_cast<uint32_t *>(c->h_ones.p) = 1;
+		NXGPU_CUDA_OK(cudaMemsetAsync(c->d_flags.p, 0, (n_slices + 1) * 4, c->stream));
+		// the copy stream must not overtake earlier work on d_in or the flag reset
+		NXGPU_CUDA_OK(cudaEventRecord(c->ev_main, c->stream));
+		NXGPU_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+		for (size_t lo = 0, k = 0; lo < n && src_len; lo += per_slice, k++) {
+			const size_t cnt = n - lo < per_slice ? n - lo : per_slice;
+			const uint64_t b0 = (uint64_t)lo * chunk;
+			const uint64_t b1 = (lo + cnt == n) ? src_len : (uint64_t)(lo + cnt) * chunk;
+			NXGPU_CUDA_OK(cudaMemcpyAsync(static_cast<uint8_t *>(c->d_in.p) + b0, static_cast<const uint8_t *>(src) + b0, b1 - b0,
+						      cudaMemcpyHostToDevice, c->copy_stream));
+			NXGPU_CUDA_OK(cudaMemcpyAsync(static_cast<uint32_t *>(c->d_flags.p) + k, c->h_ones.p, 4, cudaMemcpyHostToDevice, c->copy_stream));
+		}
+		NXGPU_CUDA_OK(cudaEventRecord(c->ev_copy, c->copy_stream));
+		if (src_len) {
+			c->ready_flags = static_cast<const uint32_t *>(c->d_flags.p);
+			c->jobs_per_flag = (uint32_t)per_slice;
+		}
 		dsrc = static_cast<const uint8_t *>(c->d_in.p);
 		ddst = static_cast<uint8_t *>(c->d_out.p);
 	}
@@ -522,9 +556,15 @@ int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *
 		jh[i].src = dsrc + o;
 		jh[i].src_len = (uint32_t)(src_len - o < chunk ? src_len - o : chunk);
 		jh[i].hist_len = (uint32_t)(o < 32768 ? o : 32768);
-		jh[i].flags = (i + 1 == n) ? NXGPU_F_FINAL : 0;
+		jh[i].flags = (i + 1 == n && !cont) ? NXGPU_F_FINAL : 0;
 	}
-	if ((rc = deflate_device(c, jh, n, level, false))) return rc;
+	rc = deflate_device(c, jh, n, level, false);
+	if (c->ready_flags) {
+		// everything behind the kernel (checksums, a later call's uploads) must see the whole input
+		c->ready_flags = nullptr;
+		cudaStreamWaitEvent(c->stream, c->ev_copy, 0);
+	}
+	if (rc) return rc;
 	// whole-stream checksums: chunks are the ranges of one job
 	nxgpu_cksum_item whole = { dsrc, src_len, 0, 1 };
 	if ((rc = checksum_device(c, &whole, 1, 3))) return rc;

@@ -319,3 +319,59 @@ def test_large_roundtrip_checksum_of_checksums(engine, pg, alice):
     assert gzip.decompress(blob) == data
     for b in (dsrc, ddst, dback):
         b.free()
+
+
+@pytest.mark.gpu
+def test_deflate_stress_many_shapes(engine, pg):
+    """Hundreds of inputs with copies of every length at every distance, sized around the kernel's
+    internal boundaries (512-byte sub-blocks, 4 KiB staging blocks, the 64 KiB ring), with and without
+    a dictionary in front: each must inflate back bit-exactly with zlib (one batch per level)."""
+    import ctypes as C
+    rnd = random.Random(1234)
+
+    def mosaic(n, alphabet, maxlen, maxdist):
+        out = bytearray(rnd.choice(alphabet) for _ in range(min(n, 40)))
+        while len(out) < n:
+            if rnd.random() < 0.15:
+                out += bytes(rnd.choice(alphabet) for _ in range(rnd.randint(1, 6)))
+            else:
+                d = rnd.randint(1, min(len(out), maxdist))
+                ln = rnd.randint(3, maxlen)
+                for _ in range(ln):
+                    out.append(out[-d])
+        return bytes(out[:n])
+
+    sizes = [1, 2, 4, 5, 6, 31, 32, 33, 500, 511, 512, 513, 514, 767, 1023, 1024, 1025, 1030, 4090, 4095, 4096, 4097, 4100,
+             8191, 8192, 8200, 16383, 16384, 16385, 32767, 32768, 32769, 65535, 65536, 65537, 70000, 131072, 200000, 262144, 262145, 300000]
+    cases = []
+    for n in sizes:
+        for alphabet, maxlen, maxdist in ((b"ab", 300, 40), (b"abcdefgh", 80, 3000), (bytes(range(256)), 20, 40000), (b"\0", 258, 1)):
+            hist = rnd.choice([0, 0, 16, 4096, 32768])
+            cases.append((mosaic(hist + n, alphabet, maxlen, maxdist), hist))
+    for level in (1, 6, 9):
+        bufs, items = [], []
+        for data, hist in cases:
+            n = len(data) - hist
+            src = C.create_string_buffer(data, len(data))
+            cap = 2 * n + 1024
+            dst = C.create_string_buffer(cap)
+            bufs.append((src, dst))
+            items.append(pg.DeflateItem(C.addressof(src) + hist, n, hist, C.addressof(dst), cap, pg.F_FINAL))
+        res = engine.deflate_batch(items, level=level, mem=pg.MEM_HOST)
+        for (data, hist), (src, dst), r in zip(cases, bufs, res):
+            assert r.rc == 0, (level, len(data), hist, r.rc)
+            d = zlib.decompressobj(-15, zdict=data[:hist]) if hist else zlib.decompressobj(-15)
+            got = d.decompress(dst.raw[: r.out_len])
+            assert got == data[hist:], (level, len(data) - hist, hist)
+            assert r.crc32 == zlib.crc32(data[hist:])
+
+
+@pytest.mark.gpu
+def test_deflate_stream_raw_continuation(engine, pg, alice):
+    """NXGPU_WRAP_RAW_CONT: a GPU's range of a multi-GPU stream carries no BFINAL and ends on the
+    joiner, so ranges concatenate bytewise (bench.py --gpus N relies on it)."""
+    a, b = (alice * 3)[:400000], (alice * 3)[100000:450000]
+    first = engine.compress(a, level=6, wrap=pg.WRAP_RAW_CONT)
+    last = engine.compress(b, level=6, wrap=pg.WRAP_RAW)
+    assert first[-4:] == b"\x00\x00\xff\xff"
+    assert zlib.decompress(first + last, -15) == a + b
