@@ -64,33 +64,50 @@ def peaks():
     return 6650.0, "fallback"          # /opt/skills/guides/B200_PROFILING.md
 
 
-class ClockSampler(threading.Thread):
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+class ClockSampler:
+    """nvidia-smi polled every 100 ms in ONE long-lived process (spawning it per sample takes longer than a
+    step); only samples that fall inside [mark_start, mark_end] — the timed region — are summarised."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu):
-        super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu, [], threading.Event()
+        self.gpu, self.rows, self.t0, self.t1 = gpu, [], None, None
+        self.proc = None
 
-    def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 8:
+                self.rows.append((time.time(), parts))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        lo, hi = (self.t0 or 0) - 0.05, (self.t1 or time.time()) + 0.15
+        rows = [r for t, r in self.rows if lo <= t <= hi] or [r for _, r in self.rows[-3:]]
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         reasons = []
         for i, name in ((4, "hw_slowdown"), (5, "hw_thermal_slowdown"), (6, "sw_thermal_slowdown"), (7, "sw_power_cap")):
-            if any(len(r) > i and r[i].lower().startswith("active") for r in self.rows):
+            if any(len(r) > i and r[i].lower().startswith("active") for r in rows):
                 reasons.append(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(rows)}
 
 
 def oracle_lib():
@@ -243,6 +260,7 @@ def main():
 
     # ---- headline: deflate level 6, device resident ----
     sampler = ClockSampler(local)
+    sampler.start()
     l0 = eng.launch_count()
     eng.kernel_time_reset()
     for _ in range(args.warmup):
@@ -250,14 +268,14 @@ def main():
     barrier()
     eng.kernel_time_reset()
     l0 = eng.launch_count()
-    sampler.start()
+    sampler.mark_start()
     per = []
     last = None
     for _ in range(args.steps):
         ms, res, total = deflate_step(6)
         per.append(ms); last = (res, total)
     barrier()
-    sampler.stop_flag.set()
+    sampler.mark_end()
     launches = eng.launch_count() - l0
     kms, kn = eng.kernel_time("deflate")
     step_ms = sum(per) / len(per)
@@ -286,6 +304,7 @@ def main():
         t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t[0])
+    sampler.stop()
     e2e = {"value": world * n / e2e_ms / 1e6, "unit": "GB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": int(res_h.out_len)}
 
     cpu = None

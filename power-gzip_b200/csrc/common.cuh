@@ -113,12 +113,12 @@ __host__ __device__ inline LevelParams level_params(int level)
 	case 2: return { 3, 0, 64 };
 	case 3: return { 4, 0, 128 };
 	case 4: return { 4, 16, 128 };
-	case 5: return { 10, 32, 258 };
-	case 6: return { 14, 32, 258 };
+	case 5: return { 9, 32, 258 };
+	case 6: return { 12, 32, 258 };
 	case 7: return { 16, 64, 258 };
 	case 8: return { 24, 258, 258 };
 	case 9: return { 48, 258, 258 };
-	default: return { 14, 32, 258 };
+	default: return { 12, 32, 258 };
 	}
 }
 

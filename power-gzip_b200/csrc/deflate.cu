@@ -31,7 +31,7 @@ namespace {
 
 constexpr int kThreads = 1024;
 constexpr uint32_t kRingMask = 0xFFFFu;   // 64 KiB data ring / 64 Ki-entry chain ring
-constexpr int kHashBits = 13;
+constexpr int kHashBits = 14;
 constexpr int kHashSize = 1 << kHashBits;
 constexpr uint32_t kNone = 0xFFFFFFFFu;    // empty hash head
 constexpr int kStageWords = 2048;
@@ -45,7 +45,7 @@ struct __align__(16) Smem {
 	uint32_t ring32[16384 + kMirrorWords];   // 64 KiB input ring (position & 0xFFFF) + copy of its first bytes,
 	                                  // so that reads of up to 320 bytes never have to wrap
 	uint16_t prev[65536];             // 128 KiB: distance to the previous position with the same hash
-	uint32_t head[kHashSize];         // 32 KiB: most recent position per hash (kNone = empty)
+	uint16_t head[kHashSize];         // 32 KiB: low 16 bits of the most recent position per hash
 	uint64_t mbar[kSlots];            // TMA completion barriers of the staging blocks
 	uint64_t done_bar[kDoneSlots];    // producer arrives once block b's chains are built; parsers sleep on it
 	volatile uint32_t parse_pos[32];  // per parser warp: first position of the sub-block in flight
@@ -169,19 +169,21 @@ __device__ void build_chains(Smem &S, uint32_t lo, uint32_t hi)
 #pragma unroll
 		for (int u = 0; u < U; u++) {
 			const uint32_t pos = p0 + 32 * u + lane;
-			old[u] = kNone;
+			old[u] = 0;
 			if (pos < hi) {
 				old[u] = S.head[h[u]];
-				S.head[h[u]] = pos;
+				S.head[h[u]] = (uint16_t)pos;
 			}
 			__syncwarp();
 		}
 #pragma unroll
 		for (int u = 0; u < U; u++) {
 			const uint32_t pos = p0 + 32 * u + lane;
-			const uint32_t d = pos - old[u];
+			// heads keep 16 bits: the distance is exact for anything inside the window; an empty or stale
+			// bucket yields some in-window position that the parser's byte comparison rejects
+			const uint32_t d = (pos - old[u]) & 0xFFFFu;
 			if (pos < hi)
-				S.prev[pos & kRingMask] = (uint16_t)((old[u] < pos && d <= (uint32_t)kWindow) ? d : 0);
+				S.prev[pos & kRingMask] = (uint16_t)(d <= (uint32_t)kWindow ? d : 0);
 		}
 	}
 }
@@ -885,7 +887,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 
 		// ---- init ----
 		for (int i = threadIdx.x; i < kHashSize; i += kThreads)
-			S.head[i] = kNone;
+			S.head[i] = 0;
 		for (int i = threadIdx.x; i < 288; i += kThreads)
 			S.ll_freq[i] = 0;
 		if (threadIdx.x < 32) {
