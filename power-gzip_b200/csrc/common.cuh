@@ -105,20 +105,20 @@ struct CksumJob {
 };
 
 // deflate tuning per zlib-style level
-struct LevelParams { int depth; int lazy; int nice; };
+struct LevelParams { int depth; int lazy; int nice; int d1; };   // d1 != 0: two-pass parse, d1 = depth of the shallow pass
 __host__ __device__ inline LevelParams level_params(int level)
 {
-	switch (level) {          // base chain depth (x1..x4 with the data, see parse_subblock), lazy threshold (0 = greedy), nice length
-	case 1: return { 2, 0, 32 };
-	case 2: return { 3, 0, 64 };
-	case 3: return { 4, 0, 128 };
-	case 4: return { 4, 16, 128 };
-	case 5: return { 9, 32, 258 };
-	case 6: return { 12, 32, 258 };
-	case 7: return { 16, 64, 258 };
-	case 8: return { 24, 258, 258 };
-	case 9: return { 48, 258, 258 };
-	default: return { 12, 32, 258 };
+	switch (level) {          // chain depth, lazy threshold (0 = greedy), nice length, shallow-pass depth (0 = single pass)
+	case 1: return { 2, 0, 32, 0 };
+	case 2: return { 3, 0, 64, 0 };
+	case 3: return { 4, 0, 128, 0 };
+	case 4: return { 4, 16, 128, 0 };
+	case 5: return { 12, 32, 258, 2 };
+	case 6: return { 24, 32, 258, 2 };
+	case 7: return { 32, 64, 258, 3 };
+	case 8: return { 48, 258, 258, 3 };
+	case 9: return { 96, 258, 258, 4 };
+	default: return { 24, 32, 258, 2 };
 	}
 }
 

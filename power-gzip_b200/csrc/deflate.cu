@@ -415,6 +415,169 @@ __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, ui
 	return n;
 }
 
+// ---- two-pass parser (levels 5 and up) ----
+// Searching every position to full depth wastes most of the work: only the positions where a token
+// starts (about one in ten) ever use their result.  So: pass 1 walks every position of the
+// sub-block to a SHALLOW depth (d1 hops, one lane per position, 32 consecutive positions per window)
+// and parses those results; the token starts of that parse — plus the position behind each start
+// whose match is short enough for the lazy rule to look at — are queued, and pass 2 walks only the
+// queued positions to the FULL depth, 32 of them per step, one per lane.  The final parse reads the
+// per-position results (deep where there is one, shallow elsewhere) back from scratch.
+// tools/lzsim.c (two=2): same or better ratio than full depth everywhere at a third of the hops.
+
+// one lane's chain walk: longest match for `pos` among the first `depth` chain candidates
+__device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, uint32_t pos, uint32_t maxl, uint32_t maxdist,
+					   int depth, uint32_t nice, uint32_t &bl, uint32_t &bd)
+{
+	uint32_t P0, P1, P2, P3;
+	{
+		const uint32_t o = pos & kRingMask, a = o & ~3u, sh = (o & 3) * 8;
+		const uint32_t w0 = ld32(ring8, a), w1 = ld32(ring8, a + 4), w2 = ld32(ring8, a + 8), w3 = ld32(ring8, a + 12), w4 = ld32(ring8, a + 16);
+		P0 = __funnelshift_r(w0, w1, sh); P1 = __funnelshift_r(w1, w2, sh);
+		P2 = __funnelshift_r(w2, w3, sh); P3 = __funnelshift_r(w3, w4, sh);
+	}
+	bl = kMinMatch - 1; bd = 0;
+	uint32_t acc = 0;
+	uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;
+	uint32_t endw = __funnelshift_r(P0, P1, 8);                  // the 4 bytes ending at offset bl = 4
+	for (int hop = 0; hop < depth; hop++) {
+		if (!__any_sync(0xffffffffu, d != 0))
+			break;
+		if (d) {
+			acc += d;
+			if (acc > maxdist) {
+				d = 0;
+			} else {
+				const uint32_t q = pos - acc;
+				d = S.prev[q & kRingMask];
+				if (load4(ring8, q + bl - 3) == endw) {
+					const uint32_t len = match_length(ring8, pos, q, maxl, P0, P1, P2, P3);
+					if (len > bl) {
+						bl = len; bd = acc;
+						if (len >= nice || len >= maxl)
+							d = 0;
+						else
+							endw = load4(ring8, pos + bl - 3);
+					}
+				}
+			}
+		}
+	}
+}
+
+// greedy / lazy choice per position of one window, then pointer jumping: every lane ends up with
+// the set of token starts reached from it (Rl) and where the stream leaves the window (J >= nlive)
+__device__ __forceinline__ void window_parse(uint32_t lane, uint32_t nlive, uint32_t len, int lazy, bool &take, uint32_t &J, uint32_t &Rl)
+{
+	const bool live = lane < nlive;
+	uint32_t nlen = __shfl_down_sync(0xffffffffu, len, 1);
+	if (lane == 31)
+		nlen = 0;                                              // no look-ahead across windows
+	take = len != 0;
+	if (take && lazy && len < (uint32_t)lazy && nlen > len)
+		take = false;
+	J = live ? lane + (take ? len : 1) : 64;
+	Rl = live ? (1u << lane) : 0;
+#pragma unroll
+	for (int k = 0; k < 5; k++) {
+		const uint32_t tJ = __shfl_sync(0xffffffffu, J, J & 31);
+		const uint32_t tR = __shfl_sync(0xffffffffu, Rl, J & 31);
+		if (J < nlive) { Rl |= tR; J = tJ; }
+	}
+}
+
+__device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_hi, uint32_t valid_lo, uint32_t PE,
+					 int d1, int depth, int nice, int lazy, uint32_t *tk, uint32_t *pres,
+					 uint32_t &nwin, uint32_t &end_pos)
+{
+	const uint32_t lane = lane_id();
+	const uint32_t lt = (1u << lane) - 1;
+	const uint8_t *ring8 = reinterpret_cast<const uint8_t *>(S.ring32);
+	const uint32_t npos = sub_hi - sub_lo;
+	uint32_t qpos = 0, qn = 0;                                 // pass-2 queue: one position per lane
+	uint32_t headA = 0;                                        // pass-1 parse: next token start (relative to sub_lo)
+	uint32_t carry = 0;                                        // mark for lane 0 of the next window
+
+	auto deep = [&](uint32_t count) {
+		const bool act = lane < count;
+		const uint32_t pos = act ? qpos : sub_lo;
+		const uint32_t maxl = act ? min((uint32_t)kMaxMatch, PE - pos) : 0;
+		uint32_t bl, bd;
+		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), depth, (uint32_t)nice, bl, bd);
+		if (act && bl >= (uint32_t)kMinMatch)
+			__stcg(&pres[pos - sub_lo], tok_match(bl, bd));
+	};
+
+	// ---- pass 1 (+ pass 2 whenever 32 positions are queued) ----
+	for (uint32_t w0 = 0; w0 < npos; w0 += 32) {
+		nwin++;
+		const uint32_t pos = sub_lo + w0 + lane;
+		const uint32_t nlive = min(32u, npos - w0);
+		const bool live = lane < nlive;
+		const uint32_t maxl = live ? min((uint32_t)kMaxMatch, PE - pos) : 0;
+		uint32_t bl, bd;
+		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), d1, (uint32_t)nice, bl, bd);
+		const uint32_t len = bl >= (uint32_t)kMinMatch ? bl : 0;
+		if (live)
+			__stcg(&pres[w0 + lane], len ? tok_match(len, bd) : (uint32_t)ring8[pos & kRingMask]);
+		uint32_t M = carry;
+		carry = 0;
+		if (headA < w0 + nlive) {
+			bool take; uint32_t J, Rl;
+			window_parse(lane, nlive, len, lazy, take, J, Rl);
+			const uint32_t h = headA - w0;
+			const uint32_t R = __shfl_sync(0xffffffffu, Rl, h);
+			headA = w0 + __shfl_sync(0xffffffffu, J, h);
+			// a start whose match is short enough for the lazy rule also needs the position behind it
+			const uint32_t nx = __ballot_sync(0xffffffffu, ((R >> lane) & 1) && lazy && len < (uint32_t)lazy);
+			M |= R | (nx << 1);
+			carry = nx >> 31;
+		}
+		if (nlive < 32)
+			M &= (1u << nlive) - 1;
+		while (M) {
+			const uint32_t cnt = __popc(M), room = 32 - qn, tk_n = min(cnt, room);
+			if (lane >= qn && lane < qn + tk_n)
+				qpos = sub_lo + w0 + __fns(M, 0, (int)(lane - qn + 1));
+			qn += tk_n;
+			if (tk_n == cnt)
+				M = 0;
+			else
+				M &= ~((1u << __fns(M, 0, (int)(tk_n + 1))) - 1);
+			if (qn == 32) {
+				deep(32);
+				qn = 0;
+			}
+		}
+	}
+	if (qn)
+		deep(qn);
+	__threadfence_block();
+	__syncwarp();
+
+	// ---- final parse over the stored per-position results ----
+	uint32_t n = 0, head = 0;
+	for (uint32_t w0 = 0; w0 < npos; w0 += 32) {
+		const uint32_t nlive = min(32u, npos - w0);
+		if (head >= w0 + nlive)
+			continue;
+		const bool live = lane < nlive;
+		const uint32_t pos = sub_lo + w0 + lane;
+		const uint32_t t = live ? __ldcg(&pres[w0 + lane]) : 0;
+		const uint32_t len = (live && tok_is_match(t)) ? tok_len(t) : 0;
+		bool take; uint32_t J, Rl;
+		window_parse(lane, nlive, len, lazy, take, J, Rl);
+		const uint32_t h = head - w0;
+		const uint32_t R = __shfl_sync(0xffffffffu, Rl, h);
+		head = w0 + __shfl_sync(0xffffffffu, J, h);
+		if ((R >> lane) & 1)
+			tk[n + __popc(R & lt)] = take ? t : (uint32_t)ring8[pos & kRingMask];
+		n += __popc(R);
+	}
+	end_pos = sub_lo + head;
+	return n;
+}
+
 // ---- stitch helpers (after the parse): sub-block sb+1 was parsed from its nominal start although
 // the last match of sub-block sb may cover its first bytes.  The match is cut back to the latest
 // token start of sb+1 it reaches, and sb+1 drops the tokens in front of that start.
@@ -844,12 +1007,12 @@ __device__ uint32_t emit_stored(const DeflateJob &J, bool final_flag)
 __host__ __device__ inline uint32_t scratch_nsub(uint32_t tok_stride) { return tok_stride / kSub + 2; }
 constexpr int kMeta = 8;     // per sub-block: tokens, end position, tokens dropped in front, kept tokens, flat offset, tail count, tail tokens[2]
 enum { M_CNT = 0, M_END = 1, M_SKIP = 2, M_NEW = 3, M_OFF = 4, M_TAILN = 5, M_TAIL0 = 6, M_TAIL1 = 7 };
-__host__ __device__ inline size_t scratch_words(uint32_t tok_stride) { return 2 * (size_t)tok_stride + kMeta * (size_t)scratch_nsub(tok_stride); }
+__host__ __device__ inline size_t scratch_words(uint32_t tok_stride) { return 2 * (size_t)tok_stride + kMeta * (size_t)scratch_nsub(tok_stride) + 32 * (size_t)(kSub + 32); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ outs, uint32_t n_jobs,
 	       int depth, int lazy, int nice, uint32_t *tok_scratch, uint32_t tok_stride, uint32_t parser_mask,
-	       uint32_t *job_counter, const volatile uint32_t *ready, uint32_t jobs_per_flag)
+	       uint32_t *job_counter, const volatile uint32_t *ready, uint32_t jobs_per_flag, int d1)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -858,6 +1021,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 	uint32_t *tok = tok_scratch + (size_t)blockIdx.x * scratch_words(tok_stride);
 	uint32_t *tokpos = tok + tok_stride;
 	uint32_t *meta = tokpos + tok_stride;
+	uint32_t *pres = meta + kMeta * (size_t)scratch_nsub(tok_stride);     // per parser warp: result per position of its sub-block
 
 	for (;;) {
 		// jobs are handed out in order; when the input is still being uploaded (host-pointer streams)
@@ -941,7 +1105,10 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 				__threadfence_block();
 				const long long t1 = clock64();
 				uint32_t end_pos;
-				const uint32_t cnt = parse_subblock(S, sub_lo, sub_hi, P0, PE, depth, nice, lazy, tokpos + (size_t)sb * kSub, nwin, end_pos);
+				const uint32_t cnt = d1
+					? parse_subblock_2pass(S, sub_lo, sub_hi, P0, PE, d1, depth, nice, lazy, tokpos + (size_t)sb * kSub,
+							       pres + (size_t)warp * (kSub + 32), nwin, end_pos)
+					: parse_subblock(S, sub_lo, sub_hi, P0, PE, depth, nice, lazy, tokpos + (size_t)sb * kSub, nwin, end_pos);
 				if (lane_id() == 0) {
 					meta[sb * kMeta + M_CNT] = cnt;
 					meta[sb * kMeta + M_END] = end_pos;
@@ -1221,7 +1388,9 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 	LevelParams lp = level_params(level);
 	if (const char *ov = getenv("NXGPU_LZ_PARAMS")) {         // developer override: "depth,lazy,nice"
 		int a, b, c;
-		if (sscanf(ov, "%d,%d,%d", &a, &b, &c) == 3 && a >= 1) { lp.depth = a; lp.lazy = b; lp.nice = c; }
+		int d = 0;
+		const int got = sscanf(ov, "%d,%d,%d,%d", &a, &b, &c, &d);
+		if (got >= 3 && a >= 1) { lp.depth = a; lp.lazy = b; lp.nice = c; lp.d1 = got == 4 ? d : 0; }
 	}
 	static const bool dbg = getenv("NXGPU_DEBUG_CYCLES") != nullptr;
 	unsigned long long *d_dbg = nullptr;
@@ -1239,7 +1408,7 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 	if (me != cudaSuccess)
 		return me;
 	deflate_kernel<<<grid, kThreads, sizeof(Smem), s>>>(jobs, outs, n_jobs, lp.depth, lp.lazy, lp.nice, tok_scratch, tok_stride, parser_mask,
-							    job_counter, ready, jobs_per_flag ? jobs_per_flag : 1);
+							    job_counter, ready, jobs_per_flag ? jobs_per_flag : 1, lp.d1);
 	cudaError_t e = cudaGetLastError();
 	if (dbg) {
 		std::vector<unsigned long long> h((size_t)grid * 8);
@@ -1250,8 +1419,8 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 		const double st = t[4] ? (double)t[4] : 1.0;
 		(void)st;
 		const double nj = n_jobs;
-		fprintf(stderr, "[nxgpu cycles/job] level %d (depth %d lazy %d nice %d): producer build %.0f wait-data %.0f wait-space %.0f | parser(w1) busy %.0f wait %.0f windows %.0f | huff+pack %.0f total %.0f\n",
-			level, lp.depth, lp.lazy, lp.nice, t[0] / nj, t[1] / nj, t[2] / nj, t[3] / nj, t[4] / nj, t[7] / nj, t[5] / nj, t[6] / nj);
+		fprintf(stderr, "[nxgpu cycles/job] level %d (depth %d lazy %d nice %d d1 %d): producer build %.0f wait-data %.0f wait-space %.0f | parser(w1) busy %.0f wait %.0f windows %.0f | huff+pack %.0f total %.0f\n",
+			level, lp.depth, lp.lazy, lp.nice, lp.d1, t[0] / nj, t[1] / nj, t[2] / nj, t[3] / nj, t[4] / nj, t[7] / nj, t[5] / nj, t[6] / nj);
 		d_dbg = nullptr;
 		cudaMemcpyToSymbol(g_dbg, &d_dbg, sizeof(d_dbg));
 	}
