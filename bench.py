@@ -342,13 +342,14 @@ def main():
         extra["ratio_level1"] = n / r1.out_len
         # ---- batched inflate of independent 64 KiB gzip members (configs[2], scaled to the input) ----
         M = 65536
-        nm = n // M
-        sample_members = min(nm, 2048)
+        nm = 100000 if args.log2 >= 30 else n // M          # configs[2]: 100 k independent 64 KiB gzip members
+        sample_members = min(n // M, 2048)
         hb = C.string_at(hsrc, sample_members * M)
         blobs = [zlib.compress(hb[i * M:(i + 1) * M], 6, wbits=31) for i in range(sample_members)]
-        packed = b"".join(blobs * (nm // sample_members))
-        lens = [len(b) for b in blobs] * (nm // sample_members)
-        nm = len(lens)
+        reps = -(-nm // sample_members)
+        packed = b"".join(blobs * reps)
+        lens = ([len(b) for b in blobs] * reps)[:nm]
+        packed = packed[:sum(lens)]
         comp = torch.empty(len(packed), dtype=torch.uint8, device="cuda")
         pk = C.create_string_buffer(packed, len(packed))
         eng._check(lib.nxgpu_memcpy_h2d(eng.ctx, comp.data_ptr(), C.addressof(pk), len(packed)), "h2d")
@@ -373,6 +374,29 @@ def main():
         extra["inflate_64KiB_members_GBps"] = world * nm * M / (sum(pi) / len(pi)) / 1e6
         extra["inflate_kernel_GBps"] = nm * M / (ki / max(kni, 1)) / 1e6
         extra["inflate_roofline_frac"] = (nm * M + len(packed)) / (ki / max(kni, 1)) / 1e6 / hbm_peak
+        del comp, out
+        # ---- crc32 + adler32 (configs[4]): one buffer of 4 KiB .. 1 GiB, and a storm of small buffers ----
+        sweep = {}
+        for lg in range(12, args.log2 + 1, 2):
+            sz = 1 << lg
+            best = None
+            for _ in range(3):
+                eng.timer_start()
+                r = eng.checksum_batch([(src.data_ptr(), sz, 0, 1)], mem=pg.MEM_DEVICE)
+                ms = eng.timer_stop()
+                best = ms if best is None else min(best, ms)
+            sweep[str(sz)] = round(sz / best / 1e6, 3)
+        assert r[0][0] == res6.crc32, "crc32 of the whole buffer differs from the deflate path's"
+        extra["crc32_adler32_GBps_by_size"] = sweep
+        small = [(src.data_ptr() + (i * 4099) % (n - 70000), 1 << (12 + i % 5), 0, 1) for i in range(100000)]
+        eng.checksum_batch(small[:1000], mem=pg.MEM_DEVICE)
+        t0 = time.perf_counter()
+        rs = eng.checksum_batch(small, mem=pg.MEM_DEVICE)
+        dt = time.perf_counter() - t0
+        probe = small[12345]
+        assert rs[12345][0] == zlib.crc32(C.string_at(hsrc + (probe[0] - src.data_ptr()), probe[1]))
+        extra["checksum_storm"] = {"buffers": len(small), "bytes": sum(x[1] for x in small), "buffers_per_s": round(len(small) / dt),
+                                   "GBps": round(sum(x[1] for x in small) / dt / 1e9, 2), "note": "4-64 KiB buffers, one batched call, host wall clock"}
 
     if rank == 0:
         threads = os.cpu_count() or 1

@@ -1,17 +1,19 @@
 // deflate.cu — the NX compress function (inc_nx/nxu.h:803-811) and the
 // dynamic-Huffman-table generation of lib/nx_dhtgen.c:945 (row a6) as ONE persistent sm_100a
 // kernel: one CTA per SM, each CTA compresses one job (chunk) at a time entirely out of
-// shared memory.
+// shared memory (DESIGN.md §4.1).
 //
-//   LZ77     exact hash chains (4-byte hash, 13 bits) over a 64 KiB shared-memory ring of the
-//            input (cp.async-staged, 16-byte vectorised) with a 64 Ki-entry u16 chain ring.
-//            Warp 0 inserts positions in stream order, 32 per iteration, resolving intra-warp
-//            predecessors with match.any; all 32 warps then search the chains for EVERY
-//            position of the step in parallel (one lane per position); warp 1 turns the per-
-//            position best matches into the greedy/lazy token stream with an in-warp
-//            pointer-jumping reachability scan (no serial token walk).
-//   Huffman  lit/len + dist histograms accumulate in shared memory during the parse; code
-//            lengths come from a rank sort, a two-queue merge and a Kraft-sum length limiter;
+//   Stage    warp 0 copies the chunk into a 64 KiB shared-memory ring with TMA bulk copies
+//            (cp.async.bulk + mbarrier, 4 KiB blocks) and threads 5-byte-hash chains through it
+//            (14-bit table of 16-bit heads, u16 distance links), non-atomically and pipelined.
+//   LZ77     warps 1-31 take 512-byte sub-blocks in order, sleep on the mbarrier of the block
+//            that completes their chains, and parse one lane per position in windows of 32:
+//            single pass with window skipping (levels 1-4) or shallow pass + deep pass over the
+//            queued token starts (levels 5-9).  No CTA-wide barrier inside this stage.
+//   Stitch   matches that run over a sub-block end are cut back to a token start of the next
+//            sub-block; token counts are prefix-summed and the tokens copied to a flat stream
+//            while the lit/len + dist histograms accumulate in shared memory.
+//   Huffman  code lengths from a rank sort, a two-queue merge and a Kraft-sum length limiter;
 //            the RFC 1951 §3.2.7 header uses a real code-length code.
 //   Pack     code widths are prefix-summed across the CTA (warp shuffles) and the codes are
 //            OR-ed into a shared-memory staging window that is flushed with coalesced stores.
@@ -129,14 +131,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
-// try_wait suspends the warp in hardware until the phase completes or the time hint (ns) runs out;
-// without the hint it returns after a few cycles and the retry loop eats issue slots
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
 	uint32_t ok;
-	asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
-		     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(100000u) : "memory");
+	asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+		     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
 	return ok != 0;
+}
+// Waiting warps must not poll at full rate: the SM is issue-bound and a spinning warp takes an issue
+// slot every few cycles (ncu: a third of all instructions were wait loops, with try_wait's suspend
+// hint too).  Back off with real sleeps instead; short sleeps (<~0.5 us) return immediately.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity)
+{
+	uint32_t ns = 512;
+	while (!mbar_try_wait(bar, parity)) {
+		__nanosleep(ns);
+		if (ns < 4096)
+			ns *= 2;
+	}
 }
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
 {
@@ -1099,8 +1111,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 					const uint32_t bw = min(nblk - 1, (min(PE, sub_hi + kMaxMatch) + 3) / kBlk);
 					uint64_t *bar = &S.done_bar[bw % kDoneSlots];
 					const uint32_t parity = (bw / kDoneSlots) & 1;
-					while (!mbar_try_wait(bar, parity))
-						;
+					mbar_wait_sleep(bar, parity);
 				}
 				__threadfence_block();
 				const long long t1 = clock64();
