@@ -1,22 +1,27 @@
 // inflate.cu — the NX decompress function (inc_nx/nxu.h:812) as a batched
 // sm_100a kernel: one warp per independent member / sync-point segment.
 //
-// Per warp: lane 0 walks the Huffman stream through shared-memory lookup tables (10-bit
-// lit/len, 9-bit distance, canonical fall-back for longer codes) and queues up to 32 symbols;
-// then all 32 lanes materialise the queue — a shuffle prefix sum gives every symbol its output
-// offset, literals are stored in parallel and each match is copied by the whole warp.  The
-// window is the output buffer itself (L1/L2-resident), so no history copies are needed
-// (the reference's host side copies 32 KiB per job, lib/nx_inflate.c:1633-1687).
+// Per warp: the compressed bytes are staged into a small shared-memory ring with coalesced loads;
+// lane 0 walks the Huffman stream through shared-memory lookup tables (10-bit lit/len, 9-bit
+// distance, canonical fall-back for longer codes) and queues up to 32 symbols; then all 32 lanes
+// materialise the queue — a shuffle prefix sum gives every symbol its output offset, literals and
+// every match that does not read this batch's own output are written byte-parallel with all loads
+// in flight at once, the few short-distance matches follow in order.  The window is the output
+// buffer itself (L1/L2-resident), so no history copies are needed (the reference's host side copies
+// 32 KiB per job, lib/nx_inflate.c:1633-1687).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/nxgpu.h"
 
 namespace nxgpu {
 namespace {
 
-constexpr int kWarpsPerCta = 8;
+constexpr int kWarpsPerCta = 4;
 constexpr int kLitBits = 10, kDistBits = 9;
+constexpr uint32_t kInWords = 128;         // per-warp staging ring for the compressed input (512 B)
+constexpr uint32_t kInAhead = 64;          // the warp tops the ring up while fewer words than this lie ahead
 
 struct WarpTables {
 	uint32_t lit[1 << kLitBits];      // codelen | type<<4 | nextra<<6 | value<<10   (0 = slow path)
@@ -26,6 +31,7 @@ struct WarpTables {
 	uint16_t lit_count[16], dist_count[16];
 	uint8_t lens[320];
 	uint32_t q[32];                   // decoded symbols: literal, or tok_match(len, dist)
+	uint32_t in[kInWords];            // compressed input, word w of the member at in[w % kInWords]
 };
 
 __constant__ uint16_t k_len_base[29] = { 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258 };
@@ -34,50 +40,105 @@ __constant__ uint16_t k_dist_base[30] = { 1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 4
 __constant__ uint8_t k_dist_extra[30] = { 0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13 };
 __constant__ uint8_t k_clorder[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
 
-// LSB-first bit reader over global memory (lane 0 only)
+// LSB-first bit reader (lane 0 only).  The compressed bytes come out of a small shared-memory ring
+// that the whole warp fills with coalesced loads between symbol batches (stage_input), so the
+// decode loop never waits for global memory; when the ring runs dry inside a long header lane 0
+// fills it on its own.  Positions are 32-bit words counted from the 4-byte aligned address at or
+// below the first source byte; bytes outside [src, src+len) read as zero.
+// The bit window is three 32-bit registers (current word, next word, one prefetched from the ring)
+// and a bit offset: peeking is one funnel shift, dropping one add and a rarely taken advance — no
+// 64-bit shifts on the symbol path.
 struct BitReader {
-	const uint8_t *src;
-	uint32_t len;       // valid bytes
-	uint32_t pos;       // bytes loaded so far (may run past len: zero fill)
-	uint64_t buf;
-	uint32_t cnt;
+	const uint32_t *base32;   // aligned base
+	uint32_t *ring;           // shared, kInWords words
+	uint32_t skip;            // first valid byte (0..3) relative to base32
+	uint64_t end;             // one past the last valid byte, relative to base32
+	uint32_t end_word;        // end / 4: no overrun is possible while wpos <= end_word
+	uint32_t wpos;            // words fetched so far: the window holds words wpos-3, wpos-2, wpos-1
+	uint32_t staged;          // words [.., staged) are in the ring
+	uint32_t w0, w1, w2;
+	uint32_t bo;              // bits of w0 already consumed (< 32)
 
-	__device__ __forceinline__ void init(const uint8_t *s, uint32_t n, uint32_t start)
+	// word w of the source with the bytes outside the member zeroed (any lane)
+	static __device__ __forceinline__ uint32_t load_word(const uint32_t *base32, uint32_t skip, uint64_t end, uint32_t w)
 	{
-		src = s; len = n; pos = start; buf = 0; cnt = 0;
-		// byte loads until the address is 4-byte aligned
-		while (((reinterpret_cast<uintptr_t>(src) + pos) & 3) && cnt <= 56) {
-			uint64_t b = pos < len ? src[pos] : 0;
-			buf |= b << cnt; cnt += 8; pos++;
+		const uint64_t b0 = (uint64_t)w * 4;
+		if (b0 >= end)
+			return 0;
+		uint32_t v = base32[w];
+		if (b0 + 4 > end)
+			v &= (1u << ((uint32_t)(end - b0) * 8)) - 1;
+		if (b0 < skip)
+			v &= ~0u << (skip * 8);
+		return v;
+	}
+	// lane 0 on its own: 8 more words (only when the warp-wide staging did not reach far enough)
+	static __device__ __noinline__ void fill_single(const uint32_t *base32, uint32_t skip, uint64_t end, uint32_t *ring, uint32_t staged)
+	{
+		uint32_t w[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++)
+			w[k] = load_word(base32, skip, end, staged + k);
+#pragma unroll
+		for (int k = 0; k < 8; k++)
+			ring[(staged + k) % kInWords] = w[k];
+	}
+	__device__ __forceinline__ uint32_t next_word()
+	{
+		if (wpos == staged) {
+			fill_single(base32, skip, end, ring, staged);
+			staged += 8;
+		}
+		return ring[wpos++ % kInWords];
+	}
+	__device__ __forceinline__ void setup(const uint8_t *s, uint32_t n, uint32_t *ring_)
+	{
+		const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+		base32 = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+		skip = (uint32_t)(a & 3);
+		end = (uint64_t)skip + n;
+		end_word = (uint32_t)(end >> 2);
+		ring = ring_;
+		wpos = staged = 0; w0 = w1 = w2 = 0; bo = 0;
+	}
+	// start reading at byte `start` of the member (lane 0); setup() must have run
+	__device__ __forceinline__ void seek(uint32_t start)
+	{
+		const uint64_t p = (uint64_t)skip + start;
+		wpos = staged = (uint32_t)(p >> 2);
+		w0 = next_word(); w1 = next_word(); w2 = next_word();
+		bo = (uint32_t)(p & 3) * 8;
+	}
+	__device__ __forceinline__ void init(const uint8_t *s, uint32_t n, uint32_t start, uint32_t *ring_)
+	{
+		setup(s, n, ring_);
+		seek(start);
+	}
+	__device__ __forceinline__ uint32_t peek32() const { return __funnelshift_r(w0, w1, bo); }
+	__device__ __forceinline__ uint32_t peek(uint32_t n) const { return peek32() & ((1u << n) - 1); }   // n < 32
+	__device__ __forceinline__ void drop(uint32_t n)                                                 // n <= 32
+	{
+		bo += n;
+		if (bo >= 32) {
+			w0 = w1; w1 = w2; w2 = next_word();
+			bo -= 32;
 		}
 	}
-	__device__ __forceinline__ void refill()
-	{
-		while (cnt <= 32) {
-			uint32_t w;
-			if (pos + 4 <= len) {
-				w = *reinterpret_cast<const uint32_t *>(src + pos);
-			} else {
-				w = 0;
-				for (int k = 0; k < 4; k++)
-					if (pos + k < len)
-						w |= (uint32_t)src[pos + k] << (8 * k);
-			}
-			buf |= (uint64_t)w << cnt;
-			cnt += 32; pos += 4;
-		}
-	}
-	__device__ __forceinline__ uint32_t peek(uint32_t n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
-	__device__ __forceinline__ void drop(uint32_t n) { buf >>= n; cnt -= n; }
 	__device__ __forceinline__ uint32_t get(uint32_t n) { uint32_t v = peek(n); drop(n); return v; }
-	__device__ __forceinline__ uint64_t bits_used() const { return (uint64_t)pos * 8 - cnt; }
-	__device__ __forceinline__ bool overrun() const { return bits_used() > (uint64_t)len * 8; }
+	__device__ __forceinline__ void align_byte() { drop((8 - (bo & 7)) & 7); }
+	// bits consumed, counted from base32 / from the first byte of the member
+	__device__ __forceinline__ uint64_t bits_abs() const { return (uint64_t)(wpos - 3) * 32 + bo; }
+	__device__ __forceinline__ uint64_t bits_used() const { return bits_abs() - skip * 8; }
+	__device__ __forceinline__ bool overrun() const { return bits_abs() > end * 8; }
+	// first byte not yet consumed, at a byte boundary (stored blocks are copied straight from memory)
+	__device__ __forceinline__ uint32_t byte_pos() const { return (uint32_t)(bits_abs() >> 3) - skip; }
 };
 
 // canonical decode, one bit at a time (codes longer than the primary table)
 __device__ int slow_decode(BitReader &br, const uint16_t *count, const uint16_t *sorted)
 {
 	int code = 0, first = 0, index = 0;
+#pragma unroll 1
 	for (int l = 1; l <= 15; l++) {
 		code |= (int)br.get(1);
 		int c = count[l];
@@ -173,7 +234,6 @@ __device__ bool build_table(const uint8_t *lens, int n, uint32_t *lut, int lut_b
 __device__ int parse_dyn_header(BitReader &br, uint8_t *lens, int &hlit, int &hdist)
 {
 	int rc = 0;
-	br.refill();
 	const uint32_t v = br.get(14);
 	hlit = (int)(v & 31) + 257; hdist = (int)((v >> 5) & 31) + 1;
 	const int hclen = (int)(v >> 10) + 4;
@@ -181,7 +241,7 @@ __device__ int parse_dyn_header(BitReader &br, uint8_t *lens, int &hlit, int &hd
 	// code-length code: 19 symbols, <= 7 bits, decoded canonically
 	uint8_t cl[19];
 	for (int i = 0; i < 19; i++) cl[i] = 0;
-	for (int i = 0; i < hclen; i++) { br.refill(); cl[k_clorder[i]] = (uint8_t)br.get(3); }
+	for (int i = 0; i < hclen; i++) cl[k_clorder[i]] = (uint8_t)br.get(3);
 	uint16_t ccount[16], csorted[19], coffs[16];
 	for (int i = 0; i < 16; i++) ccount[i] = 0;
 	for (int i = 0; i < 19; i++) ccount[cl[i]]++;
@@ -193,7 +253,6 @@ __device__ int parse_dyn_header(BitReader &br, uint8_t *lens, int &hlit, int &hd
 	for (int i = 0; i < 19; i++) if (cl[i]) csorted[coffs[cl[i]]++] = (uint16_t)i;
 	int n = 0;
 	while (!rc && n < hlit + hdist) {
-		br.refill();
 		const int sym = slow_decode(br, ccount, csorted);
 		if (sym < 0) { rc = NXGPU_E_DATA; break; }
 		if (sym < 16) { lens[n++] = (uint8_t)sym; continue; }
@@ -214,6 +273,7 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 	const bool job = J.wrap == kWrapJob;     // NX decompress-job semantics: stop at the source end and report where
 	const uint64_t total_bits = (uint64_t)J.src_len * 8;
 	BitReader br;
+	br.setup(J.src, J.src_len, T.in);   // every lane knows the geometry; the read position lives in lane 0
 	int rc = 0;                      // uniform after each broadcast
 	uint32_t out = 0;
 	uint32_t start = 0, wrap = J.wrap;
@@ -255,11 +315,9 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 			start = 2;
 		}
 		if (!rc) {
-			br.init(J.src, J.src_len, start);
-			if (job && J.start_bit) {
-				br.refill();
+			br.seek(start);
+			if (job && J.start_bit)
 				br.drop(J.start_bit & 7);
-			}
 		}
 	}
 	rc = __shfl_sync(0xffffffffu, rc, 0);
@@ -282,25 +340,24 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 				} else {
 					btype = 2;
 					BitReader dr;
-					dr.init(J.dht, (J.dht_bits + 7) >> 3, 0);
+					dr.init(J.dht, (J.dht_bits + 7) >> 3, 0, T.lit);   // the LUT is not built yet: borrow it as the ring
 					rc = parse_dyn_header(dr, T.lens, hlit, hdist);
 					if (rc || dr.bits_used() > J.dht_bits) rc = 68;
 					dht_saved = true; dht_from = 0; dht_len = J.dht_bits;
 				}
 			} else {
 				const uint64_t blk = br.bits_used();
-				br.refill();
 				const uint32_t h = br.get(3);
 				final_block = h & 1;
 				btype = h >> 1;
 				if (btype == 0) {
-					br.drop(br.cnt & 7);
-					br.refill();
-					const uint32_t v = br.get(32);
+					br.align_byte();
+					const uint32_t v = br.peek32();
+					br.drop(32);
 					if (((v ^ (v >> 16)) & 0xffff) != 0xffff) rc = NXGPU_E_DATA;
 					stored_len = v & 0xffff;
 					// give the buffered bytes back: stored data is copied straight from memory
-					stored_at = br.pos - (br.cnt >> 3);
+					stored_at = br.byte_pos();
 				} else if (btype == 2) {
 					dht_from = br.bits_used();
 					rc = parse_dyn_header(br, T.lens, hlit, hdist);
@@ -355,7 +412,7 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 				break;
 			}
 			if (lane == 0)
-				br.init(J.src, J.src_len, stored_at + stored_len);
+				br.seek(stored_at + stored_len);
 			__syncwarp();
 			continue;
 		}
@@ -378,47 +435,76 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 		// ---- symbols ----
 		bool block_done = false;
 		while (!block_done && !rc && !suspended) {
+			// ---- stage the compressed input: one coalesced 128-byte load per lane-0 shortfall ----
+			{
+				const uint32_t wp = __shfl_sync(0xffffffffu, br.wpos, 0);
+				uint32_t st = __shfl_sync(0xffffffffu, br.staged, 0);
+				if (st - wp < kInAhead && (uint64_t)st * 4 < br.end) {
+					const uint32_t w0 = BitReader::load_word(br.base32, br.skip, br.end, st + lane);
+					const uint32_t w1 = BitReader::load_word(br.base32, br.skip, br.end, st + 32 + lane);
+					T.in[(st + lane) % kInWords] = w0;
+					T.in[(st + 32 + lane) % kInWords] = w1;
+					br.staged = st + 64;
+					__syncwarp();
+				}
+			}
 			uint32_t qn = 0;
 			if (lane == 0) {
+				// overruns can only happen once the last words of the source are in the window: a batch
+				// consumes at most 32 x 48 bits = 48 words
+				const bool careful = br.wpos + 52 > br.end_word;
 				while (qn < 32) {
-					const uint64_t sym_at = br.bits_used();
+					const uint32_t s_wpos = br.wpos, s_bo = br.bo;     // where this symbol starts (careful mode)
 					int err = 0;
 					uint32_t tokv = 0;
 					int kind = 0;                            // 0 literal, 1 match, 2 end of block
-					br.refill();
-					uint32_t e = T.lit[br.peek(kLitBits)];
-					uint32_t type, value, nextra;
-					if (e & 15) {
-						br.drop(e & 15);
-						type = (e >> 4) & 3; nextra = (e >> 6) & 15; value = e >> 10;
+					const uint32_t w = br.peek32();
+					const uint32_t e = T.lit[w & ((1u << kLitBits) - 1)];
+					const uint32_t cl = e & 15;
+					uint32_t type, len = 0;
+					if (cl) {
+						type = (e >> 4) & 3;
+						if (type == 0) {
+							br.drop(cl);
+							tokv = e >> 10;
+							if (!careful) {
+								T.q[qn++] = tokv;            // literal straight from the table: the common case
+								continue;
+							}
+						} else {
+							const uint32_t nextra = (e >> 6) & 15;
+							len = (e >> 10) + ((w >> cl) & ((1u << nextra) - 1));
+							br.drop(cl + nextra);
+						}
 					} else {
 						const int sym = slow_decode(br, T.lit_count, T.lit_sorted);
-						if (sym < 0 || sym >= 286) { err = 66; type = 2; value = 0; nextra = 0; }
-						else if (sym < 256) { type = 0; value = sym; nextra = 0; }
-						else if (sym == 256) { type = 2; value = 0; nextra = 0; }
-						else { type = 1; value = k_len_base[sym - 257]; nextra = k_len_extra[sym - 257]; }
+						if (sym < 0 || sym >= 286) { err = 66; type = 2; }
+						else if (sym < 256) { type = 0; tokv = (uint32_t)sym; }
+						else if (sym == 256) { type = 2; }
+						else { type = 1; len = k_len_base[sym - 257] + br.get(k_len_extra[sym - 257]); }
 					}
-					if (!err && type == 0) { tokv = value; kind = 0; }
-					else if (!err && type == 2) { kind = 2; }
-					else if (!err) {
-						const uint32_t len = value + br.get(nextra);
-						br.refill();
-						uint32_t d = T.dist[br.peek(kDistBits)];
-						uint32_t dbase = 1, dextra = 0;
-						if (d & 15) {
-							br.drop(d & 15);
-							dextra = (d >> 4) & 15; dbase = d >> 8;
+					if (type == 2) {
+						kind = 2;
+					} else if (type == 1) {
+						const uint32_t wd = br.peek32();
+						const uint32_t d = T.dist[wd & ((1u << kDistBits) - 1)];
+						const uint32_t dl = d & 15;
+						uint32_t dist = 1;
+						if (dl) {
+							const uint32_t dextra = (d >> 4) & 15;
+							dist = (d >> 8) + ((wd >> dl) & ((1u << dextra) - 1));
+							br.drop(dl + dextra);
 						} else {
 							const int ds = slow_decode(br, T.dist_count, T.dist_sorted);
 							if (ds < 0 || ds >= 30) err = 66;
-							else { dbase = k_dist_base[ds]; dextra = k_dist_extra[ds]; }
+							else dist = k_dist_base[ds] + br.get(k_dist_extra[ds]);
 						}
-						const uint32_t dist = dbase + br.get(dextra);
 						tokv = tok_match(len, dist); kind = 1;
 					}
-					if (br.overrun()) {
+					if (careful && br.overrun()) {
 						// the symbol needs bits the source does not have
 						if (job) {
+							const uint64_t sym_at = (uint64_t)(s_wpos - 3) * 32 + s_bo - br.skip * 8;
 							o_sfbt = (btype == 1 ? 0xau : 0xcu) | (final_block ? 1u : 0u);
 							o_subc = (uint32_t)(total_bits - sym_at);
 							suspended = true;
@@ -454,9 +540,33 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 			if (total > J.dst_cap - out) { rc = job ? 13 : NXGPU_E_BUF; break; }
 			const bool bad = is_m && tok_dist(t) > my_out + J.hist_len;
 			if (__any_sync(0xffffffffu, bad)) { rc = job ? 67 : NXGPU_E_DATA; break; }
-			if (lane < qn && !is_m)
-				J.dst[my_out] = (uint8_t)t;
-			uint32_t mm = __ballot_sync(0xffffffffu, is_m);
+			// A match whose source ends in front of this batch's output (distance >= the bytes the batch
+			// has produced up to and including it) depends on nothing written in this batch.  Those and
+			// the literals are materialised byte-parallel: output byte b belongs to the first symbol whose
+			// inclusive prefix exceeds b (binary search over the lanes' prefixes by shuffle), so all the
+			// loads of a batch are in flight together.  The rest (short distances) follow one by one.
+			uint32_t mm = __ballot_sync(0xffffffffu, is_m && tok_dist(t) < incl);
+			uint8_t *const dq = J.dst + out;
+			for (uint32_t b0 = 0; b0 < total; b0 += 64) {
+				const uint32_t ba = b0 + lane, bb = ba + 32;
+				uint32_t la = 0, lb = 0;
+#pragma unroll
+				for (int s = 16; s; s >>= 1) {
+					const uint32_t va = __shfl_sync(0xffffffffu, incl, la + s - 1);
+					const uint32_t vb = __shfl_sync(0xffffffffu, incl, lb + s - 1);
+					if (va <= ba) la += s;
+					if (vb <= bb) lb += s;
+				}
+				const uint32_t ta = __shfl_sync(0xffffffffu, t, la), ia = __shfl_sync(0xffffffffu, incl, la);
+				const uint32_t tb = __shfl_sync(0xffffffffu, t, lb), ib = __shfl_sync(0xffffffffu, incl, lb);
+				uint32_t xa = ta, xb = tb;
+				const bool ca = ba < total && tok_is_match(ta) && tok_dist(ta) >= ia;
+				const bool cb = bb < total && tok_is_match(tb) && tok_dist(tb) >= ib;
+				if (ca) xa = dq[(int32_t)ba - (int32_t)tok_dist(ta)];
+				if (cb) xb = dq[(int32_t)bb - (int32_t)tok_dist(tb)];
+				if (ba < total && (ca || !tok_is_match(ta))) dq[ba] = (uint8_t)xa;
+				if (bb < total && (cb || !tok_is_match(tb))) dq[bb] = (uint8_t)xb;
+			}
 			__syncwarp();
 			while (mm) {
 				const int src_lane = __ffs(mm) - 1;
@@ -565,7 +675,8 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 	}
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+template <int kMinCtas>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtas)
 inflate_kernel(const InflateJob *__restrict__ jobs, InflateOut *__restrict__ outs, uint32_t n_jobs, uint32_t *next_job)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -587,12 +698,13 @@ inflate_kernel(const InflateJob *__restrict__ jobs, InflateOut *__restrict__ out
 
 } // namespace
 
-cudaError_t launch_inflate(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s)
+template <int kMinCtas>
+static cudaError_t launch_inflate_t(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s)
 {
 	static bool configured = false;
 	const size_t smem = sizeof(WarpTables) * kWarpsPerCta;
 	if (!configured) {
-		cudaError_t e = cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaError_t e = cudaFuncSetAttribute(inflate_kernel<kMinCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess)
 			return e;
 		configured = true;
@@ -600,17 +712,29 @@ cudaError_t launch_inflate(const InflateJob *jobs, InflateOut *outs, uint32_t n_
 	cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
 	if (e != cudaSuccess)
 		return e;
-	// persistent grid: CTAs-per-SM limited by shared memory (about 3 with 8 warps each)
+	// persistent grid: as many CTAs as fit an SM (registers and shared memory allow kMinCtas)
 	int per_sm = 1;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_kernel, kWarpsPerCta * 32, smem);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_kernel<kMinCtas>, kWarpsPerCta * 32, smem);
 	if (per_sm < 1)
 		per_sm = 1;
 	uint32_t want = (n_jobs + kWarpsPerCta - 1) / kWarpsPerCta;
 	uint32_t grid = (uint32_t)(kNumSMs * per_sm);
 	if (want < grid)
 		grid = want ? want : 1;
-	inflate_kernel<<<grid, kWarpsPerCta * 32, smem, s>>>(jobs, outs, n_jobs, counter);
+	inflate_kernel<kMinCtas><<<grid, kWarpsPerCta * 32, smem, s>>>(jobs, outs, n_jobs, counter);
 	return cudaGetLastError();
+}
+
+cudaError_t launch_inflate(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s)
+{
+	static const int occ = getenv("NXGPU_INFLATE_OCC") ? atoi(getenv("NXGPU_INFLATE_OCC")) : 7;   // developer switch
+	if (occ <= 4)
+		return launch_inflate_t<4>(jobs, outs, n_jobs, counter, s);
+	if (occ == 5)
+		return launch_inflate_t<5>(jobs, outs, n_jobs, counter, s);
+	if (occ == 6)
+		return launch_inflate_t<6>(jobs, outs, n_jobs, counter, s);
+	return launch_inflate_t<7>(jobs, outs, n_jobs, counter, s);
 }
 
 } // namespace nxgpu
