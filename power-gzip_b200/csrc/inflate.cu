@@ -10,6 +10,7 @@
 // buffer itself (L1/L2-resident), so no history copies are needed (the reference's host side copies
 // 32 KiB per job, lib/nx_inflate.c:1633-1687).
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -24,8 +25,9 @@ constexpr uint32_t kInWords = 128;         // per-warp staging ring for the comp
 constexpr uint32_t kInAhead = 64;          // the warp tops the ring up while fewer words than this lie ahead
 
 struct WarpTables {
-	uint32_t lit[1 << kLitBits];      // codelen | type<<4 | nextra<<6 | value<<10   (0 = slow path)
-	uint32_t dist[1 << kDistBits];    // codelen | nextra<<4 | base<<8
+	uint32_t lit[1 << kLitBits];      // codelen | type<<4 | nextra<<6 | value<<10   (0 = slow path); type 2 literal (value = byte),
+	                                  // 3 length (value = base - 3), 1 end of block: bit 5 set = the fast loop handles it
+	uint32_t dist[1 << kDistBits];    // codelen | nextra<<4 | (base - 1)<<8
 	uint16_t lit_sorted[288];
 	uint16_t dist_sorted[32];
 	uint16_t lit_count[16], dist_count[16];
@@ -134,6 +136,17 @@ struct BitReader {
 	__device__ __forceinline__ uint32_t byte_pos() const { return (uint32_t)(bits_abs() >> 3) - skip; }
 };
 
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+	return v;
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v)
+{
+	asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
 // canonical decode, one bit at a time (codes longer than the primary table)
 __device__ int slow_decode(BitReader &br, const uint16_t *count, const uint16_t *sorted)
 {
@@ -210,13 +223,13 @@ __device__ bool build_table(const uint8_t *lens, int n, uint32_t *lut, int lut_b
 				const uint32_t code = __brev(nc + r) >> (32 - l);
 				uint32_t e;
 				if (is_dist) {
-					e = s < 30 ? ((uint32_t)l | ((uint32_t)k_dist_extra[s] << 4) | ((uint32_t)k_dist_base[s] << 8)) : 0;
+					e = s < 30 ? ((uint32_t)l | ((uint32_t)k_dist_extra[s] << 4) | ((uint32_t)(k_dist_base[s] - 1) << 8)) : 0;
 				} else if (s < 256) {
-					e = (uint32_t)l | (0u << 4) | ((uint32_t)s << 10);
+					e = (uint32_t)l | (2u << 4) | ((uint32_t)s << 10);
 				} else if (s == 256) {
-					e = (uint32_t)l | (2u << 4);
+					e = (uint32_t)l | (1u << 4);
 				} else if (s < 286) {
-					e = (uint32_t)l | (1u << 4) | ((uint32_t)k_len_extra[s - 257] << 6) | ((uint32_t)k_len_base[s - 257] << 10);
+					e = (uint32_t)l | (3u << 4) | ((uint32_t)k_len_extra[s - 257] << 6) | ((uint32_t)(k_len_base[s - 257] - 3) << 10);
 				} else {
 					e = 0;
 				}
@@ -272,6 +285,12 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 	const uint32_t lane = threadIdx.x & 31;
 	const bool job = J.wrap == kWrapJob;     // NX decompress-job semantics: stop at the source end and report where
 	const uint64_t total_bits = (uint64_t)J.src_len * 8;
+	// shared-window addresses of the tables, computed once (the fast decode loop addresses them directly)
+	uint32_t lit_sa = (uint32_t)__cvta_generic_to_shared(T.lit);
+	asm volatile("" : "+r"(lit_sa));
+	const uint32_t dist_sa = lit_sa + (uint32_t)offsetof(WarpTables, dist);
+	const uint32_t q_sa = lit_sa + (uint32_t)offsetof(WarpTables, q);
+	const uint32_t ring_sa = lit_sa + (uint32_t)offsetof(WarpTables, in);
 	BitReader br;
 	br.setup(J.src, J.src_len, T.in);   // every lane knows the geometry; the read position lives in lane 0
 	int rc = 0;                      // uniform after each broadcast
@@ -454,6 +473,49 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 				// consumes at most 32 x 48 bits = 48 words
 				const bool careful = br.wpos + 52 > br.end_word;
 				while (qn < 32) {
+					if (!careful) {
+						// ---- fast loop: symbols straight out of the tables, no bounds checks needed.  The
+						// ring cannot run dry here: the staging above left >= 64 words ahead and a batch
+						// consumes at most 48.  Anything else (long code, end of block) drops to the
+						// general code below for one symbol.
+						uint32_t w0 = br.w0, w1 = br.w1, w2 = br.w2, bo = br.bo, wpos = br.wpos;
+						do {
+							const uint32_t w = __funnelshift_r(w0, w1, bo);
+							const uint32_t e = lds32(lit_sa + ((w << 2) & ((4u << kLitBits) - 4)));
+							if (!(e & 0x20))
+								break;
+							uint32_t tokv = e >> 10;
+							uint32_t adv = e & 15;
+							if (e & 0x10) {
+								const uint32_t nextra = (e >> 6) & 15;
+								tokv += (w >> adv) & ~(~0u << nextra);
+								bo += adv + nextra;
+								if (bo >= 32) {
+									w0 = w1; w1 = w2; w2 = lds32(ring_sa + ((wpos << 2) & (4 * kInWords - 4))); wpos++;
+									bo -= 32;
+								}
+								const uint32_t wd = __funnelshift_r(w0, w1, bo);
+								const uint32_t d = lds32(dist_sa + ((wd << 2) & ((4u << kDistBits) - 4)));
+								const uint32_t dl = d & 15;
+								if (!dl)
+									break;       // long distance code: the general code redoes the whole symbol (br is unchanged)
+								const uint32_t dextra = (d >> 4) & 15;
+								const uint32_t dm1 = (d >> 8) + ((wd >> dl) & ~(~0u << dextra));
+								tokv = 0x80000000u | (tokv << 15) | dm1;
+								adv = dl + dextra;
+							}
+							bo += adv;
+							if (bo >= 32) {
+								w0 = w1; w1 = w2; w2 = lds32(ring_sa + ((wpos << 2) & (4 * kInWords - 4))); wpos++;
+								bo -= 32;
+							}
+							sts32(q_sa + 4 * qn, tokv);
+							qn++;
+							br.w0 = w0; br.w1 = w1; br.w2 = w2; br.bo = bo; br.wpos = wpos;
+						} while (qn < 32);
+						if (qn == 32)
+							break;
+					}
 					const uint32_t s_wpos = br.wpos, s_bo = br.bo;     // where this symbol starts (careful mode)
 					int err = 0;
 					uint32_t tokv = 0;
@@ -463,18 +525,19 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 					const uint32_t cl = e & 15;
 					uint32_t type, len = 0;
 					if (cl) {
-						type = (e >> 4) & 3;
-						if (type == 0) {
+						const uint32_t tc = (e >> 4) & 3;
+						if (tc == 2) {
+							type = 0;
 							br.drop(cl);
 							tokv = e >> 10;
-							if (!careful) {
-								T.q[qn++] = tokv;            // literal straight from the table: the common case
-								continue;
-							}
-						} else {
+						} else if (tc == 3) {
+							type = 1;
 							const uint32_t nextra = (e >> 6) & 15;
-							len = (e >> 10) + ((w >> cl) & ((1u << nextra) - 1));
+							len = (e >> 10) + 3 + ((w >> cl) & ((1u << nextra) - 1));
 							br.drop(cl + nextra);
+						} else {
+							type = 2;
+							br.drop(cl);
 						}
 					} else {
 						const int sym = slow_decode(br, T.lit_count, T.lit_sorted);
@@ -492,7 +555,7 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 						uint32_t dist = 1;
 						if (dl) {
 							const uint32_t dextra = (d >> 4) & 15;
-							dist = (d >> 8) + ((wd >> dl) & ((1u << dextra) - 1));
+							dist = (d >> 8) + 1 + ((wd >> dl) & ((1u << dextra) - 1));
 							br.drop(dl + dextra);
 						} else {
 							const int ds = slow_decode(br, T.dist_count, T.dist_sorted);
