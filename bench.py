@@ -398,6 +398,24 @@ def main():
         extra["checksum_storm"] = {"buffers": len(small), "bytes": sum(x[1] for x in small), "buffers_per_s": round(len(small) / dt),
                                    "GBps": round(sum(x[1] for x in small) / dt / 1e9, 2), "note": "4-64 KiB buffers, one batched call, host wall clock"}
 
+    if rank == 0 and world == 1 and not args.skip_extra:
+        # ---- many concurrent small z_streams through the UNCHANGED zlib surface (configs[4]): the reference's host
+        # code over the GPU engine, test/test_multithread_stress.c pattern; descriptors coalesce inside nxu_run_job ----
+        gpu_nxz = os.path.join(ROOT, "oracle", "_ref", "libnxz_gpu.so")
+        if os.path.exists(gpu_nxz):
+            import subprocess
+            try:
+                env = dict(os.environ, NX_GZIP_LOGFILE="/tmp/nx_bench.log")
+                p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "nx_dropin_driver.py"), gpu_nxz, "stress", "64", "2"],
+                                   capture_output=True, text=True, timeout=300, env=env)
+                st = json.loads(p.stdout.strip().splitlines()[-1])
+                extra["zstream_storm"] = {"threads": st["threads"], "calls_per_s": round(st["calls_per_s"]), "MBps": round(st["MBps"], 1),
+                                          "descriptors": st.get("jobs"), "gpu_batches": st.get("batches"), "largest_batch": st.get("max_batch"),
+                                          "errors": len(st["errors"]),
+                                          "note": "compress()/uncompress() of 4 KiB-1 MiB buffers from 64 threads via libnxz host code + nxu_run_job, Python harness"}
+            except Exception as e:                      # noqa: BLE001 - an extra, never fatal
+                extra["zstream_storm"] = {"error": repr(e)[:200]}
+
     if rank == 0:
         threads = os.cpu_count() or 1
         sample = min(n, max(CHUNK * threads, 4 * 1024 * 1024 * threads))

@@ -237,6 +237,12 @@ int nxgpu_inflate_batch(nxgpu_ctx *ctx, const nxgpu_inflate_item *items, size_t 
 uint64_t nxgpu_makedata(int seed, int log2size, const void *seedfile, uint64_t seedfile_len,
 			void *out, uint64_t out_cap);
 
+/* --- job coalescing inside nxu_run_job (the reference submits one CRB per
+ * paste, lib/gzip_vas.c:281-417).  Descriptors submitted concurrently from different threads are
+ * run as one GPU batch; this reports how that went on device `dev` since process start:
+ * batches served, descriptors served, largest batch. */
+void nxgpu_job_stats(int dev, uint64_t *batches, uint64_t *jobs, uint64_t *max_batch);
+
 #ifdef __cplusplus
 }
 #endif

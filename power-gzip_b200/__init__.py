@@ -72,7 +72,7 @@ EXPORTS = [
     "nxgpu_timer_start", "nxgpu_timer_stop", "nxgpu_launch_count", "nxgpu_kernel_time", "nxgpu_kernel_time_reset",
     "nxgpu_checksum_batch", "nxgpu_crc32", "nxgpu_adler32", "nxgpu_crc32_combine", "nxgpu_adler32_combine",
     "nxgpu_deflate_batch", "nxgpu_deflate_bound", "nxgpu_deflate_stream", "nxgpu_deflate_stream_bound",
-    "nxgpu_inflate_batch", "nxgpu_makedata",
+    "nxgpu_inflate_batch", "nxgpu_makedata", "nxgpu_job_stats",
 ]
 
 _lib = None
@@ -116,6 +116,7 @@ def load_library() -> C.CDLL:
         "nxgpu_deflate_stream_bound": (u64, [u64, u32]),
         "nxgpu_inflate_batch": (i32, [vp, P(InflateItem), sz, P(InflateResult), i32]),
         "nxgpu_makedata": (u64, [i32, i32, vp, u64, vp, u64]),
+        "nxgpu_job_stats": (None, [i32, P(u64), P(u64), P(u64)]),
         "nx_function_begin": (i32, [i32, i32, vp]),
         "nx_function_end": (i32, [vp]),
         "nx_wait_ticks": (u64, [u64, u64, i32]),

@@ -76,7 +76,7 @@ struct nxgpu_ctx {
 	uint32_t jobs_per_flag = 0;
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
 	uint64_t launches = 0;
-	DevBuf d_jobs, d_outs, d_tok, d_slots, d_ranges, d_parts, d_rs, d_seeds, d_cks, d_in, d_out, d_offsets, d_misc, d_dst_ptrs, d_dht, d_lz, d_ctr, d_flags;
+	DevBuf d_jobs, d_outs, d_tok, d_slots, d_ranges, d_parts, d_rs, d_seeds, d_cks, d_in, d_out, d_offsets, d_misc, d_dst_ptrs, d_dht, d_lz, d_ctr, d_flags, d_ijobs, d_iouts;
 	PinBuf h_jobs, h_outs, h_misc, h_stage, h_ones;
 	KernelTimer timers[3];           // 0 deflate, 1 inflate, 2 checksum
 	bool timing = true;
@@ -89,4 +89,7 @@ int deflate_device(nxgpu_ctx *c, DeflateJob *jobs_h, size_t n, int level, bool w
 int checksum_device(nxgpu_ctx *c, const nxgpu_cksum_item *items, size_t n, int which);
 void timer_begin(nxgpu_ctx *c, int fam);
 void timer_end(nxgpu_ctx *c, int fam);
+// nxgpu_job.cu: NX job descriptors, one at a time or coalesced
+int run_job_impl(nxgpu_ctx *c, uint8_t *crb_cpb);
+void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n);
 }

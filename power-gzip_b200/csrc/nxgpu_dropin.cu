@@ -11,12 +11,13 @@
 #include "common.cuh"
 #include "../../include/nxgpu.h"
 
-namespace nxgpu {
-int run_job_impl(nxgpu_ctx *ctx, uint8_t *crb_cpb);   // nxgpu_job.cu
-}
+#include <condition_variable>
+#include <deque>
+#include <vector>
+#include "ctx.cuh"
 
 namespace {
-std::mutex g_mu;
+std::mutex g_mu;                  // guards g_ctx and the per-device queues
 nxgpu_ctx *g_ctx[16];
 
 // one shared context per device, created on first use (handles are shared by up to
@@ -32,6 +33,91 @@ nxgpu_ctx *ctx_for(int dev)
 		g_ctx[dev] = c;
 	}
 	return g_ctx[dev];
+}
+
+// ---- job coalescing ----
+// nxu_run_job is synchronous and is called from arbitrary application threads, one z_stream each
+// (test/test_multithread_stress.c runs up to 176).  Whoever finds the device idle becomes the
+// combiner: it takes everything that is pending — its own descriptor plus whatever other threads
+// queued while the previous batch was on the GPU — and runs it as ONE batch (run_jobs_batch: one
+// upload, one deflate launch, one inflate launch, one checksum pass, two synchronisations).  The other
+// threads sleep on a condition variable until their descriptor is complete; if the combiner's own
+// job is done while work is still queued it hands the role to one of the waiters.
+struct Request {
+	enum Kind { JOB, CRC } kind = JOB;
+	uint8_t *crb = nullptr;       // JOB
+	uint32_t crc = 0;             // CRC: running value in, result out
+	const void *p = nullptr;
+	unsigned long len = 0;
+	int rc = 0;
+	bool done = false;
+};
+struct DevQueue {
+	std::deque<Request *> pending;
+	bool busy = false;            // a combiner is at work
+	std::condition_variable cv;
+	uint64_t batches = 0, jobs = 0, max_batch = 0;
+};
+DevQueue g_q[16];
+constexpr size_t kMaxBatch = 512;
+
+void serve(nxgpu_ctx *ctx, std::vector<Request *> &batch)
+{
+	std::vector<uint8_t *> crbs;
+	std::vector<Request *> jobs;
+	for (Request *r : batch)
+		if (r->kind == Request::JOB) { crbs.push_back(r->crb); jobs.push_back(r); }
+	if (!crbs.empty()) {
+		std::vector<int> rcs(crbs.size(), 0);
+		nxgpu::run_jobs_batch(ctx, crbs.data(), rcs.data(), crbs.size());
+		for (size_t i = 0; i < jobs.size(); i++)
+			jobs[i]->rc = rcs[i];
+	}
+	for (Request *r : batch)
+		if (r->kind == Request::CRC) {
+			// raw register update (no inversion): crc32(seed) = ~raw(~seed)  =>  raw(r) = ~crc32(~r)
+			uint32_t out = 0;
+			r->rc = nxgpu_crc32(ctx, ~r->crc, r->p, r->len, NXGPU_MEM_HOST, &out);
+			r->crc = ~out;
+		}
+}
+
+int submit(int dev, Request &r)
+{
+	if (dev < 0 || dev >= 16)
+		dev = 0;
+	DevQueue &q = g_q[dev];
+	std::unique_lock<std::mutex> lk(g_mu);
+	nxgpu_ctx *ctx = ctx_for(dev);
+	if (!ctx)
+		return -EAGAIN;
+	q.pending.push_back(&r);
+	for (;;) {
+		q.cv.wait(lk, [&] { return r.done || !q.busy; });
+		if (r.done)
+			return r.rc;
+		// become the combiner
+		q.busy = true;
+		while (!r.done && !q.pending.empty()) {
+			std::vector<Request *> batch;
+			while (!q.pending.empty() && batch.size() < kMaxBatch) {
+				batch.push_back(q.pending.front());
+				q.pending.pop_front();
+			}
+			lk.unlock();
+			serve(ctx, batch);
+			lk.lock();
+			q.batches++; q.jobs += batch.size();
+			if (batch.size() > q.max_batch) q.max_batch = batch.size();
+			for (Request *b : batch)
+				b->done = true;
+			q.cv.notify_all();
+		}
+		q.busy = false;
+		q.cv.notify_all();        // a waiter whose request is still queued takes over
+		if (r.done)
+			return r.rc;
+	}
 }
 } // namespace
 
@@ -92,24 +178,32 @@ int nxu_run_job(nx_gzip_crb_cpb_t *c, nx_devp_t h)
 	nxgpu_dev_prefix *d = reinterpret_cast<nxgpu_dev_prefix *>(h);
 	if (!d->paste_addr)
 		return -EAGAIN;
-	std::lock_guard<std::mutex> lk(g_mu);   // one job at a time per process for now (coalescing)
-	nxgpu_ctx *ctx = ctx_for(d->fd);
-	if (!ctx)
-		return -EAGAIN;
-	return nxgpu::run_job_impl(ctx, reinterpret_cast<uint8_t *>(c));
+	Request r;
+	r.kind = Request::JOB;
+	r.crb = reinterpret_cast<uint8_t *>(c);
+	return submit(d->fd, r);
+}
+
+// additive: how well the coalescing worked (batches served, descriptors served, largest batch) on device `dev`
+void nxgpu_job_stats(int dev, uint64_t *batches, uint64_t *jobs, uint64_t *max_batch)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	const DevQueue &q = g_q[(dev < 0 || dev >= 16) ? 0 : dev];
+	if (batches) *batches = q.batches;
+	if (jobs) *jobs = q.jobs;
+	if (max_batch) *max_batch = q.max_batch;
 }
 
 unsigned int __crc32_vpmsum(unsigned int crc, const void *p, unsigned long len)
 {
-	// raw register update (no inversion): crc32(seed) = ~raw(~seed)  =>  raw(r) = ~crc32(~r)
-	std::lock_guard<std::mutex> lk(g_mu);
-	nxgpu_ctx *ctx = ctx_for(0);
-	uint32_t out = 0;
-	if (!ctx || nxgpu_crc32(ctx, ~crc, p, len, NXGPU_MEM_HOST, &out) != 0) {
+	Request r;
+	r.kind = Request::CRC;
+	r.crc = crc; r.p = p; r.len = len;
+	if (submit(0, r) != 0) {
 		fprintf(stderr, "libnxgpu: __crc32_vpmsum: no usable GPU (%s)\n", nxgpu_last_error());
 		abort();                  // no CPU fallback: fail loudly
 	}
-	return ~out;
+	return r.crc;
 }
 
 } // extern "C"

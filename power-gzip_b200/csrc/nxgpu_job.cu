@@ -162,12 +162,291 @@ constexpr uint32_t CE_PARTIAL = 0x4, CE_TERMINATE = 0x2, CE_TPBC_VALID = 0x1;
 
 } // namespace
 
-static int run_job_inner(nxgpu_ctx *c, uint8_t *crb);
+// One descriptor of a batch, from parsing to completion.
+namespace {
+struct JobState {
+	enum Kind { DONE, WRAP, COMP, DECOMP };
+	uint8_t *crb = nullptr, *cpb = nullptr;
+	Kind kind = DONE;
+	uint32_t fc = 0;
+	std::vector<Seg> src, dst;
+	uint64_t src_total = 0, dst_total = 0;
+	size_t in_off = 0;            // this job's source bytes in h_stage / d_in (history first)
+	size_t out_off = 0;           // decompress: first target byte in d_out (history sits right in front)
+	size_t host_off = 0;          // where the job's output bytes land in h_outs
+	uint32_t hist = 0, n_new = 0; // compress: new bytes; decompress: compressed bytes
+	uint32_t crc_seed = 0, adler_seed = 1;
+	bool use_dht = false, count = false;
+	size_t idx = 0;               // index in the DeflateJob / InflateJob array
+	size_t ck = 0;                // index in the checksum batch
+	uint32_t out_len = 0;
+	bool ok = false;              // output is to be returned
+};
+} // namespace
+
+// Runs n descriptors as ONE batch: one upload of all sources, one deflate launch for every compress
+// job, one inflate launch for every decompress job, one checksum launch pair for everything, two
+// stream synchronisations in total.  rcs[i] = 0 (CSB/CPB filled) or -EAGAIN (device unusable).
+// This is what makes many concurrent small z_streams (test/test_multithread_stress.c, LD_PRELOAD
+// users) fast without touching the zlib surface: nxu_run_job coalesces whatever is pending
+// (nxgpu_dropin.cu) and hands it over here.
+void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
+{
+	std::vector<JobState> js(n);
+	auto fail_all = [&]() { for (size_t i = 0; i < n; i++) if (js[i].kind != JobState::DONE) rcs[i] = -EAGAIN; };
+	for (size_t i = 0; i < n; i++) rcs[i] = 0;
+	if (cudaSetDevice(c->dev) != cudaSuccess) {
+		for (size_t i = 0; i < n; i++) rcs[i] = -EAGAIN;
+		return;
+	}
+	// ---- parse ----
+	size_t in_total = 0, out_total = 0, nd = 0, ni = 0;
+	for (size_t i = 0; i < n; i++) {
+		JobState &j = js[i];
+		j.crb = crbs[i];
+		j.cpb = j.crb + NXGPU_CPB;
+		j.fc = be32(j.crb + NXGPU_CRB_FC) & 0xff;
+		if (!dde_segments(j.crb + NXGPU_CRB_SRC_DDE, j.src, j.src_total) || !dde_segments(j.crb + NXGPU_CRB_DST_DDE, j.dst, j.dst_total)) {
+			complete(j.crb, 9 /* ERR_NX_BAD_DDE */, CE_TERMINATE, 0);
+			continue;
+		}
+		if (j.src_total > 0xffffff00ull || j.dst_total > 0xffffff00ull) {
+			complete(j.crb, 3, CE_TERMINATE, 0);
+			continue;
+		}
+		const uint32_t w8 = be32(j.cpb + 8);
+		// running checksums: in_adler is a plain big-endian field, in_crc holds the CRC with its
+		// bytes the other way round (lib/nx_deflate.c:1572-1577 and lib/nx_inflate.c:809-817 rely on it)
+		j.adler_seed = be32(j.cpb + NXGPU_CPB_IN_ADLER - NXGPU_CPB);
+		j.crc_seed = le32(j.cpb + NXGPU_CPB_IN_CRC - NXGPU_CPB);
+		if (j.fc == 0x1e) {
+			// GZIP_FC_WRAP (inc_nx/nxu.h:816; caller lib/nx_zlib.c:1398): copy + fresh crc32/adler32
+			if (j.dst_total < j.src_total) { complete(j.crb, 13, 0, 0); continue; }
+			j.kind = JobState::WRAP;
+			j.crc_seed = 0; j.adler_seed = 1;
+		} else if ((j.fc & 0x10) == 0) {
+			const bool resume = (j.fc & 0x08) != 0;
+			j.use_dht = (j.fc & 0x02) != 0;
+			j.count = (j.fc & 0x04) != 0;
+			j.hist = resume ? ((w8 >> 20) & 0xfff) * 16 : 0;
+			if (j.hist > j.src_total) { complete(j.crb, 3, CE_TERMINATE, 0); continue; }   // history length error
+			j.n_new = (uint32_t)(j.src_total - j.hist);
+			j.kind = JobState::COMP;
+			j.idx = nd++;
+		} else {
+			const bool resume = (j.fc & 0x04) != 0;
+			j.hist = resume ? ((w8 >> 20) & 0xfff) * 16 : 0;
+			if (j.hist > j.src_total) { complete(j.crb, 3, CE_TERMINATE, 0); continue; }
+			j.n_new = (uint32_t)(j.src_total - j.hist);
+			j.kind = JobState::DECOMP;
+			j.idx = ni++;
+			out_total += align16(j.hist);
+			j.out_off = out_total;
+			out_total += align16(j.dst_total + 32);
+		}
+		j.in_off = in_total;
+		in_total += align16(j.src_total + 48);
+	}
+	if (in_total == 0 && nd == 0 && ni == 0)
+		return;
+
+	// ---- stage every source in pinned memory (history first, exactly as the DDE list has it), one upload ----
+	if (c->h_stage.reserve(in_total + 64) || c->d_in.reserve(in_total + 64) || c->d_dht.reserve(n * 1024) ||
+	    c->h_jobs.reserve(n * 1024 + ni * sizeof(InflateJob)) || c->d_lz.reserve((nd + 1) * 316 * 4) ||
+	    c->d_out.reserve(out_total + 64) || c->d_ijobs.reserve((ni + 1) * sizeof(InflateJob)) ||
+	    c->d_iouts.reserve((ni + 1) * sizeof(InflateOut)) || c->d_misc.reserve(64)) {
+		fail_all();
+		return;
+	}
+	uint8_t *hs = static_cast<uint8_t *>(c->h_stage.p);
+	uint8_t *d_in = static_cast<uint8_t *>(c->d_in.p);
+	uint8_t *d_out = static_cast<uint8_t *>(c->d_out.p);
+	uint8_t *d_dht = static_cast<uint8_t *>(c->d_dht.p);
+	uint8_t *h_dht = static_cast<uint8_t *>(c->h_jobs.p);                      // n x 1024: caller tables, as the kernels want them
+	InflateJob *ij = reinterpret_cast<InflateJob *>(h_dht + n * 1024);
+	for (size_t i = 0; i < n; i++)
+		if (js[i].kind != JobState::DONE)
+			gather(js[i].src, hs + js[i].in_off);
+	if (in_total && cudaMemcpyAsync(d_in, hs, in_total, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { fail_all(); return; }
+
+	// ---- device job arrays ----
+	std::vector<DeflateJob> dj(nd);
+	bool any_dht = false;
+	for (size_t i = 0; i < n; i++) {
+		JobState &j = js[i];
+		if (j.kind == JobState::COMP) {
+			DeflateJob &job = dj[j.idx];
+			memset(&job, 0, sizeof(job));
+			job.src = d_in + j.in_off + j.hist;
+			job.src_len = j.n_new;
+			job.hist_len = j.hist > 32768 ? 32768 : j.hist;
+			job.flags = NXGPU_F_NO_JOINER | (j.use_dht ? 0 : NXGPU_F_FIXED);
+			if (j.use_dht) {
+				const uint32_t dhtlen = be32(j.cpb + 12) & 0xfff;
+				uint8_t *blob = h_dht + i * 1024;
+				memset(blob, 0, 320 + 288);
+				if (dhtlen < 42 || dhtlen > 288 * 8 || !dht_to_lengths(j.cpb + NXGPU_CPB_IN_DHT - NXGPU_CPB, dhtlen, blob)) {
+					complete(j.crb, 68 /* invalid DHT */, CE_TERMINATE, 0);
+					j.kind = JobState::DONE;
+					job.src_len = 0; job.flags |= NXGPU_F_FIXED;       // keeps its slot in the launch, result ignored
+					continue;
+				}
+				memcpy(blob + 320, j.cpb + NXGPU_CPB_IN_DHT - NXGPU_CPB, (dhtlen + 7) / 8);
+				job.dht = d_dht + i * 1024;
+				job.dht_bits = dhtlen;
+				any_dht = true;
+			}
+			if (j.count)
+				job.lzcount = static_cast<uint32_t *>(c->d_lz.p) + j.idx * 316;
+		} else if (j.kind == JobState::DECOMP) {
+			const uint32_t w8 = be32(j.cpb + 8), w12 = be32(j.cpb + 12);
+			const bool resume = (j.fc & 0x04) != 0;
+			const uint32_t in_subc = resume ? (w8 & 7) : 0;
+			const uint32_t sfbt = resume ? (w12 >> 16) & 0xf : 0;
+			InflateJob &job = ij[j.idx];
+			memset(&job, 0, sizeof(job));
+			job.src = d_in + j.in_off + j.hist;
+			job.src_len = j.n_new;
+			job.wrap = kWrapJob;
+			job.dst = d_out + j.out_off;
+			job.dst_cap = (uint32_t)j.dst_total;
+			job.hist_len = j.hist;
+			job.start_bit = (8 - in_subc) & 7;
+			job.sfbt = sfbt;
+			job.rembytecnt = w12 & 0xffff;
+			job.out_dht = d_dht + i * 1024 + 640;
+			if ((sfbt & 0xe) == 0xc) {
+				job.dht_bits = w12 & 0xfff;
+				memcpy(h_dht + i * 1024, j.cpb + NXGPU_CPB_IN_DHT - NXGPU_CPB, 288);
+				job.dht = d_dht + i * 1024;
+				any_dht = true;
+			}
+			// the window: the history bytes go right in front of the target (device-to-device, they are already up)
+			if (j.hist && cudaMemcpyAsync(d_out + j.out_off - j.hist, d_in + j.in_off, j.hist, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) { fail_all(); return; }
+		}
+	}
+	if (any_dht && cudaMemcpyAsync(d_dht, h_dht, n * 1024, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { fail_all(); return; }
+
+	// ---- launches ----
+	if (nd && deflate_device(c, dj.data(), nd, job_level(), false)) { fail_all(); return; }
+	if (ni) {
+		if (cudaMemcpyAsync(c->d_ijobs.p, ij, ni * sizeof(InflateJob), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { fail_all(); return; }
+		timer_begin(c, 1);
+		if (launch_inflate(static_cast<const InflateJob *>(c->d_ijobs.p), static_cast<InflateOut *>(c->d_iouts.p), (uint32_t)ni,
+				   static_cast<uint32_t *>(c->d_misc.p), c->stream) != cudaSuccess) { fail_all(); return; }
+		timer_end(c, 1);
+		c->launches++;
+	}
+	// ---- results of the codec kernels (sizes, states) ----
+	const size_t res_bytes = align16(nd * sizeof(DeflateOut)) + align16(ni * sizeof(InflateOut)) + align16(nd * 316 * 4) + n * 288 + n * 8 + 64;
+	size_t data_total = 0;
+	for (size_t i = 0; i < n; i++) {
+		js[i].host_off = res_bytes + data_total;
+		if (js[i].kind == JobState::COMP) data_total += align16(2 * (size_t)js[i].n_new + 2048);
+		else if (js[i].kind == JobState::DECOMP) data_total += align16(js[i].dst_total + 64);
+	}
+	if (c->h_outs.reserve(res_bytes + data_total + 64)) { fail_all(); return; }
+	uint8_t *ho = static_cast<uint8_t *>(c->h_outs.p);
+	DeflateOut *dout = reinterpret_cast<DeflateOut *>(ho);
+	InflateOut *iout = reinterpret_cast<InflateOut *>(ho + align16(nd * sizeof(DeflateOut)));
+	uint32_t *lz = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(iout) + align16(ni * sizeof(InflateOut)));
+	uint8_t *odht = reinterpret_cast<uint8_t *>(lz) + align16(nd * 316 * 4);
+	uint32_t *ck = reinterpret_cast<uint32_t *>(odht + n * 288);
+	bool any_count = false, any_decomp_dht = false;
+	for (size_t i = 0; i < n; i++) { any_count |= js[i].kind == JobState::COMP && js[i].count; any_decomp_dht |= js[i].kind == JobState::DECOMP; }
+	if (nd && cudaMemcpyAsync(dout, c->d_outs.p, nd * sizeof(DeflateOut), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { fail_all(); return; }
+	if (ni && cudaMemcpyAsync(iout, c->d_iouts.p, ni * sizeof(InflateOut), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { fail_all(); return; }
+	if (any_count && cudaMemcpyAsync(lz, c->d_lz.p, nd * 316 * 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { fail_all(); return; }
+	if (cudaStreamSynchronize(c->stream) != cudaSuccess) { fail_all(); return; }
+
+	// ---- per-job verdict; checksums and output bytes of the good ones ----
+	std::vector<nxgpu_cksum_item> items;
+	for (size_t i = 0; i < n; i++) {
+		JobState &j = js[i];
+		if (j.kind == JobState::WRAP) {
+			j.ok = true; j.out_len = (uint32_t)j.src_total;
+			j.ck = items.size();
+			items.push_back({ d_in + j.in_off, j.src_total, 0, 1 });
+		} else if (j.kind == JobState::COMP) {
+			const DeflateOut &o = dout[j.idx];
+			if (o.rc == 66) { complete(j.crb, 66, CE_TERMINATE, 0); continue; }            // a needed symbol has no code
+			if (o.rc != 0 || o.out_len > j.dst_total) { complete(j.crb, 13, 0, 0); continue; }  // ERR_NX_TARGET_SPACE: caller halves the input
+			j.ok = true; j.out_len = o.out_len;
+			j.ck = items.size();
+			items.push_back({ dj[j.idx].src, j.n_new, j.crc_seed, j.adler_seed });
+			if (o.out_len && cudaMemcpyAsync(ho + j.host_off, dj[j.idx].out, o.out_len, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { fail_all(); return; }
+		} else if (j.kind == JobState::DECOMP) {
+			const InflateOut &o = iout[j.idx];
+			if (o.rc != 0) {
+				// 13: target full, the caller retries with less input; 66/67/68: bad code / distance / table
+				complete(j.crb, (uint32_t)o.rc, o.rc == 13 ? 0 : CE_TERMINATE, 0);
+				continue;
+			}
+			j.ok = true; j.out_len = o.out_len;
+			j.ck = items.size();
+			items.push_back({ ij[j.idx].dst, o.out_len, j.crc_seed, j.adler_seed });
+			if (o.out_len && cudaMemcpyAsync(ho + j.host_off, ij[j.idx].dst, o.out_len, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { fail_all(); return; }
+			if ((o.sfbt & 0xe) == 0xc &&
+			    cudaMemcpyAsync(odht + i * 288, ij[j.idx].out_dht, 288, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { fail_all(); return; }
+		}
+	}
+	(void)any_decomp_dht;
+	if (items.empty())
+		return;
+	if (checksum_device(c, items.data(), items.size(), 3)) { for (size_t i = 0; i < n; i++) if (js[i].ok) rcs[i] = -EAGAIN; return; }
+	if (cudaMemcpyAsync(ck, c->d_cks.p, items.size() * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+	    cudaStreamSynchronize(c->stream) != cudaSuccess) { for (size_t i = 0; i < n; i++) if (js[i].ok) rcs[i] = -EAGAIN; return; }
+	const size_t nck = items.size();
+
+	// ---- hand the bytes and the parameter-block outputs back ----
+	for (size_t i = 0; i < n; i++) {
+		JobState &j = js[i];
+		if (!j.ok)
+			continue;
+		uint8_t *cpb = j.cpb;
+		put_be32(cpb + NXGPU_CPB_OUT_ADLER - NXGPU_CPB, ck[nck + j.ck]);
+		put_le32(cpb + NXGPU_CPB_OUT_CRC - NXGPU_CPB, ck[j.ck]);
+		if (j.kind == JobState::WRAP) {
+			scatter(j.dst, hs + j.in_off, j.src_total);
+			put_be32(cpb + NXGPU_CPB_OUT_SPBC_COMP - NXGPU_CPB, (uint32_t)j.src_total);
+			complete(j.crb, 0, 0, (uint32_t)j.src_total);
+		} else if (j.kind == JobState::COMP) {
+			const DeflateOut &o = dout[j.idx];
+			scatter(j.dst, ho + j.host_off, o.out_len);
+			put_be32(cpb + NXGPU_CPB_OUT_TEBC - NXGPU_CPB, (o.tebc & 7) << 16);
+			if (j.count) {
+				// 286 + 30 symbol counts, big-endian like every other field (lib/nx_dht.c:187-199 detects the
+				// byte order by looking at the end-of-block count, which is always 1)
+				uint8_t *p = cpb + NXGPU_CPB_OUT_LZCOUNT - NXGPU_CPB;
+				const uint32_t *l = lz + j.idx * 316;
+				for (int k = 0; k < 316; k++)
+					put_be32(p + 4 * k, l[k] > 0xffffff ? 0xffffff : l[k]);
+				put_be32(cpb + NXGPU_CPB_OUT_SPBC_COMP_WITH_COUNT - NXGPU_CPB, (uint32_t)j.src_total);
+			} else {
+				put_be32(cpb + NXGPU_CPB_OUT_SPBC_COMP - NXGPU_CPB, (uint32_t)j.src_total);
+			}
+			// manual Table 6-8: the target came out larger than the source
+			complete(j.crb, o.out_len > j.src_total ? 64 : 0, 0, o.out_len);
+		} else {
+			const InflateOut &o = iout[j.idx];
+			scatter(j.dst, ho + j.host_off, o.out_len);
+			put_be32(cpb + NXGPU_CPB_OUT_TEBC - NXGPU_CPB, o.subc & 0xffff);                   // out_subc: low half of this word
+			const bool in_dyn = (o.sfbt & 0xe) == 0xc;
+			put_be32(cpb + NXGPU_CPB_OUT_SFBT - NXGPU_CPB, (o.sfbt & 0xf) << 16 | (in_dyn ? (o.dhtlen & 0xfff) : (o.rembytecnt & 0xffff)));
+			if (in_dyn)
+				memcpy(cpb + NXGPU_CPB_OUT_DHT - NXGPU_CPB, odht + i * 288, 288);
+			put_be32(cpb + NXGPU_CPB_OUT_SPBC_DECOMP - NXGPU_CPB, (uint32_t)j.src_total);
+			// CC=3 with CE "partial completion" is the normal way a decompress job ends (lib/nx_inflate.c:1372-1390)
+			complete(j.crb, 3, CE_PARTIAL | CE_TPBC_VALID, o.out_len);
+		}
+	}
+}
 
 // returns 0 (CSB/CPB filled) or -EAGAIN when the device cannot be used
 int run_job_impl(nxgpu_ctx *c, uint8_t *crb)
 {
-	const int rc = run_job_inner(c, crb);
+	int rc = 0;
+	run_jobs_batch(c, &crb, &rc, 1);
 	static const bool trace = getenv("NXGPU_TRACE") != nullptr;
 	if (trace) {
 		const uint8_t *cpb = crb + NXGPU_CPB;
@@ -176,201 +455,6 @@ int run_job_impl(nxgpu_ctx *c, uint8_t *crb)
 			be32(crb + NXGPU_CRB_CSB), be32(crb + NXGPU_CRB_CSB + 4), be32(cpb + 392), be32(cpb + 396));
 	}
 	return rc;
-}
-
-static int run_job_inner(nxgpu_ctx *c, uint8_t *crb)
-{
-	uint8_t *cpb = crb + NXGPU_CPB;
-	const uint32_t fc = be32(crb + NXGPU_CRB_FC) & 0xff;
-	std::vector<Seg> src, dst;
-	uint64_t src_total = 0, dst_total = 0;
-	if (!dde_segments(crb + NXGPU_CRB_SRC_DDE, src, src_total) || !dde_segments(crb + NXGPU_CRB_DST_DDE, dst, dst_total)) {
-		complete(crb, 9 /* ERR_NX_BAD_DDE */, CE_TERMINATE, 0);
-		return 0;
-	}
-	if (src_total > 0xffffff00ull || dst_total > 0xffffff00ull) {
-		complete(crb, 3, CE_TERMINATE, 0);
-		return 0;
-	}
-	if (cudaSetDevice(c->dev) != cudaSuccess)
-		return -EAGAIN;
-	const bool is_compress = (fc & 0x10) == 0;
-	const bool is_wrap = fc == 0x1e;
-	const uint32_t w8 = be32(cpb + 8), w12 = be32(cpb + 12);
-
-	// ---- source into pinned staging (history first, exactly as the DDE list has it) ----
-	if (c->h_stage.reserve(src_total + 64)) return -EAGAIN;
-	uint8_t *hs = static_cast<uint8_t *>(c->h_stage.p);
-	gather(src, hs);
-
-	if (is_wrap) {
-		// GZIP_FC_WRAP (inc_nx/nxu.h:816; caller lib/nx_zlib.c:1398): copy + fresh crc32/adler32
-		if (dst_total < src_total) { complete(crb, 13, 0, 0); return 0; }
-		if (c->d_in.reserve(src_total + 16)) return -EAGAIN;
-		if (cudaMemcpyAsync(c->d_in.p, hs, src_total, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return -EAGAIN;
-		nxgpu_cksum_item it = { c->d_in.p, src_total, 0, 1 };
-		if (checksum_device(c, &it, 1, 3)) return -EAGAIN;
-		if (c->h_outs.reserve(src_total + 64)) return -EAGAIN;
-		uint8_t *ho = static_cast<uint8_t *>(c->h_outs.p);
-		if (cudaMemcpyAsync(ho, c->d_cks.p, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -EAGAIN;
-		if (cudaMemcpyAsync(ho + 16, c->d_in.p, src_total, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -EAGAIN;
-		if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -EAGAIN;
-		scatter(dst, ho + 16, src_total);
-		const uint32_t *ck = reinterpret_cast<const uint32_t *>(ho);
-		put_be32(cpb + NXGPU_CPB_OUT_ADLER - NXGPU_CPB, ck[1]);
-		put_le32(cpb + NXGPU_CPB_OUT_CRC - NXGPU_CPB, ck[0]);
-		put_be32(cpb + NXGPU_CPB_OUT_SPBC_COMP - NXGPU_CPB, (uint32_t)src_total);
-		complete(crb, 0, 0, (uint32_t)src_total);
-		return 0;
-	}
-
-	// running checksums: in_adler is a plain big-endian field, in_crc holds the CRC with its
-	// bytes the other way round (lib/nx_deflate.c:1572-1577 and lib/nx_inflate.c:809-817 rely on it)
-	const uint32_t adler_seed = be32(cpb + NXGPU_CPB_IN_ADLER - NXGPU_CPB);
-	const uint32_t crc_seed = le32(cpb + NXGPU_CPB_IN_CRC - NXGPU_CPB);
-
-	if (is_compress) {
-		const bool resume = (fc & 0x08) != 0, use_dht = (fc & 0x02) != 0, count = (fc & 0x04) != 0;
-		const uint32_t hist = resume ? ((w8 >> 20) & 0xfff) * 16 : 0;
-		if (hist > src_total) { complete(crb, 3, CE_TERMINATE, 0); return 0; }   // history length error
-		const uint32_t n_new = (uint32_t)(src_total - hist);
-		if (c->d_in.reserve(src_total + 32)) return -EAGAIN;
-		if (src_total && cudaMemcpyAsync(c->d_in.p, hs, src_total, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return -EAGAIN;
-		DeflateJob job;
-		memset(&job, 0, sizeof(job));
-		job.src = static_cast<const uint8_t *>(c->d_in.p) + hist;
-		job.src_len = n_new;
-		job.hist_len = hist > 32768 ? 32768 : hist;
-		job.flags = NXGPU_F_NO_JOINER | (use_dht ? 0 : NXGPU_F_FIXED);
-		if (use_dht) {
-			const uint32_t dhtlen = w12 & 0xfff;
-			uint8_t blob[320 + 288];
-			memset(blob, 0, sizeof(blob));
-			if (dhtlen < 42 || dhtlen > 288 * 8 || !dht_to_lengths(cpb + NXGPU_CPB_IN_DHT - NXGPU_CPB, dhtlen, blob)) {
-				complete(crb, 68 /* invalid DHT */, CE_TERMINATE, 0);
-				return 0;
-			}
-			memcpy(blob + 320, cpb + NXGPU_CPB_IN_DHT - NXGPU_CPB, (dhtlen + 7) / 8);
-			if (c->d_dht.reserve(1024)) return -EAGAIN;
-			if (cudaMemcpyAsync(c->d_dht.p, blob, sizeof(blob), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return -EAGAIN;
-			job.dht = static_cast<const uint8_t *>(c->d_dht.p);
-			job.dht_bits = dhtlen;
-		}
-		if (count) {
-			if (c->d_lz.reserve(316 * 4)) return -EAGAIN;
-			job.lzcount = static_cast<uint32_t *>(c->d_lz.p);
-		}
-		if (deflate_device(c, &job, 1, job_level(), false)) return -EAGAIN;
-		nxgpu_cksum_item it = { job.src, n_new, crc_seed, adler_seed };
-		if (checksum_device(c, &it, 1, 3)) return -EAGAIN;
-		if (c->h_outs.reserve(sizeof(DeflateOut) + 64 + 316 * 4 + 2 * (size_t)n_new + 2048)) return -EAGAIN;
-		uint8_t *ho = static_cast<uint8_t *>(c->h_outs.p);
-		DeflateOut *o = reinterpret_cast<DeflateOut *>(ho);
-		uint32_t *ck = reinterpret_cast<uint32_t *>(ho + sizeof(DeflateOut));
-		uint32_t *lz = reinterpret_cast<uint32_t *>(ho + sizeof(DeflateOut) + 64);
-		uint8_t *data = ho + sizeof(DeflateOut) + 64 + 316 * 4;
-		if (cudaMemcpyAsync(o, c->d_outs.p, sizeof(DeflateOut), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -EAGAIN;
-		if (cudaMemcpyAsync(ck, c->d_cks.p, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -EAGAIN;
-		if (count && cudaMemcpyAsync(lz, c->d_lz.p, 316 * 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -EAGAIN;
-		if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -EAGAIN;
-		if (o->rc == 66) { complete(crb, 66, CE_TERMINATE, 0); return 0; }            // a needed symbol has no code
-		if (o->rc != 0) { complete(crb, 13, 0, 0); return 0; }
-		if (o->out_len > dst_total) { complete(crb, 13, 0, 0); return 0; }           // ERR_NX_TARGET_SPACE: caller halves the input
-		if (o->out_len && cudaMemcpyAsync(data, job.out, o->out_len, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -EAGAIN;
-		if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -EAGAIN;
-		scatter(dst, data, o->out_len);
-		put_be32(cpb + NXGPU_CPB_OUT_ADLER - NXGPU_CPB, ck[1]);
-		put_le32(cpb + NXGPU_CPB_OUT_CRC - NXGPU_CPB, ck[0]);
-		put_be32(cpb + NXGPU_CPB_OUT_TEBC - NXGPU_CPB, (o->tebc & 7) << 16);
-		if (count) {
-			// 286 + 30 symbol counts, big-endian like every other field (lib/nx_dht.c:187-199 detects the
-			// byte order by looking at the end-of-block count, which is always 1)
-			uint8_t *p = cpb + NXGPU_CPB_OUT_LZCOUNT - NXGPU_CPB;
-			for (int i = 0; i < 316; i++)
-				put_be32(p + 4 * i, lz[i] > 0xffffff ? 0xffffff : lz[i]);
-			put_be32(cpb + NXGPU_CPB_OUT_SPBC_COMP_WITH_COUNT - NXGPU_CPB, (uint32_t)src_total);
-		} else {
-			put_be32(cpb + NXGPU_CPB_OUT_SPBC_COMP - NXGPU_CPB, (uint32_t)src_total);
-		}
-		// manual Table 6-8: the target came out larger than the source
-		complete(crb, o->out_len > src_total ? 64 : 0, 0, o->out_len);
-		return 0;
-	}
-
-	// ---- decompress (inc_nx/nxu.h:812-815): raw deflate from a bit offset, with a preloaded window ----
-	const bool resume = (fc & 0x04) != 0;
-	const uint32_t hist = resume ? ((w8 >> 20) & 0xfff) * 16 : 0;
-	if (hist >= src_total && !(hist == 0 && src_total == 0)) {
-		if (hist > src_total) { complete(crb, 3, CE_TERMINATE, 0); return 0; }
-	}
-	const uint32_t comp_len = (uint32_t)(src_total - hist);
-	const uint32_t in_subc = resume ? (w8 & 7) : 0;
-	const uint32_t sfbt = resume ? (w12 >> 16) & 0xf : 0;
-	const size_t out_off = align16(hist);
-	if (c->d_in.reserve(comp_len + 32)) return -EAGAIN;
-	if (c->d_out.reserve(out_off + dst_total + 32)) return -EAGAIN;
-	if (c->d_dht.reserve(1024)) return -EAGAIN;
-	if (c->d_jobs.reserve(sizeof(InflateJob))) return -EAGAIN;
-	if (c->d_outs.reserve(sizeof(InflateOut))) return -EAGAIN;
-	if (c->d_misc.reserve(64)) return -EAGAIN;
-	uint8_t *d_out = static_cast<uint8_t *>(c->d_out.p);
-	if (hist && cudaMemcpyAsync(d_out + out_off - hist, hs, hist, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return -EAGAIN;
-	if (comp_len && cudaMemcpyAsync(c->d_in.p, hs + hist, comp_len, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return -EAGAIN;
-	InflateJob job;
-	memset(&job, 0, sizeof(job));
-	job.src = static_cast<const uint8_t *>(c->d_in.p);
-	job.src_len = comp_len;
-	job.wrap = kWrapJob;
-	job.dst = d_out + out_off;
-	job.dst_cap = (uint32_t)dst_total;
-	job.hist_len = hist;
-	job.start_bit = (8 - in_subc) & 7;
-	job.sfbt = sfbt;
-	job.rembytecnt = w12 & 0xffff;
-	job.out_dht = static_cast<uint8_t *>(c->d_dht.p) + 512;
-	if ((sfbt & 0xe) == 0xc) {
-		job.dht_bits = w12 & 0xfff;
-		if (cudaMemcpyAsync(c->d_dht.p, cpb + NXGPU_CPB_IN_DHT - NXGPU_CPB, 288, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return -EAGAIN;
-		job.dht = static_cast<const uint8_t *>(c->d_dht.p);
-	}
-	if (c->h_jobs.reserve(sizeof(InflateJob))) return -EAGAIN;
-	memcpy(c->h_jobs.p, &job, sizeof(job));
-	if (cudaMemcpyAsync(c->d_jobs.p, c->h_jobs.p, sizeof(job), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return -EAGAIN;
-	timer_begin(c, 1);
-	if (launch_inflate(static_cast<const InflateJob *>(c->d_jobs.p), static_cast<InflateOut *>(c->d_outs.p), 1,
-			   static_cast<uint32_t *>(c->d_misc.p), c->stream) != cudaSuccess) return -EAGAIN;
-	timer_end(c, 1);
-	if (c->h_outs.reserve(sizeof(InflateOut) + 64 + 288 + dst_total + 64)) return -EAGAIN;
-	uint8_t *ho = static_cast<uint8_t *>(c->h_outs.p);
-	InflateOut *o = reinterpret_cast<InflateOut *>(ho);
-	uint32_t *ck = reinterpret_cast<uint32_t *>(ho + sizeof(InflateOut));
-	uint8_t *odht = ho + sizeof(InflateOut) + 64;
-	uint8_t *data = odht + 288;
-	if (cudaMemcpyAsync(o, c->d_outs.p, sizeof(InflateOut), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -EAGAIN;
-	if (cudaMemcpyAsync(odht, job.out_dht, 288, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -EAGAIN;
-	if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -EAGAIN;
-	if (o->rc != 0) {
-		// 13: target full, the caller retries with less input; 66/67/68: bad code / distance / table
-		complete(crb, (uint32_t)o->rc, o->rc == 13 ? 0 : CE_TERMINATE, 0);
-		return 0;
-	}
-	nxgpu_cksum_item it = { job.dst, o->out_len, crc_seed, adler_seed };
-	if (checksum_device(c, &it, 1, 3)) return -EAGAIN;
-	if (cudaMemcpyAsync(ck, c->d_cks.p, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -EAGAIN;
-	if (o->out_len && cudaMemcpyAsync(data, job.dst, o->out_len, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -EAGAIN;
-	if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -EAGAIN;
-	scatter(dst, data, o->out_len);
-	put_be32(cpb + NXGPU_CPB_OUT_ADLER - NXGPU_CPB, ck[1]);
-	put_le32(cpb + NXGPU_CPB_OUT_CRC - NXGPU_CPB, ck[0]);
-	put_be32(cpb + NXGPU_CPB_OUT_TEBC - NXGPU_CPB, o->subc & 0xffff);                   // out_subc: low half of this word
-	const bool in_dyn = (o->sfbt & 0xe) == 0xc;
-	put_be32(cpb + NXGPU_CPB_OUT_SFBT - NXGPU_CPB, (o->sfbt & 0xf) << 16 | (in_dyn ? (o->dhtlen & 0xfff) : (o->rembytecnt & 0xffff)));
-	if (in_dyn)
-		memcpy(cpb + NXGPU_CPB_OUT_DHT - NXGPU_CPB, odht, 288);
-	put_be32(cpb + NXGPU_CPB_OUT_SPBC_DECOMP - NXGPU_CPB, (uint32_t)src_total);
-	// CC=3 with CE "partial completion" is the normal way a decompress job ends (lib/nx_inflate.c:1372-1390)
-	complete(crb, 3, CE_PARTIAL | CE_TPBC_VALID, o->out_len);
-	return 0;
 }
 
 } // namespace nxgpu

@@ -10,7 +10,12 @@ Run as a subprocess (the selector is read when the library is loaded).  Prints o
 Mirrors the round trips of the reference's test/test_deflate.c and test/test_inflate.c: output of
 the nx deflate must inflate with system zlib, and streams made by system zlib must inflate through
 nx, in one shot and in small pieces.
-usage: nx_dropin_driver.py <libnxz .so> [size_log2]"""
+usage: nx_dropin_driver.py <libnxz .so> [size_log2]
+       nx_dropin_driver.py <libnxz .so> stress <threads> <iterations>
+The stress mode follows the reference's test/test_multithread_stress.c:26-120: every thread runs
+compress()/uncompress() over the same ten buffers (4 KiB .. 1 MiB of the 33-symbol alphabet of
+test/test_utils.c:22-28, srand(1)) and checks the round trip; it also reports how many descriptors
+the engine coalesced per GPU batch (nxgpu_job_stats) when the engine exports that."""
 import ctypes as C
 import faulthandler
 import gzip
@@ -26,7 +31,8 @@ os.environ.setdefault("NX_GZIP_LOGFILE", "/tmp/nx_dropin.log")
 if os.environ.get("NX_DRIVER_WATCHDOG"):
     faulthandler.dump_traceback_later(int(os.environ["NX_DRIVER_WATCHDOG"]), exit=True)
 lib = C.CDLL(sys.argv[1], mode=C.RTLD_GLOBAL)
-log2 = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+STRESS = len(sys.argv) > 2 and sys.argv[2] == "stress"
+log2 = int(sys.argv[2]) if len(sys.argv) > 2 and not STRESS else 20
 
 
 class ZStream(C.Structure):
@@ -133,6 +139,52 @@ def nx_inflate_stream(blob, wbits, in_piece, out_piece, expect_len):
     lib.inflateEnd(C.byref(s))
     return bytes(out)
 
+
+def stress(n_threads, iterations):
+    import threading
+    import time
+    dict33 = b"abcdefghijklmnopqrstuvwxyz,.!?.{}"
+    rnd = random.Random(1)
+    bufs = [bytes(rnd.choice(dict33) for _ in range(n)) for n in (4096, 4096, 65536, 65536, 131072, 131072, 262144, 262144, 1048576, 1048576)]
+    refs = [zlib.compress(b, 6) for b in bufs]
+    nx_compress2(bufs[0], 6)                     # opens the device outside the timed region
+    errors, done_bytes = [], [0] * n_threads
+    start = threading.Barrier(n_threads + 1)
+
+    def worker(t):
+        try:
+            start.wait()
+            for it in range(iterations):
+                for k, b in enumerate(bufs):
+                    z = nx_compress2(b, 6)
+                    if zlib.decompress(z) != b:
+                        raise AssertionError(f"thread {t}: zlib cannot decode nx compress of buffer {k}")
+                    if nx_uncompress(z, len(b)) != b or nx_uncompress(refs[k], len(b)) != b:
+                        raise AssertionError(f"thread {t}: nx uncompress of buffer {k} differs")
+                    done_bytes[t] += 3 * len(b)
+        except Exception as e:                       # noqa: BLE001 - reported to the parent
+            errors.append(repr(e))
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for x in th:
+        x.start()
+    start.wait()
+    t0 = time.time()
+    for x in th:
+        x.join()
+    dt = time.time() - t0
+    rep = {"lib": os.path.basename(sys.argv[1]), "threads": n_threads, "iterations": iterations, "errors": errors,
+           "seconds": dt, "MBps": sum(done_bytes) / dt / 1e6, "calls_per_s": n_threads * iterations * len(bufs) * 3 / dt}
+    if hasattr(lib, "nxgpu_job_stats"):
+        b, j, m = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib.nxgpu_job_stats(0, C.byref(b), C.byref(j), C.byref(m))
+        rep.update(batches=b.value, jobs=j.value, max_batch=m.value)
+    print(json.dumps(rep))
+
+
+if STRESS:
+    stress(int(sys.argv[3]), int(sys.argv[4]))
+    sys.exit(0)
 
 alice = gzip.decompress(open(os.path.join(ROOT, "tests", "golden", "alice29.txt.gz"), "rb").read())
 rnd = random.Random(7)

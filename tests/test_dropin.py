@@ -44,6 +44,30 @@ def test_reference_host_code_over_gpu_engine():
     assert rep["cases"]["alice"]["compress2"] < 70000, rep
 
 
+def _stress(lib, threads, iterations):
+    p = subprocess.run([sys.executable, DRIVER, lib, "stress", str(threads), str(iterations)], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    return json.loads(p.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CPU), reason="oracle/_ref not built (needs /root/reference)")
+def test_multithread_stress_over_cpu_engine():
+    # reference test/test_multithread_stress.c: concurrent compress()/uncompress() of ten buffers per thread
+    rep = _stress(REF_CPU, 4, 1)
+    assert rep["errors"] == [], rep
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REF_GPU), reason="oracle/_ref/libnxz_gpu.so not built (needs /root/reference at build time)")
+def test_multithread_stress_is_coalesced_on_the_gpu():
+    # descriptors from concurrent z_streams share GPU launches, results stay per stream
+    rep = _stress(REF_GPU, 32, 2)
+    assert rep["errors"] == [], rep
+    assert rep["jobs"] >= 32 * 2 * 10 and rep["max_batch"] > 1, rep
+    one = _stress(REF_GPU, 1, 2)
+    assert one["errors"] == [] and one["max_batch"] == 1, one
+
+
 # ---------------------------------------------------------------------------------------------
 # single descriptors
 # ---------------------------------------------------------------------------------------------
