@@ -105,7 +105,8 @@ struct CksumJob {
 };
 
 // deflate tuning per zlib-style level
-struct LevelParams { int depth; int lazy; int nice; int d1; };   // d1 != 0: two-pass parse, d1 = depth of the shallow pass
+struct LevelParams { int depth; int lazy; int nice; int d1; };   // d1 != 0: two-pass parse, d1 = depth of the shallow pass;
+                                                                 // there `depth` is the base the deep pass scales with the data (deflate.cu)
 __host__ __device__ inline LevelParams level_params(int level)
 {
 	switch (level) {          // chain depth, lazy threshold (0 = greedy), nice length, shallow-pass depth (0 = single pass)
@@ -114,11 +115,11 @@ __host__ __device__ inline LevelParams level_params(int level)
 	case 3: return { 4, 0, 128, 0 };
 	case 4: return { 4, 16, 128, 0 };
 	case 5: return { 12, 32, 258, 2 };
-	case 6: return { 24, 32, 258, 2 };
+	case 6: return { 32, 32, 258, 2 };
 	case 7: return { 32, 64, 258, 3 };
 	case 8: return { 48, 258, 258, 3 };
 	case 9: return { 96, 258, 258, 4 };
-	default: return { 24, 32, 258, 2 };
+	default: return { 32, 32, 258, 2 };
 	}
 }
 

@@ -510,7 +510,16 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 	uint32_t headA = 0;                                        // pass-1 parse: next token start (relative to sub_lo)
 	uint32_t carry = 0;                                        // mark for lane 0 of the next window
 
-	auto deep = [&](uint32_t count) {
+	// Chain depth of the deep pass follows the data: the cost of a sub-block is (queued positions) x
+	// depth, and long-match data (few token starts per byte, many equally good candidates) is where
+	// deeper chains pay, so the depth grows with the bytes scanned per queued position:
+	// depth = base * bytes_per_queued / 12, within [base / 3, 2 * base].
+	const int base_depth = depth;
+	uint32_t fired_at = 0;                                     // bytes of the sub-block scanned when the queue last fired
+	auto deep = [&](uint32_t count, uint32_t scanned) {
+		const uint32_t bpq16 = ((scanned - fired_at) << 4) / max(count, 1u);      // bytes per queued position, x16
+		fired_at = scanned;
+		depth = max(base_depth / 3, min(2 * base_depth, (int)((uint32_t)base_depth * bpq16 / (12 * 16))));
 		const bool act = lane < count;
 		const uint32_t pos = act ? qpos : sub_lo;
 		const uint32_t maxl = act ? min((uint32_t)kMaxMatch, PE - pos) : 0;
@@ -557,13 +566,13 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 			else
 				M &= ~((1u << __fns(M, 0, (int)(tk_n + 1))) - 1);
 			if (qn == 32) {
-				deep(32);
+				deep(32, min(w0 + 32, npos));
 				qn = 0;
 			}
 		}
 	}
 	if (qn)
-		deep(qn);
+		deep(qn, npos);
 	__threadfence_block();
 	__syncwarp();
 
