@@ -301,3 +301,66 @@ def test_compress_jobs(engines, oracle, alice):
         assert j.crc() == zlib.crc32(alice[:60000]) and j.adler() == zlib.adler32(alice[:60000])
         j = run(Job(0x1e, [alice[:5000]], 100))
         assert j.cc() == 13
+
+
+@pytest.mark.gpu
+def test_mixed_descriptors_from_many_threads_coalesce_and_stay_exact(engines, pg, alice):
+    """descriptors submitted concurrently (compress FHT/COUNT, decompress fresh and
+    resumed with history, wrap) are run as shared GPU batches; every one must come back exactly as if it
+    had been alone: decompress/wrap bit-exact with the CPU engine, compress decoding to its source."""
+    import threading
+    gpu, cpu = engines
+    lib = pg.load_library()
+    rnd = random.Random(11)
+
+    def make(i):
+        k = i % 4
+        data = (alice[(i * 997) % 50000:][: 3000 + 2311 * (i % 13)]) + rnd.randbytes(50 * (i % 3))
+        if k == 0:                                   # fresh decompress of a whole raw stream
+            return "dec", data, lambda: Job(0x10, [zlib.compress(data, 6)[2:-4]], len(data) + 100, split_dst=(i % 8 == 0))
+        if k == 1:                                   # resumed decompress: second half, first half as history
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            a = co.compress(data[: len(data) // 2]) + co.flush(zlib.Z_FULL_FLUSH)
+            b = co.compress(data[len(data) // 2:]) + co.flush()
+            hist = data[: len(data) // 2][-32768:]
+            hist = bytes((-len(hist)) % 16) + hist
+            return "dec2", data[len(data) // 2:], lambda: Job(0x14, [hist, b], len(data) + 100, histlen_qw=len(hist) // 16)
+        if k == 2:                                   # wrap: copy + checksums
+            return "wrap", data, lambda: Job(0x1e, [data], len(data))
+        return "comp", data, lambda: Job(0x04 if i % 8 == 3 else 0x00, [data], 2 * len(data) + 1000)
+
+    specs = [make(i) for i in range(96)]
+    jobs = [mk() for _, _, mk in specs]
+    refs = [cpu(mk()) for _, _, mk in specs]
+    b0, j0, m0 = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    lib.nxgpu_job_stats(0, C.byref(b0), C.byref(j0), C.byref(m0))
+    start = threading.Barrier(len(jobs))
+    errs = []
+
+    def worker(j):
+        try:
+            start.wait()
+            gpu(j)
+        except Exception as e:                       # noqa: BLE001
+            errs.append(repr(e))
+    th = [threading.Thread(target=worker, args=(j,)) for j in jobs]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    b1, j1, m1 = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    lib.nxgpu_job_stats(0, C.byref(b1), C.byref(j1), C.byref(m1))
+    assert j1.value - j0.value == len(jobs)
+    assert b1.value - b0.value < len(jobs), "no descriptor shared a batch"
+    for (kind, data, _), g, c in zip(specs, jobs, refs):
+        assert g.cc() == c.cc(), (kind, g.cc(), c.cc())
+        if kind in ("dec", "dec2"):
+            assert g.out() == c.out() == data, kind
+            assert (g.tpbc(), g.w392() & 0xffff, g.w396(), g.spbc_decomp()) == (c.tpbc(), c.w392() & 0xffff, c.w396(), c.spbc_decomp()), kind
+            assert (g.crc(), g.adler()) == (c.crc(), c.adler()), kind
+        elif kind == "wrap":
+            assert g.out() == data and (g.crc(), g.adler()) == (zlib.crc32(data), zlib.adler32(data))
+        else:
+            assert zlib.decompress(_decode_one_block(0, g), -15) == data
+            assert (g.crc(), g.adler()) == (zlib.crc32(data), zlib.adler32(data))
