@@ -209,6 +209,18 @@ int nxgpu_deflate_stream(nxgpu_ctx *ctx, const void *src, uint64_t src_len, void
 			 int level, int wrap, uint32_t chunk, uint64_t *chunk_offsets,
 			 nxgpu_stream_result *res, int mem);
 uint64_t nxgpu_deflate_stream_bound(uint64_t src_len, uint32_t chunk);
+/* OR into `wrap` of nxgpu_deflate_stream: chunks do not look back into each other (true
+ * Z_FULL_FLUSH semantics, the resetting flush of lib/nx_deflate.c:1690-1712) — costs a little
+ * ratio, makes the member seekable: any zlib still inflates it, and nxgpu_inflate_stream inflates
+ * all chunks of the index in parallel. */
+#define NXGPU_STREAM_INDEPENDENT 0x100
+/* Inflates ONE member as the n_chunks segments of `chunk_offsets` (n_chunks + 1 entries, as returned
+ * by nxgpu_deflate_stream with the same `wrap` and `chunk`) in a single batch; verifies the
+ * zlib/gzip trailer against the combined per-segment checksums (lib/nx_crc.c:374,
+ * lib/nx_adler32.c:154).  NXGPU_E_DATA if the segments turn out to depend on each other. */
+int nxgpu_inflate_stream(nxgpu_ctx *ctx, const void *src, uint64_t src_len, void *dst, uint64_t dst_cap,
+			 int wrap, const uint64_t *chunk_offsets, uint32_t n_chunks, uint32_t chunk,
+			 nxgpu_stream_result *res, int mem);
 
 /* --- inflate: the NX decompress function code (inc_nx/nxu.h:812) as a batch of
  * independent members / sync-point segments. */
@@ -226,7 +238,8 @@ typedef struct {
 	uint32_t in_used;      /* source bytes consumed incl. header and trailer   */
 	uint32_t crc32;        /* of the output                                    */
 	uint32_t adler32;
-	uint32_t flags;        /* bit0: final block seen; bit1: trailer verified   */
+	uint32_t flags;        /* bit0: final block seen; bit1: trailer verified;
+	                          bit2: source ended on a block boundary, no final block (rc = NXGPU_E_DATA) */
 } nxgpu_inflate_result;
 int nxgpu_inflate_batch(nxgpu_ctx *ctx, const nxgpu_inflate_item *items, size_t n,
 			nxgpu_inflate_result *results, int mem);

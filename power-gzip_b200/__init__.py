@@ -21,6 +21,7 @@ LIB_PATH = os.path.join(_HERE, "libnxgpu.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
 WRAP_RAW, WRAP_ZLIB, WRAP_GZIP, WRAP_AUTO, WRAP_RAW_CONT = 0, 1, 2, 3, 5
+STREAM_INDEPENDENT = 0x100
 F_FINAL, F_FIXED, F_NO_JOINER = 1, 2, 4
 E_NODEV, E_ARG, E_DATA, E_MEM, E_BUF = -100, -2, -3, -4, -5
 
@@ -72,7 +73,7 @@ EXPORTS = [
     "nxgpu_timer_start", "nxgpu_timer_stop", "nxgpu_launch_count", "nxgpu_kernel_time", "nxgpu_kernel_time_reset",
     "nxgpu_checksum_batch", "nxgpu_crc32", "nxgpu_adler32", "nxgpu_crc32_combine", "nxgpu_adler32_combine",
     "nxgpu_deflate_batch", "nxgpu_deflate_bound", "nxgpu_deflate_stream", "nxgpu_deflate_stream_bound",
-    "nxgpu_inflate_batch", "nxgpu_makedata", "nxgpu_job_stats",
+    "nxgpu_inflate_batch", "nxgpu_inflate_stream", "nxgpu_makedata", "nxgpu_job_stats",
 ]
 
 _lib = None
@@ -115,6 +116,7 @@ def load_library() -> C.CDLL:
         "nxgpu_deflate_stream": (i32, [vp, vp, u64, vp, u64, i32, i32, u32, P(u64), P(StreamResult), i32]),
         "nxgpu_deflate_stream_bound": (u64, [u64, u32]),
         "nxgpu_inflate_batch": (i32, [vp, P(InflateItem), sz, P(InflateResult), i32]),
+        "nxgpu_inflate_stream": (i32, [vp, vp, u64, vp, u64, i32, P(u64), u32, u32, P(StreamResult), i32]),
         "nxgpu_makedata": (u64, [i32, i32, vp, u64, vp, u64]),
         "nxgpu_job_stats": (None, [i32, P(u64), P(u64), P(u64)]),
         "nx_function_begin": (i32, [i32, i32, vp]),
@@ -297,6 +299,23 @@ class Engine:
         res = (InflateResult * n)()
         self._check(self.lib.nxgpu_inflate_batch(self.ctx, arr, n, res, mem), "nxgpu_inflate_batch")
         return list(res)
+
+    def inflate_stream(self, blob, out_len: int, index: Sequence[int], chunk: int = 0, wrap: int = WRAP_GZIP) -> bytes:
+        """One member inflated as the segments of its sync-point index, all in one batch (host bytes)."""
+        a, n, keep = _addr(blob)
+        out = (C.c_char * max(out_len, 1))()
+        idx = (C.c_uint64 * len(index))(*index)
+        res = StreamResult()
+        self._check(self.lib.nxgpu_inflate_stream(self.ctx, a, n, C.addressof(out), out_len, wrap, idx, len(index) - 1, chunk,
+                                                  C.byref(res), MEM_HOST), "nxgpu_inflate_stream")
+        return bytes(memoryview(out)[: res.out_len])
+
+    def inflate_stream_device(self, src_ptr: int, n: int, dst_ptr: int, cap: int, index, n_chunks: int, chunk: int = 0,
+                              wrap: int = WRAP_GZIP) -> StreamResult:
+        res = StreamResult()
+        self._check(self.lib.nxgpu_inflate_stream(self.ctx, src_ptr, n, dst_ptr, cap, wrap, index, n_chunks, chunk,
+                                                  C.byref(res), MEM_DEVICE), "nxgpu_inflate_stream")
+        return res
 
     def uncompress(self, blob, out_len: int, wrap: int = WRAP_AUTO) -> bytes:
         """libnxz.h ``uncompress`` (lib/nx_uncompr.c:91) for one member."""

@@ -139,7 +139,7 @@ struct BitReader {
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr)
 {
 	uint32_t v;
-	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");   // ordered against the C++ stores that fill the tables
 	return v;
 }
 __device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v)
@@ -396,6 +396,8 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 						rc = 0;
 					} else {
 						rc = NXGPU_E_DATA;
+						if (blk == total_bits)
+							flags |= 4;          // the source ended exactly on a block boundary, no final block seen
 					}
 				} else if (rc && job) {
 					rc = 68;

@@ -511,6 +511,10 @@ int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *
 			 int level, int wrap, uint32_t chunk, uint64_t *chunk_offsets, nxgpu_stream_result *res, int mem)
 {
 	if (!c || (!src && src_len) || !dst || !res) return NXGPU_E_ARG;
+	// true Z_FULL_FLUSH semantics: no chunk looks back into the previous one, so the chunks of the
+	// index can be inflated in parallel (nxgpu_inflate_stream)
+	const bool independent = (wrap & NXGPU_STREAM_INDEPENDENT) != 0;
+	wrap &= ~NXGPU_STREAM_INDEPENDENT;
 	const bool cont = wrap == NXGPU_WRAP_RAW_CONT;
 	if (cont) wrap = NXGPU_WRAP_RAW;
 	if (wrap != NXGPU_WRAP_RAW && wrap != NXGPU_WRAP_ZLIB && wrap != NXGPU_WRAP_GZIP) return NXGPU_E_ARG;
@@ -555,7 +559,7 @@ int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *
 		const uint64_t o = (uint64_t)i * chunk;
 		jh[i].src = dsrc + o;
 		jh[i].src_len = (uint32_t)(src_len - o < chunk ? src_len - o : chunk);
-		jh[i].hist_len = (uint32_t)(o < 32768 ? o : 32768);
+		jh[i].hist_len = independent ? 0 : (uint32_t)(o < 32768 ? o : 32768);
 		jh[i].flags = (i + 1 == n && !cont) ? NXGPU_F_FINAL : 0;
 	}
 	rc = deflate_device(c, jh, n, level, false);
@@ -713,7 +717,7 @@ int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n,
 		nxgpu_inflate_result &r = results[i];
 		r.rc = oh[i].rc; r.out_len = oh[i].out_len; r.in_used = oh[i].in_used;
 		r.crc32 = ck[i]; r.adler32 = ck[n + i];
-		r.flags = oh[i].flags & 1;
+		r.flags = oh[i].flags & 5;
 		const uint32_t wrap = oh[i].flags >> 8;
 		if (r.rc == 0 && wrap == NXGPU_WRAP_GZIP) {
 			// the check lib/nx_inflate.c:763-848 does on the host
@@ -728,6 +732,93 @@ int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n,
 				NXGPU_CUDA_OK(cudaMemcpyAsync(items[i].dst, jh[i].dst, results[i].out_len, cudaMemcpyDeviceToHost, c->stream));
 		NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
 	}
+	return 0;
+}
+
+/* One big member, inflated as its sync-point segments in ONE batch (the index
+ * nxgpu_deflate_stream returns, consumed by inflate).  Legal when the segments do not look back
+ * into each other (NXGPU_STREAM_INDEPENDENT); a primed stream is detected (a distance reaches in
+ * front of a segment) and refused with NXGPU_E_DATA — inflate it as one member instead. */
+int nxgpu_inflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *dst, uint64_t dst_cap, int wrap,
+			 const uint64_t *chunk_offsets, uint32_t n_chunks, uint32_t chunk, nxgpu_stream_result *res, int mem)
+{
+	if (!c || !src || (!dst && dst_cap) || !res || !chunk_offsets || n_chunks == 0) return NXGPU_E_ARG;
+	if (wrap != NXGPU_WRAP_RAW && wrap != NXGPU_WRAP_ZLIB && wrap != NXGPU_WRAP_GZIP) return NXGPU_E_ARG;
+	if (chunk == 0) chunk = 262144;
+	const uint64_t trailer = wrap == NXGPU_WRAP_GZIP ? 8 : wrap == NXGPU_WRAP_ZLIB ? 4 : 0;
+	for (uint32_t i = 0; i < n_chunks; i++)
+		if (chunk_offsets[i] > chunk_offsets[i + 1] || chunk_offsets[i + 1] - chunk_offsets[i] > 0xffffff00ull) return NXGPU_E_ARG;
+	if (chunk_offsets[n_chunks] + trailer > src_len) { set_error("index runs past the end of the stream"); return NXGPU_E_DATA; }
+	if ((uint64_t)(n_chunks - 1) * chunk > dst_cap) return NXGPU_E_BUF;
+	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
+	int rc;
+	const uint8_t *dsrc = static_cast<const uint8_t *>(src);
+	uint8_t *ddst = static_cast<uint8_t *>(dst);
+	if (mem == NXGPU_MEM_HOST) {
+		if ((rc = c->d_in.reserve(src_len + 16))) return rc;
+		if ((rc = c->d_out.reserve(dst_cap + 16))) return rc;
+		NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_in.p, src, src_len, cudaMemcpyHostToDevice, c->stream));
+		dsrc = static_cast<const uint8_t *>(c->d_in.p);
+		ddst = static_cast<uint8_t *>(c->d_out.p);
+	}
+	std::vector<nxgpu_inflate_item> items(n_chunks);
+	std::vector<nxgpu_inflate_result> rs(n_chunks);
+	for (uint32_t i = 0; i < n_chunks; i++) {
+		const uint64_t o = (uint64_t)i * chunk;
+		items[i].src = dsrc + chunk_offsets[i];
+		items[i].src_len = (uint32_t)(chunk_offsets[i + 1] - chunk_offsets[i]);
+		items[i].dst = ddst + o;
+		items[i].dst_cap = (uint32_t)(dst_cap - o < chunk ? dst_cap - o : chunk);
+		items[i].wrap = NXGPU_WRAP_RAW;
+		items[i].hist_len = 0;
+	}
+	if ((rc = nxgpu_inflate_batch(c, items.data(), n_chunks, rs.data(), NXGPU_MEM_DEVICE))) return rc;
+	// every segment but the last fills its chunk exactly and ends on the joiner; the last one carries BFINAL
+	uint64_t total = 0;
+	uint32_t crc = 0, adler = 1;
+	for (uint32_t i = 0; i < n_chunks; i++) {
+		const bool last = i + 1 == n_chunks;
+		// an inner segment ends on the joiner without a final block: reported as E_DATA + "clean end" (bit 2)
+		const bool ok = last ? (rs[i].rc == 0 && (rs[i].flags & 1))
+				     : (rs[i].rc == NXGPU_E_DATA && (rs[i].flags & 5) == 4 && rs[i].out_len == chunk);
+		if (!ok) {
+			set_error("segment %u: rc %d, %u bytes, final %u (a stream whose chunks were primed cannot be split)", i, rs[i].rc, rs[i].out_len, rs[i].flags & 1);
+			return rs[i].rc == NXGPU_E_BUF ? NXGPU_E_BUF : NXGPU_E_DATA;
+		}
+		total += rs[i].out_len;
+	}
+	// checksums of the whole output in one pass (the segments are the ranges of one job, combined on the device)
+	{
+		nxgpu_cksum_item whole = { ddst, total, 0, 1 };
+		uint32_t ck[2];
+		if ((rc = checksum_device(c, &whole, 1, 3))) return rc;
+		NXGPU_CUDA_OK(cudaMemcpyAsync(ck, c->d_cks.p, 8, cudaMemcpyDeviceToHost, c->stream));
+		NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+		crc = ck[0]; adler = ck[1];
+	}
+	// trailer (the check lib/nx_inflate.c:763-848 does on the host)
+	if (trailer) {
+		uint8_t t[8];
+		if (mem == NXGPU_MEM_HOST) memcpy(t, static_cast<const uint8_t *>(src) + chunk_offsets[n_chunks], trailer);
+		else NXGPU_CUDA_OK(cudaMemcpy(t, dsrc + chunk_offsets[n_chunks], trailer, cudaMemcpyDeviceToHost));
+		if (wrap == NXGPU_WRAP_GZIP) {
+			const uint32_t tc = t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;
+			const uint32_t ts = t[4] | (uint32_t)t[5] << 8 | (uint32_t)t[6] << 16 | (uint32_t)t[7] << 24;
+			if (tc != crc || ts != (uint32_t)total) { set_error("gzip trailer mismatch"); return NXGPU_E_DATA; }
+		} else {
+			const uint32_t ta = (uint32_t)t[0] << 24 | (uint32_t)t[1] << 16 | (uint32_t)t[2] << 8 | t[3];
+			if (ta != adler) { set_error("zlib trailer mismatch"); return NXGPU_E_DATA; }
+		}
+	}
+	if (mem == NXGPU_MEM_HOST && total) {
+		NXGPU_CUDA_OK(cudaMemcpyAsync(dst, ddst, total, cudaMemcpyDeviceToHost, c->stream));
+		NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	}
+	res->out_len = total;
+	res->crc32 = crc;
+	res->adler32 = adler;
+	res->n_chunks = n_chunks;
+	res->n_tokens = 0;
 	return 0;
 }
 

@@ -219,7 +219,7 @@ def test_inflate_batch_bit_exact(engine, oracle, pg, alice):
         items.append(pg.InflateItem(C.addressof(sb), len(b), C.addressof(ob), cap, pg.WRAP_AUTO, 0))
     res = engine.inflate_batch(items, mem=pg.MEM_HOST)
     for r, (sb, ob), b, d in zip(res, keep, blobs, want):
-        assert r.rc == 0, (len(d), r.rc)
+        assert r.rc == 0, (len(d), r.rc, r.out_len, r.in_used, r.flags, hex(r.crc32), hex(r.adler32), b.hex()[:80])
         assert bytes(memoryview(ob)[: r.out_len]) == d
         assert r.in_used == len(b)
         assert r.crc32 == zlib.crc32(d) and r.adler32 == zlib.adler32(d)
@@ -297,6 +297,51 @@ def test_inflate_segments_device(engine, pg, alice):
         assert r.out_len == n and (r.flags & 1) == want_final, (i, r.rc, r.out_len)
     assert ddst.download() == data
     dsrc.free(); ddst.free()
+
+
+def test_independent_stream_inflates_in_parallel(engine, pg, alice):
+    """a stream written with NXGPU_STREAM_INDEPENDENT (true Z_FULL_FLUSH semantics,
+    test/test_inflatesyncpoint.c checks the same sync markers) is one valid member for any zlib AND splits
+    at its index into segments that nxgpu_inflate_stream runs as one batch; results are bit-exact."""
+    for wrap, unwrap in ((pg.WRAP_GZIP, gzip.decompress), (pg.WRAP_ZLIB, zlib.decompress), (pg.WRAP_RAW, lambda b: zlib.decompress(b, -15))):
+        for data, chunk in ((pg.makedata(1, 21, alice) + alice[:12345], 65536), (alice, 16384), (b"", 65536), (b"x" * 70000, 65536),
+                            (pg.makedata(5, 20, alice), 262144)):
+            primed = engine.compress(data, level=6, wrap=wrap, chunk=chunk)
+            blob, index, res = engine.compress(data, level=6, wrap=wrap | pg.STREAM_INDEPENDENT, chunk=chunk, with_index=True)
+            assert unwrap(blob) == data
+            assert len(primed) <= len(blob) + 64 and len(blob) <= 1.6 * len(primed) + 64, (len(blob), len(primed))   # independence costs the window
+            # at every chunk start (makedata copies from anywhere in the last 32-64 KiB: +41 % at 64 KiB chunks, ~+10 % at 256 KiB)
+            assert engine.inflate_stream(blob, len(data), index, chunk=chunk, wrap=wrap) == data
+            if len(data) > 2 * chunk:
+                # the primed stream's segments reach into their neighbours: refused, not mis-decoded
+                pblob, pindex, _ = engine.compress(data, level=6, wrap=wrap, chunk=chunk, with_index=True)
+                with pytest.raises(pg.NxGpuError) as e:
+                    engine.inflate_stream(pblob, len(data), pindex, chunk=chunk, wrap=wrap)
+                assert e.value.rc == pg.E_DATA
+    # a damaged trailer is caught by the combined checksums
+    data = pg.makedata(4, 20, alice)
+    blob, index, _ = engine.compress(data, level=6, wrap=pg.WRAP_GZIP | pg.STREAM_INDEPENDENT, chunk=65536, with_index=True)
+    bad = bytearray(blob); bad[-6] ^= 1
+    with pytest.raises(pg.NxGpuError):
+        engine.inflate_stream(bytes(bad), len(data), index, chunk=65536, wrap=pg.WRAP_GZIP)
+
+
+def test_independent_stream_device_at_scale(engine, pg, alice):
+    # 64 MiB, device resident: deflate (independent chunks) -> parallel segment inflate -> checksum of checksums
+    data = pg.makedata(1, 26, alice)
+    n = len(data)
+    dsrc = engine.alloc(n); dsrc.upload(data)
+    cap = engine.deflate_bound(n)
+    ddst = engine.alloc(cap)
+    idx = (C.c_uint64 * 257)()
+    res = engine.deflate_stream_device(dsrc.ptr, n, ddst.ptr, cap, level=6, wrap=pg.WRAP_GZIP | pg.STREAM_INDEPENDENT, index=idx)
+    assert res.crc32 == 0xece3d95e and res.n_chunks == 256
+    dback = engine.alloc(n)
+    r = engine.inflate_stream_device(ddst.ptr, res.out_len, dback.ptr, n, idx, 256, wrap=pg.WRAP_GZIP)
+    assert r.out_len == n and r.crc32 == 0xece3d95e and r.adler32 == zlib.adler32(data)
+    assert dback.download(1 << 20, 37 << 20) == data[37 << 20: 38 << 20]
+    for b in (dsrc, ddst, dback):
+        b.free()
 
 
 # ---------------------------------------------------------------- size-independent properties at scale
