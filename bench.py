@@ -149,6 +149,13 @@ def gen_input(pg, log2):
     return hptr.value, n
 
 
+def workload_config(n, world):
+    """the `config` object both arms print (BASELINE.json configs[1])"""
+    return {"workload": "1 GiB makedata text (seed 1) per GPU, deflate level 6, dynamic Huffman, 256 KiB chunks primed with 32 KiB, one gzip member + crc32",
+            "bytes_per_gpu": n, "chunk": CHUNK, "level": 6, "l2": "inputs (1 GiB) larger than the 126 MB L2; no flush needed",
+            "parallelism": f"chunk-range x{world}" if world > 1 else "1 GPU"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -173,7 +180,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "deflate uncompressed GB/s", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "1 GiB makedata text (seed 1), deflate level 6, dynamic Huffman, 256 KiB chunks", "chunk": CHUNK, "level": 6},
+            "config": workload_config(GIB, args.gpus),
             "cpu_baseline": {"value": val, "unit": "GB/s", "cores": threads, "kind": kind,
                              "sample": f"first {sample >> 20} MiB of the workload, compress2(level 6) per 256 KiB piece, zlib {zlib.ZLIB_RUNTIME_VERSION}"},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -193,6 +200,10 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -450,9 +461,7 @@ def main():
             "metric": "deflate uncompressed GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "1 GiB makedata text (seed 1) per GPU, deflate level 6, dynamic Huffman, 256 KiB chunks primed with 32 KiB, one gzip member + crc32",
-                       "bytes_per_gpu": n, "chunk": CHUNK, "level": 6, "l2": "inputs (1 GiB) larger than the 126 MB L2; no flush needed",
-                       "parallelism": f"chunk-range x{world}" if world > 1 else "1 GPU"},
+            "config": workload_config(n, world),
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": (ncu_traffic_per_input_byte() * n) if ncu_traffic_per_input_byte() else None,
@@ -460,7 +469,8 @@ def main():
                          "note": "algorithmic bytes = U + C per launch (SURVEY.md §8d); LZ77 search is latency/issue bound, not HBM bound"},
             "cpu_baseline": cpu, "clocks": sampler.summary(), "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
