@@ -250,6 +250,19 @@ int nxgpu_inflate_batch(nxgpu_ctx *ctx, const nxgpu_inflate_item *items, size_t 
 uint64_t nxgpu_makedata(int seed, int log2size, const void *seedfile, uint64_t seedfile_len,
 			void *out, uint64_t out_cap);
 
+/* --- DHT generation: what lib/nx_dhtgen.c:945 dhtgen() computes on the host on a
+ * DHT-cache miss (call site lib/nx_dht.c:632) — 286 lit/len + 30 distance counts to a length-limited
+ * (<= 15 bit) dynamic Huffman table, written as the RFC 1951 3.2.7 block header from HLIT on, the
+ * bytes of cpb.in_dht.  nxgpu_dhtgen has dhtgen()'s own argument list (counts in host byte order;
+ * *dht_num_valid_bits: valid bits of the last byte, 0 meaning 8; cpb_header: prepend the 16-byte CPB
+ * prefix holding in_dhtlen).  The batch flavour takes n x 316 counters and returns n x 288 bytes +
+ * n bit lengths.  Unlike the reference's one-pass heuristic limiter the code is an exact Kraft-complete
+ * Huffman code; symbols with a zero count get no code (pre-fill with fill_zero_lzcounts(…, 1), as
+ * lib/nx_dht.c:627 does, for a table that is reused on other data). */
+int nxgpu_dhtgen(nxgpu_ctx *ctx, const uint32_t *lhist, int num_lhist, const uint32_t *dhist, int num_dhist,
+		 char *dht, int *dht_num_bytes, int *dht_num_valid_bits, int cpb_header);
+int nxgpu_dhtgen_batch(nxgpu_ctx *ctx, const uint32_t *counts, size_t n, uint8_t *dht, uint32_t *dht_bits, int mem);
+
 /* --- job coalescing inside nxu_run_job (the reference submits one CRB per
  * paste, lib/gzip_vas.c:281-417).  Descriptors submitted concurrently from different threads are
  * run as one GPU batch; this reports how that went on device `dev` since process start:

@@ -74,6 +74,7 @@ EXPORTS = [
     "nxgpu_checksum_batch", "nxgpu_crc32", "nxgpu_adler32", "nxgpu_crc32_combine", "nxgpu_adler32_combine",
     "nxgpu_deflate_batch", "nxgpu_deflate_bound", "nxgpu_deflate_stream", "nxgpu_deflate_stream_bound",
     "nxgpu_inflate_batch", "nxgpu_inflate_stream", "nxgpu_makedata", "nxgpu_job_stats",
+    "nxgpu_dhtgen", "nxgpu_dhtgen_batch",
 ]
 
 _lib = None
@@ -119,6 +120,8 @@ def load_library() -> C.CDLL:
         "nxgpu_inflate_stream": (i32, [vp, vp, u64, vp, u64, i32, P(u64), u32, u32, P(StreamResult), i32]),
         "nxgpu_makedata": (u64, [i32, i32, vp, u64, vp, u64]),
         "nxgpu_job_stats": (None, [i32, P(u64), P(u64), P(u64)]),
+        "nxgpu_dhtgen": (i32, [vp, P(u32), i32, P(u32), i32, C.c_char_p, P(i32), P(i32), i32]),
+        "nxgpu_dhtgen_batch": (i32, [vp, P(u32), sz, vp, P(u32), i32]),
         "nx_function_begin": (i32, [i32, i32, vp]),
         "nx_function_end": (i32, [vp]),
         "nx_wait_ticks": (u64, [u64, u64, i32]),
@@ -291,6 +294,24 @@ class Engine:
         res = (DeflateResult * n)()
         self._check(self.lib.nxgpu_deflate_batch(self.ctx, arr, n, res, level, mem), "nxgpu_deflate_batch")
         return list(res)
+
+    # ---- dynamic Huffman table generation (lib/nx_dhtgen.c:945) ----
+    def dhtgen(self, lhist: Sequence[int], dhist: Sequence[int]) -> Tuple[bytes, int]:
+        """286 lit/len + 30 distance counts -> (cpb.in_dht bytes, length in bits)."""
+        la = (C.c_uint32 * len(lhist))(*lhist)
+        da = (C.c_uint32 * len(dhist))(*dhist)
+        out = C.create_string_buffer(320)
+        nb, vb = C.c_int(), C.c_int()
+        self._check(self.lib.nxgpu_dhtgen(self.ctx, la, len(lhist), da, len(dhist), out, C.byref(nb), C.byref(vb), 0), "nxgpu_dhtgen")
+        return out.raw[: nb.value], 8 * nb.value - ((8 - vb.value) if vb.value else 0)
+
+    def dhtgen_batch(self, counts: Sequence[Sequence[int]]) -> List[Tuple[bytes, int]]:
+        n = len(counts)
+        flat = (C.c_uint32 * (316 * n))(*[x for c in counts for x in c])
+        out = C.create_string_buffer(288 * n)
+        bits = (C.c_uint32 * n)()
+        self._check(self.lib.nxgpu_dhtgen_batch(self.ctx, flat, n, out, bits, MEM_HOST), "nxgpu_dhtgen_batch")
+        return [(out.raw[288 * i: 288 * i + (bits[i] + 7) // 8], bits[i]) for i in range(n)]
 
     # ---- inflate ----
     def inflate_batch(self, items: Sequence[InflateItem], mem: int = MEM_HOST) -> List[InflateResult]:

@@ -132,6 +132,7 @@ size_t deflate_scratch_words(uint32_t tok_stride);   // per-CTA token scratch (u
 cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_jobs, int level,
 			   uint32_t *tok_scratch, uint32_t tok_stride, int grid, cudaStream_t s,
 			   uint32_t *job_counter, const uint32_t *ready, uint32_t jobs_per_flag);
+cudaError_t launch_dhtgen(const uint32_t *counts, uint32_t n, uint8_t *dht_out, uint32_t *dht_bits, cudaStream_t s);
 cudaError_t launch_inflate(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s);
 // checksum.cu
 cudaError_t checksum_init_tables();

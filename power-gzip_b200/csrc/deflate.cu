@@ -1389,7 +1389,73 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 	}
 }
 
+// ---- DHT generation on its own (lib/nx_dhtgen.c:945 dhtgen(), called from lib/nx_dht.c:632 on a cache miss) ----
+// One CTA per histogram: 286 lit/len + 30 distance counts in, the RFC 1951 §3.2.7 dynamic header from
+// HLIT on (the bytes of cpb.in_dht, inc_nx/nxu.h:300-310) and its length in bits out.  Same
+// length-limited Huffman construction the deflate kernel uses for its own blocks (build_dynamic).
+__global__ void __launch_bounds__(kThreads, 1)
+dhtgen_kernel(const uint32_t *__restrict__ counts, uint32_t n, uint8_t *__restrict__ dht_out, uint32_t *__restrict__ dht_bits)
+{
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+	HuffScratch &H = *reinterpret_cast<HuffScratch *>(S.prev);
+	for (uint32_t b = blockIdx.x; b < n; b += gridDim.x) {
+		const uint32_t *c = counts + (size_t)b * 316;
+		for (int i = threadIdx.x; i < 288; i += kThreads)
+			S.ll_freq[i] = i < 286 ? c[i] : 0;
+		if (threadIdx.x < 32)
+			S.d_freq[threadIdx.x] = threadIdx.x < 30 ? c[286 + threadIdx.x] : 0;
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			if (S.ll_freq[256] == 0)
+				S.ll_freq[256] = 1;                           // every block ends with an end-of-block symbol
+			// every tree needs two coded symbols to be complete (as in deflate_kernel)
+			S.misc[0] = S.misc[1] = 0xFFFFu; S.misc[2] = 0;
+			int nz = 0;
+			for (int i = 0; i < 30; i++) nz += S.d_freq[i] != 0;
+			if (nz == 0) { S.d_freq[0] = 1; S.d_freq[1] = 1; S.misc[0] = 0; S.misc[1] = 1; }
+			else if (nz == 1) { const int f = S.d_freq[0] ? 1 : 0; S.d_freq[f] = 1; S.misc[0] = f; }
+			nz = 0;
+			for (int i = 0; i < 286; i++) nz += S.ll_freq[i] != 0;
+			if (nz == 1) { S.ll_freq[0] += 1; S.misc[2] = 1; }
+		}
+		__syncthreads();
+		build_dynamic(S, H, 0);
+		// drop the 3 block-header bits in front: cpb.in_dht starts at HLIT
+		const uint32_t nbits = H.hdr_bits - 3;
+		for (uint32_t i = threadIdx.x; i < 288; i += kThreads) {
+			uint32_t v = 0;
+			if (8 * i < nbits) {
+				const uint32_t bit = 8 * i + 3, w = bit >> 5, o = bit & 31;
+				v = H.hdr_words[w] >> o;
+				if (o > 24)
+					v |= H.hdr_words[w + 1] << (32 - o);
+				v &= 0xff;
+				if (nbits - 8 * i < 8)
+					v &= (1u << (nbits - 8 * i)) - 1;
+			}
+			dht_out[(size_t)b * 288 + i] = (uint8_t)v;
+		}
+		if (threadIdx.x == 0)
+			dht_bits[b] = nbits;
+		__syncthreads();
+	}
+}
+
 } // namespace
+
+cudaError_t launch_dhtgen(const uint32_t *counts, uint32_t n, uint8_t *dht_out, uint32_t *dht_bits, cudaStream_t s)
+{
+	static bool configured = false;
+	if (!configured) {
+		cudaError_t e = cudaFuncSetAttribute(dhtgen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+		if (e != cudaSuccess)
+			return e;
+		configured = true;
+	}
+	dhtgen_kernel<<<n < (uint32_t)kNumSMs ? n : kNumSMs, kThreads, sizeof(Smem), s>>>(counts, n, dht_out, dht_bits);
+	return cudaGetLastError();
+}
 
 size_t deflate_smem_bytes() { return sizeof(Smem); }
 size_t deflate_scratch_words(uint32_t tok_stride) { return scratch_words(tok_stride); }

@@ -632,6 +632,66 @@ int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *
 	return 0;
 }
 
+/* --------------------------- DHT generation --------------------------- */
+
+// n histograms of 316 counters (286 lit/len then 30 distances, host byte order) -> n dynamic headers of
+// up to 288 bytes (bits from HLIT on, LSB first, exactly the bytes of cpb.in_dht) + their bit lengths.
+int nxgpu_dhtgen_batch(nxgpu_ctx *c, const uint32_t *counts, size_t n, uint8_t *dht, uint32_t *dht_bits, int mem)
+{
+	if (!c || !counts || !dht || !dht_bits) return NXGPU_E_ARG;
+	if (n == 0) return 0;
+	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
+	int rc;
+	const uint32_t *d_counts = counts;
+	uint8_t *d_dht = dht;
+	uint32_t *d_bits = dht_bits;
+	if (mem == NXGPU_MEM_HOST) {
+		if ((rc = c->d_lz.reserve(n * 316 * 4))) return rc;
+		if ((rc = c->d_dht.reserve(n * 288 + n * 4 + 16))) return rc;
+		NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_lz.p, counts, n * 316 * 4, cudaMemcpyHostToDevice, c->stream));
+		d_counts = static_cast<const uint32_t *>(c->d_lz.p);
+		d_dht = static_cast<uint8_t *>(c->d_dht.p);
+		d_bits = reinterpret_cast<uint32_t *>(d_dht + align_up(n * 288, 16));
+	}
+	NXGPU_CUDA_OK(launch_dhtgen(d_counts, (uint32_t)n, d_dht, d_bits, c->stream));
+	c->launches++;
+	if (mem == NXGPU_MEM_HOST) {
+		NXGPU_CUDA_OK(cudaMemcpyAsync(dht, d_dht, n * 288, cudaMemcpyDeviceToHost, c->stream));
+		NXGPU_CUDA_OK(cudaMemcpyAsync(dht_bits, d_bits, n * 4, cudaMemcpyDeviceToHost, c->stream));
+	}
+	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+// The signature of the reference's dhtgen() (lib/nx_dhtgen.c:945-954) plus the context.
+int nxgpu_dhtgen(nxgpu_ctx *c, const uint32_t *lhist, int num_lhist, const uint32_t *dhist, int num_dhist,
+		 char *dht, int *dht_num_bytes, int *dht_num_valid_bits, int cpb_header)
+{
+	if (!c || !lhist || !dhist || !dht || !dht_num_bytes || !dht_num_valid_bits) return NXGPU_E_ARG;
+	if (num_lhist < 257 || num_lhist > 286 || num_dhist < 0 || num_dhist > 30) return NXGPU_E_ARG;
+	uint32_t counts[316];
+	memset(counts, 0, sizeof(counts));
+	memcpy(counts, lhist, (size_t)num_lhist * 4);
+	memcpy(counts + 286, dhist, (size_t)num_dhist * 4);
+	uint8_t out[288];
+	uint32_t bits = 0;
+	const int rc = nxgpu_dhtgen_batch(c, counts, 1, out, &bits, NXGPU_MEM_HOST);
+	if (rc) return rc;
+	const int nbytes = (int)((bits + 7) / 8);
+	char *body = dht;
+	if (cpb_header) {
+		// the 16 bytes in front of in_dht: in_dhtlen lives in the low 12 bits of the fourth word (inc_nx/nxu.h:296-310)
+		memset(dht, 0, 16);
+		dht[14] = (char)((bits >> 8) & 0x0f);
+		dht[15] = (char)(bits & 0xff);
+		body = dht + 16;
+	}
+	memcpy(body, out, (size_t)nbytes);
+	*dht_num_bytes = nbytes;
+	*dht_num_valid_bits = (int)(bits % 8);      // 0 is encoded as 8 bits
+	return 0;
+}
+
 /* ------------------------------- inflate ------------------------------- */
 
 int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n, nxgpu_inflate_result *results, int mem)

@@ -364,3 +364,42 @@ def test_mixed_descriptors_from_many_threads_coalesce_and_stay_exact(engines, pg
         else:
             assert zlib.decompress(_decode_one_block(0, g), -15) == data
             assert (g.crc(), g.adler()) == (zlib.crc32(data), zlib.adler32(data))
+
+
+@pytest.mark.gpu
+def test_dhtgen_against_the_reference_tables(engines, pg, alice):
+    """nxgpu_dhtgen stands in for lib/nx_dhtgen.c:945 dhtgen().  For the histograms of
+    tests/golden/dhtgen_vectors.json (tables there were made by the reference's own code) the GPU's table must
+    be a complete code of at most 15 bits covering every counted symbol and must not cost more bits than the
+    reference's; the single and the batch call agree; and a table made from a COUNT job's lzcounts drives a
+    DHT compress job on both engines whose block decodes to the source."""
+    from dht_util import parse_dht, block_cost, kraft
+    gpu, cpu = engines
+    vec = json.load(open(os.path.join(ROOT, "tests", "golden", "dhtgen_vectors.json")))["vectors"]
+    with pg.Engine(0) as eng:
+        batch = eng.dhtgen_batch([v["counts"] for v in vec])
+        for v, (bdht, bbits) in zip(vec, batch):
+            c = v["counts"]
+            dht, bits = eng.dhtgen(c[:286], c[286:])
+            assert (dht, bits) == (bdht, bbits), v["name"]
+            ll, dd = parse_dht(dht, bits)
+            assert max(ll) <= 15 and max(dd) <= 15
+            assert abs(kraft(ll) - 1.0) < 1e-9 and abs(kraft(dd) - 1.0) < 1e-9, v["name"]
+            rl, rd = parse_dht(bytes.fromhex(v["ref_dht_hex"]), v["ref_bits"])
+            assert block_cost(c, ll, dd, bits) <= block_cost(c, rl, rd, v["ref_bits"]), v["name"]
+        # sparse histograms: symbols without a count get no code; single-symbol trees are completed
+        for counts in ([0] * 97 + [5] + [0] * 158 + [1] + [0] * 29 + [0] * 30,               # only 'a' and EOB, no distances
+                       [3] * 256 + [1] + [7] + [0] * 28 + [9] + [0] * 29):                     # one length, one distance
+            dht, bits = eng.dhtgen(counts[:286], counts[286:])
+            ll, dd = parse_dht(dht, bits)
+            assert all(ll[s] for s in range(286) if counts[s]) and all(dd[s] for s in range(30) if counts[286 + s])
+            assert kraft(ll) <= 1.0 + 1e-9 and kraft(dd) <= 1.0 + 1e-9
+        # the reference's flow (lib/nx_dht.c:568-676): COUNT job -> lzcounts -> dhtgen -> DHT job
+        text = alice[20000:90000]
+        j = gpu(Job(0x04, [text], 300000))
+        lz = [max(1, int.from_bytes(j.get(256 + 400 + 4 * i, 4), "big")) for i in range(316)]
+        dht, bits = eng.dhtgen(lz[:286], lz[286:])
+        for run in (gpu, cpu):
+            j = run(Job(0x02, [text], 300000, rem_or_dhtlen=bits, dht=dht))
+            assert j.cc() == 0, j.cc()
+            assert zlib.decompress(_decode_one_block(0x02, j), -15) == text

@@ -163,3 +163,26 @@ def test_dynblock_cost_brackets_zlib(oracle, alice):
     bits = oracle.oracle_dynblock_bits(ll, d)
     # order-0 entropy coding of alice29 is about 4.6 bits/byte
     assert 4.4 * len(alice) < bits < 4.8 * len(alice)
+
+
+def test_reference_dhtgen_vectors_are_valid_tables(oracle):
+    """tests/golden/dhtgen_vectors.json holds tables made by the reference's own lib/nx_dhtgen.c
+    (oracle/_ref/dhtgen_test): each must parse as a complete, length-limited code covering every
+    counted symbol, and the oracle's Huffman restatement must not cost more than the reference."""
+    import ctypes
+    from dht_util import parse_dht, block_cost, kraft
+    vec = json.load(open(os.path.join(GOLDEN, "dhtgen_vectors.json")))["vectors"]
+    assert len(vec) >= 6
+    u32 = ctypes.c_uint32
+    for v in vec:
+        c = v["counts"]
+        ll, dd = parse_dht(bytes.fromhex(v["ref_dht_hex"]), v["ref_bits"])
+        assert max(ll) <= 15 and max(dd) <= 15
+        assert abs(kraft(ll) - 1.0) < 1e-9 and abs(kraft(dd) - 1.0) < 1e-9, v["name"]
+        ref_cost = block_cost(c, ll, dd, v["ref_bits"])
+        ol = (ctypes.c_uint8 * 286)(); od = (ctypes.c_uint8 * 30)()
+        oracle.oracle_huff_lengths((u32 * 286)(*c[:286]), 286, 15, ol)
+        oracle.oracle_huff_lengths((u32 * 30)(*c[286:]), 30, 15, od)
+        sym_bits_ref = ref_cost - 3 - v["ref_bits"]
+        sym_bits_oracle = block_cost(c, list(ol), list(od), 0) - 3
+        assert sym_bits_oracle <= sym_bits_ref, (v["name"], sym_bits_oracle, sym_bits_ref)
