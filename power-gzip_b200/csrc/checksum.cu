@@ -234,19 +234,25 @@ checksum_ranges_kernel(const Range *__restrict__ ranges, uint32_t n_ranges, Part
 	}
 }
 
-// one warp per job: job j owns ranges [rs[j], rs[j+1])
-__global__ void checksum_combine_kernel(const Range *__restrict__ ranges, const Partial *__restrict__ parts,
-					const uint32_t *__restrict__ rs, uint32_t n_jobs,
-					const uint32_t *__restrict__ crc_seed, const uint32_t *__restrict__ adler_seed,
-					uint32_t *__restrict__ crc_out, uint32_t *__restrict__ adler_out)
+// kGroup threads per job (a warp for batches of small jobs, a whole CTA for a job cut into many
+// ranges): job j owns ranges [rs[j], rs[j+1]).  Every range's partial is shifted by the bytes that
+// follow it inside the job (x^(8n) mod P by square-and-multiply, ~30 GF(2) multiplications — the
+// expensive part, hence one thread per range) and the group folds the results.
+template <int kGroup>
+__global__ void __launch_bounds__(kGroup >= 256 ? kGroup : 256)
+checksum_combine_kernel(const Range *__restrict__ ranges, const Partial *__restrict__ parts,
+			const uint32_t *__restrict__ rs, uint32_t n_jobs,
+			const uint32_t *__restrict__ crc_seed, const uint32_t *__restrict__ adler_seed,
+			uint32_t *__restrict__ crc_out, uint32_t *__restrict__ adler_out)
 {
-	const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	if (j >= n_jobs)
-		return;
-	const uint32_t r0 = rs[j], r1 = rs[j + 1];
+	__shared__ uint32_t red_c[32], red_s1[32], red_s2[32];
+	__shared__ unsigned long long red_t[32];
+	const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) / kGroup, lid = threadIdx.x % kGroup, lane = threadIdx.x & 31;
+	const bool live = j < n_jobs;
+	const uint32_t r0 = live ? rs[j] : 0, r1 = live ? rs[j + 1] : 0;
 	uint32_t c = 0, s1 = 0, s2 = 0;
 	uint64_t total = 0;
-	for (uint32_t r = r0 + lane; r < r1; r += 32) {
+	for (uint32_t r = r0 + lid; r < r1; r += kGroup) {
 		const Range R = ranges[r];
 		const Partial p = parts[r];
 		c ^= multmodp(x2nmodp_dev(R.after, 3), p.crc);
@@ -256,12 +262,26 @@ __global__ void checksum_combine_kernel(const Range *__restrict__ ranges, const 
 	}
 	for (int o = 16; o; o >>= 1) {
 		c ^= __shfl_xor_sync(0xffffffffu, c, o);
-		s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-		s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+		s1 = (s1 + __shfl_xor_sync(0xffffffffu, s1, o)) % kBase;
+		s2 = (s2 + __shfl_xor_sync(0xffffffffu, s2, o)) % kBase;
 		total += __shfl_xor_sync(0xffffffffu, total, o);
 	}
-	if (lane == 0) {
-		s1 %= kBase; s2 %= kBase;
+	if (kGroup > 32) {
+		// one job per CTA: fold the warps through shared memory
+		if (lane == 0) { red_c[threadIdx.x >> 5] = c; red_s1[threadIdx.x >> 5] = s1; red_s2[threadIdx.x >> 5] = s2; red_t[threadIdx.x >> 5] = total; }
+		__syncthreads();
+		if (threadIdx.x >= 32)
+			return;
+		const bool has = lane < kGroup / 32;
+		c = has ? red_c[lane] : 0; s1 = has ? red_s1[lane] : 0; s2 = has ? red_s2[lane] : 0; total = has ? red_t[lane] : 0;
+		for (int o = 16; o; o >>= 1) {
+			c ^= __shfl_xor_sync(0xffffffffu, c, o);
+			s1 = (s1 + __shfl_xor_sync(0xffffffffu, s1, o)) % kBase;
+			s2 = (s2 + __shfl_xor_sync(0xffffffffu, s2, o)) % kBase;
+			total += __shfl_xor_sync(0xffffffffu, total, o);
+		}
+	}
+	if (live && lane == 0 && lid == 0) {
 		if (crc_out) {
 			// crc32(seed, data) = ~( shift(~seed, len) ^ raw0(data) )
 			const uint32_t seed = crc_seed ? crc_seed[j] : 0;
@@ -390,14 +410,20 @@ cudaError_t launch_checksum_ranges(const void *d_ranges, uint32_t n_ranges, void
 
 cudaError_t launch_checksum_combine(const void *d_ranges, const void *d_parts, const uint32_t *d_rs, uint32_t n_jobs,
 				    const uint32_t *d_crc_seed, const uint32_t *d_adler_seed,
-				    uint32_t *d_crc_out, uint32_t *d_adler_out, cudaStream_t s)
+				    uint32_t *d_crc_out, uint32_t *d_adler_out, cudaStream_t s, uint32_t max_ranges_per_job)
 {
 	if (n_jobs == 0)
 		return cudaSuccess;
-	const uint32_t warps_per_cta = 8;
-	const uint32_t grid = (n_jobs + warps_per_cta - 1) / warps_per_cta;
-	checksum_combine_kernel<<<grid, warps_per_cta * 32, 0, s>>>(static_cast<const Range *>(d_ranges),
-		static_cast<const Partial *>(d_parts), d_rs, n_jobs, d_crc_seed, d_adler_seed, d_crc_out, d_adler_out);
+	const Range *r = static_cast<const Range *>(d_ranges);
+	const Partial *p = static_cast<const Partial *>(d_parts);
+	if (max_ranges_per_job > 64) {
+		// a big buffer cut into many ranges: a CTA per job, a thread per range
+		checksum_combine_kernel<1024><<<n_jobs, 1024, 0, s>>>(r, p, d_rs, n_jobs, d_crc_seed, d_adler_seed, d_crc_out, d_adler_out);
+	} else {
+		const uint32_t warps_per_cta = 8;
+		const uint32_t grid = (n_jobs + warps_per_cta - 1) / warps_per_cta;
+		checksum_combine_kernel<32><<<grid, warps_per_cta * 32, 0, s>>>(r, p, d_rs, n_jobs, d_crc_seed, d_adler_seed, d_crc_out, d_adler_out);
+	}
 	return cudaGetLastError();
 }
 

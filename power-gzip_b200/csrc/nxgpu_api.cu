@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <algorithm>
 #include <vector>
 #include "common.cuh"
 #include "../../include/nxgpu.h"
@@ -312,8 +313,10 @@ extern "C++" int nxgpu::checksum_device(nxgpu_ctx *c, const nxgpu_cksum_item *it
 	timer_begin(c, 2);
 	NXGPU_CUDA_OK(launch_checksum_ranges(d, (uint32_t)nr, c->d_parts.p, which, c->stream));
 	timer_end(c, 2);
+	uint32_t max_rpj = 1;
+	for (size_t i = 0; i < n; i++) max_rpj = std::max(max_rpj, rs[i + 1] - rs[i]);
 	NXGPU_CUDA_OK(launch_checksum_combine(d, c->d_parts.p, d_rs, (uint32_t)n, d_seeds, d_seeds + n,
-					      (which & 1) ? d_crc : nullptr, (which & 2) ? d_adler : nullptr, c->stream));
+					      (which & 1) ? d_crc : nullptr, (which & 2) ? d_adler : nullptr, c->stream, max_rpj));
 	c->launches++;
 	return 0;
 }
