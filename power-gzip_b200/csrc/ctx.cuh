@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include <utility>
 #include <vector>
 #include "common.cuh"
@@ -66,8 +67,12 @@ struct KernelTimer {
 } // namespace nxgpu
 
 using namespace nxgpu;
+#define NXGPU_LOCK(c) std::lock_guard<std::recursive_mutex> nxgpu_lock_((c)->mu)
 
 struct nxgpu_ctx {
+	// a context owns one stream and one set of staging buffers: the batch calls serialise on this
+	// (recursive: nxgpu_inflate_stream -> nxgpu_inflate_batch); contexts are independent of each other
+	std::recursive_mutex mu;
 	int dev = 0;
 	cudaStream_t stream = nullptr;
 	cudaStream_t copy_stream = nullptr;      // uploads of host-pointer streams, overlapped with compute

@@ -183,6 +183,7 @@ int nxgpu_dev_free(nxgpu_ctx *c, void *dptr)
 int nxgpu_memcpy_h2d(nxgpu_ctx *c, void *dptr, const void *hptr, size_t bytes)
 {
 	if (!c) return NXGPU_E_ARG;
+	NXGPU_LOCK(c);
 	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
 	NXGPU_CUDA_OK(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, c->stream));
 	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -191,6 +192,7 @@ int nxgpu_memcpy_h2d(nxgpu_ctx *c, void *dptr, const void *hptr, size_t bytes)
 int nxgpu_memcpy_d2h(nxgpu_ctx *c, void *hptr, const void *dptr, size_t bytes)
 {
 	if (!c) return NXGPU_E_ARG;
+	NXGPU_LOCK(c);
 	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
 	NXGPU_CUDA_OK(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
 	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -210,18 +212,21 @@ int nxgpu_host_free(void *hptr)
 int nxgpu_sync(nxgpu_ctx *c)
 {
 	if (!c) return NXGPU_E_ARG;
+	NXGPU_LOCK(c);
 	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
 	return 0;
 }
 int nxgpu_timer_start(nxgpu_ctx *c)
 {
 	if (!c) return NXGPU_E_ARG;
+	NXGPU_LOCK(c);
 	NXGPU_CUDA_OK(cudaEventRecord(c->t0, c->stream));
 	return 0;
 }
 int nxgpu_timer_stop(nxgpu_ctx *c, float *ms)
 {
 	if (!c || !ms) return NXGPU_E_ARG;
+	NXGPU_LOCK(c);
 	NXGPU_CUDA_OK(cudaEventRecord(c->t1, c->stream));
 	NXGPU_CUDA_OK(cudaEventSynchronize(c->t1));
 	NXGPU_CUDA_OK(cudaEventElapsedTime(ms, c->t0, c->t1));
@@ -230,6 +235,8 @@ int nxgpu_timer_stop(nxgpu_ctx *c, float *ms)
 uint64_t nxgpu_launch_count(nxgpu_ctx *c) { return c ? c->launches : 0; }
 int nxgpu_kernel_time(nxgpu_ctx *c, const char *family, double *ms_total, uint64_t *launches)
 {
+	if (!c) return NXGPU_E_ARG;
+	NXGPU_LOCK(c);
 	const int f = family ? fam_index(family) : -1;
 	if (!c || f < 0) return NXGPU_E_ARG;
 	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -324,6 +331,7 @@ extern "C++" int nxgpu::checksum_device(nxgpu_ctx *c, const nxgpu_cksum_item *it
 int nxgpu_checksum_batch(nxgpu_ctx *c, const nxgpu_cksum_item *items, size_t n, nxgpu_cksum_result *results, int mem)
 {
 	if (!c || (!items && n) || (!results && n)) return NXGPU_E_ARG;
+	NXGPU_LOCK(c);
 	if (n == 0) return 0;
 	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
 	int rc;
@@ -425,6 +433,7 @@ int nxgpu_deflate_batch(nxgpu_ctx *c, const nxgpu_deflate_item *items, size_t n,
 			int level, int mem)
 {
 	if (!c || (!items && n) || (!results && n)) return NXGPU_E_ARG;
+	NXGPU_LOCK(c);
 	if (n == 0) return 0;
 	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
 	int rc;
@@ -514,6 +523,7 @@ int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *
 			 int level, int wrap, uint32_t chunk, uint64_t *chunk_offsets, nxgpu_stream_result *res, int mem)
 {
 	if (!c || (!src && src_len) || !dst || !res) return NXGPU_E_ARG;
+	NXGPU_LOCK(c);
 	// true Z_FULL_FLUSH semantics: no chunk looks back into the previous one, so the chunks of the
 	// index can be inflated in parallel (nxgpu_inflate_stream)
 	const bool independent = (wrap & NXGPU_STREAM_INDEPENDENT) != 0;
@@ -642,6 +652,7 @@ int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *
 int nxgpu_dhtgen_batch(nxgpu_ctx *c, const uint32_t *counts, size_t n, uint8_t *dht, uint32_t *dht_bits, int mem)
 {
 	if (!c || !counts || !dht || !dht_bits) return NXGPU_E_ARG;
+	NXGPU_LOCK(c);
 	if (n == 0) return 0;
 	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
 	int rc;
@@ -700,6 +711,7 @@ int nxgpu_dhtgen(nxgpu_ctx *c, const uint32_t *lhist, int num_lhist, const uint3
 int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n, nxgpu_inflate_result *results, int mem)
 {
 	if (!c || (!items && n) || (!results && n)) return NXGPU_E_ARG;
+	NXGPU_LOCK(c);
 	if (n == 0) return 0;
 	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
 	int rc;
@@ -806,6 +818,7 @@ int nxgpu_inflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *
 			 const uint64_t *chunk_offsets, uint32_t n_chunks, uint32_t chunk, nxgpu_stream_result *res, int mem)
 {
 	if (!c || !src || (!dst && dst_cap) || !res || !chunk_offsets || n_chunks == 0) return NXGPU_E_ARG;
+	NXGPU_LOCK(c);
 	if (wrap != NXGPU_WRAP_RAW && wrap != NXGPU_WRAP_ZLIB && wrap != NXGPU_WRAP_GZIP) return NXGPU_E_ARG;
 	if (chunk == 0) chunk = 262144;
 	const uint64_t trailer = wrap == NXGPU_WRAP_GZIP ? 8 : wrap == NXGPU_WRAP_ZLIB ? 4 : 0;

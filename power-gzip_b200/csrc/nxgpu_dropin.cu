@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 #include <mutex>
 #include "common.cuh"
 #include "../../include/nxgpu.h"
@@ -22,10 +23,19 @@ nxgpu_ctx *g_ctx[16];
 
 // one shared context per device, created on first use (handles are shared by up to
 // 10 000 streams/threads, lib/nx_zlib.c:531-551, so the context is too)
+pid_t g_pid;
+
 nxgpu_ctx *ctx_for(int dev)
 {
 	if (dev < 0 || dev >= 16)
 		dev = 0;
+	// a forked child must not use the parent's handle (lib/nx_zlib.c:535-537 checks creator_pid the same
+	// way): the CUDA context does not survive fork(), so forget it — opening anew then fails cleanly
+	// (nx_function_begin returns -1/ENODEV) unless the child exec()s first
+	if (g_pid != getpid()) {
+		memset(g_ctx, 0, sizeof(g_ctx));
+		g_pid = getpid();
+	}
 	if (!g_ctx[dev]) {
 		nxgpu_ctx *c = nullptr;
 		if (nxgpu_open(dev, &c) != 0)

@@ -192,6 +192,7 @@ struct JobState {
 // (nxgpu_dropin.cu) and hands it over here.
 void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 {
+	NXGPU_LOCK(c);
 	std::vector<JobState> js(n);
 	auto fail_all = [&]() { for (size_t i = 0; i < n; i++) if (js[i].kind != JobState::DONE) rcs[i] = -EAGAIN; };
 	for (size_t i = 0; i < n; i++) rcs[i] = 0;

@@ -420,3 +420,26 @@ def test_deflate_stream_raw_continuation(engine, pg, alice):
     last = engine.compress(b, level=6, wrap=pg.WRAP_RAW)
     assert first[-4:] == b"\x00\x00\xff\xff"
     assert zlib.decompress(first + last, -15) == a + b
+
+
+def test_one_context_shared_by_threads(engine, pg, alice):
+    # the reference shares one device handle among up to 10 000 streams (lib/nx_zlib.c:531-551); the batch
+    # calls of one context serialise internally, so concurrent callers get their own results
+    import threading
+    datas = [pg.makedata(1 + (i % 5), 18, alice)[i * 1000:] for i in range(12)]
+    out, errs = [None] * len(datas), []
+
+    def work(i):
+        try:
+            z = engine.compress(datas[i], level=1 + (i % 9), wrap=pg.WRAP_GZIP, chunk=65536)
+            assert engine.crc32(datas[i]) == zlib.crc32(datas[i])
+            out[i] = engine.uncompress(z, len(datas[i]))
+        except Exception as e:                       # noqa: BLE001
+            errs.append(repr(e))
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(datas))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    assert out == datas
