@@ -74,7 +74,10 @@ __device__ inline uint32_t x2nmodp_dev(uint64_t n, unsigned k)
 
 struct __align__(16) CkSmem {
 	uint8_t tile[2][kCkThreads * kStripPad];   // 2 x 40 KiB
-	uint32_t slice[4][256];
+	// slice-by-4 tables, one private copy per lane: entry (k, v) of lane L sits at word ((k*256 + v) * 32 + L),
+	// i.e. always in bank L, so the four data-dependent look-ups per word never conflict (a single shared
+	// copy cost ~3.5 wavefronts per look-up and bounded the kernel at a third of the HBM peak)
+	uint32_t slice32[4 * 256 * 32];            // 128 KiB
 	uint32_t gap[4][256];
 	uint32_t red[kCkThreads / 32][4];
 };
@@ -83,11 +86,11 @@ __device__ __forceinline__ uint32_t apply4(const uint32_t (*t)[256], uint32_t c)
 {
 	return t[0][c & 255] ^ t[1][(c >> 8) & 255] ^ t[2][(c >> 16) & 255] ^ t[3][c >> 24];
 }
-// crc register after one more little-endian word
-__device__ __forceinline__ uint32_t crc_word(const uint32_t (*s)[256], uint32_t c, uint32_t w)
+// crc register after one more little-endian word; sl = the lane's own table copy (slice32 + lane)
+__device__ __forceinline__ uint32_t crc_word(const uint32_t *sl, uint32_t c, uint32_t w)
 {
 	c ^= w;
-	return s[3][c & 255] ^ s[2][(c >> 8) & 255] ^ s[1][(c >> 16) & 255] ^ s[0][c >> 24];
+	return sl[(3 * 256 + (c & 255)) << 5] ^ sl[(2 * 256 + ((c >> 8) & 255)) << 5] ^ sl[(1 * 256 + ((c >> 16) & 255)) << 5] ^ sl[(c >> 24) << 5];
 }
 
 struct Range { const uint8_t *src; uint64_t len; uint64_t after; uint32_t job; uint32_t pad_; };
@@ -118,17 +121,19 @@ __device__ void stage_tile(CkSmem &S, int buf, const uint8_t *abase, uint64_t ti
 }
 
 template <bool kCrc, bool kAdler>
-__global__ void __launch_bounds__(kCkThreads, 2)
+__global__ void __launch_bounds__(kCkThreads, 1)
 checksum_ranges_kernel(const Range *__restrict__ ranges, uint32_t n_ranges, Partial *__restrict__ parts)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	CkSmem &S = *reinterpret_cast<CkSmem *>(smem_raw);
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-	for (int i = t; i < 1024; i += kCkThreads) {
-		(&S.slice[0][0])[i] = (&g_tables.slice[0][0])[i];
+	for (int i = t; i < 1024; i += kCkThreads)
 		(&S.gap[0][0])[i] = (&g_tables.gap[0][0])[i];
-	}
+	if (kCrc)
+		for (int i = t; i < 4 * 256 * 32; i += kCkThreads)
+			S.slice32[i] = (&g_tables.slice[0][0])[i >> 5];
 	__syncthreads();
+	const uint32_t *sl = S.slice32 + lane;
 
 	for (uint32_t r = blockIdx.x; r < n_ranges; r += gridDim.x) {
 		const Range R = ranges[r];
@@ -159,7 +164,7 @@ checksum_ranges_kernel(const Range *__restrict__ ranges, uint32_t n_ranges, Part
 #pragma unroll
 				for (int j = 0; j < 4; j++) {
 					if (kCrc)
-						crc = crc_word(S.slice, crc, w[j]);
+						crc = crc_word(sl, crc, w[j]);
 					if (kAdler) {
 						b_ += 4 * a_;
 						b_ = __dp4a(w[j], 0x01020304u, b_);
@@ -396,7 +401,7 @@ cudaError_t launch_checksum_ranges(const void *d_ranges, uint32_t n_ranges, void
 {
 	if (n_ranges == 0)
 		return cudaSuccess;
-	uint32_t grid = n_ranges < (uint32_t)(2 * kNumSMs) ? n_ranges : (uint32_t)(2 * kNumSMs);
+	uint32_t grid = n_ranges < (uint32_t)kNumSMs ? n_ranges : (uint32_t)kNumSMs;      // one CTA per SM (212 KiB of shared memory)
 	const Range *r = static_cast<const Range *>(d_ranges);
 	Partial *p = static_cast<Partial *>(d_parts);
 	if (which == 1)
