@@ -386,6 +386,29 @@ def main():
         extra["inflate_kernel_GBps"] = nm * M / (ki / max(kni, 1)) / 1e6
         extra["inflate_roofline_frac"] = (nm * M + len(packed)) / (ki / max(kni, 1)) / 1e6 / hbm_peak
         del comp, out
+        # ---- the same members end to end through the host-pointer call: pinned host buffers, H2D of the compressed
+        # bytes and D2H of the inflated ones inside the timed region (wall clock) ----
+        if world == 1:
+            nh = min(nm, 16384)
+            hin_len = sum(lens[:nh])
+            hin, hout = C.c_void_p(), C.c_void_p()
+            lib.nxgpu_host_alloc(hin_len, C.byref(hin)); lib.nxgpu_host_alloc(nh * M, C.byref(hout))
+            C.memmove(hin, packed[:hin_len], hin_len)
+            hitems = (pg.InflateItem * nh)()
+            o = 0
+            for i in range(nh):
+                hitems[i] = pg.InflateItem(hin.value + o, lens[i], hout.value + i * M, M, pg.WRAP_GZIP, 0)
+                o += lens[i]
+            hres = (pg.InflateResult * nh)()
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                eng._check(lib.nxgpu_inflate_batch(eng.ctx, hitems, nh, hres, pg.MEM_HOST), "inflate e2e")
+                d = time.perf_counter() - t0
+                best = d if best is None else min(best, d)
+            assert all(r.rc == 0 and r.out_len == M for r in hres) and C.string_at(hout.value, M) == hb[:M]
+            extra["inflate_e2e_host_GBps"] = {"value": nh * M / best / 1e9, "members": nh, "h2d_bytes": hin_len, "d2h_bytes": nh * M}
+            lib.nxgpu_host_free(hin); lib.nxgpu_host_free(hout)
         # ---- ONE big member inflated as the segments of its sync-point index: the workload
         # deflated with independent chunks, then nxgpu_inflate_stream over the whole stream, device resident ----
         if world == 1:

@@ -170,7 +170,9 @@ uint32_t nxgpu_adler32_combine(uint32_t adler1, uint32_t adler2, uint64_t len2);
 enum {
 	NXGPU_F_FINAL = 1,        /* BFINAL=1, no joiner, padded to a byte          */
 	NXGPU_F_FIXED = 2,        /* fixed Huffman (Z_FIXED)                        */
-	NXGPU_F_NO_JOINER = 4     /* leave the tail bit-unaligned (nxu_run_job use) */
+	NXGPU_F_NO_JOINER = 4,    /* leave the tail bit-unaligned (nxu_run_job use) */
+	NXGPU_F_NO_HEADER = 8,    /* with FIXED or a caller's table: no block header in front ...        */
+	NXGPU_F_NO_EOB = 16       /* ... / no end-of-block behind: a piece of a block other items complete */
 };
 typedef struct {
 	const void *src;

@@ -146,6 +146,9 @@ cudaError_t launch_checksum_combine(const void *d_ranges, const void *d_parts, c
 cudaError_t launch_ranges_from_inflate(const InflateJob *jobs, const InflateOut *outs, uint32_t n, void *d_ranges, uint32_t *d_rs, cudaStream_t s);
 uint32_t host_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2);
 // stitch.cu
+struct BitPiece { const uint8_t *src; uint64_t nbits; uint64_t dst_bit; };
+struct BitGroup { uint8_t *dst; uint64_t total_bits; uint32_t first_piece; uint32_t n_pieces; };
+cudaError_t launch_bitconcat(const BitPiece *pieces, const BitGroup *groups, uint32_t n_groups, cudaStream_t s);
 cudaError_t launch_scan_offsets(const DeflateOut *outs, uint32_t n, uint64_t base, uint64_t *offsets, cudaStream_t s);
 cudaError_t launch_gather(const DeflateJob *jobs, const DeflateOut *outs, const uint64_t *offsets, uint32_t n,
 			  uint8_t *dst, uint64_t dst_cap, cudaStream_t s);

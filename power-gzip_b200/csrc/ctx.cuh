@@ -81,8 +81,8 @@ struct nxgpu_ctx {
 	uint32_t jobs_per_flag = 0;
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
 	uint64_t launches = 0;
-	DevBuf d_jobs, d_outs, d_tok, d_slots, d_ranges, d_parts, d_rs, d_seeds, d_cks, d_in, d_out, d_offsets, d_misc, d_dst_ptrs, d_dht, d_lz, d_ctr, d_flags, d_ijobs, d_iouts;
-	PinBuf h_jobs, h_outs, h_misc, h_stage, h_ones;
+	DevBuf d_jobs, d_outs, d_tok, d_slots, d_ranges, d_parts, d_rs, d_seeds, d_cks, d_in, d_out, d_offsets, d_misc, d_dst_ptrs, d_dht, d_lz, d_ctr, d_flags, d_ijobs, d_iouts, d_cat, d_catdesc;
+	PinBuf h_jobs, h_outs, h_misc, h_stage, h_ones, h_cat;
 	KernelTimer timers[3];           // 0 deflate, 1 inflate, 2 checksum
 	bool timing = true;
 };

@@ -1238,7 +1238,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 			}
 		}
 		if (threadIdx.x == 0)
-			S.ll_freq[256] = 1;                               // EOB
+			S.ll_freq[256] = (J.flags & NXGPU_F_NO_EOB) ? 0 : 1;   // EOB
 		__syncthreads();
 		const long long thuf0 = clock64();
 
@@ -1247,6 +1247,10 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 		const bool no_joiner = (J.flags & NXGPU_F_NO_JOINER) != 0;
 		const bool force_fixed = (J.flags & NXGPU_F_FIXED) != 0;
 		const bool preset = J.dht != nullptr;
+		// a piece of a block that other CTAs write the rest of (one large nxu_run_job descriptor cut into
+		// pieces, nxgpu_job.cu): no block header in front and / or no end-of-block behind; caller's or fixed table only
+		const bool no_header = (J.flags & NXGPU_F_NO_HEADER) != 0 && (preset || force_fixed);
+		const bool no_eob = (J.flags & NXGPU_F_NO_EOB) != 0;
 		if (J.lzcount) {
 			for (int i = threadIdx.x; i < 316; i += kThreads)
 				J.lzcount[i] = i < 286 ? S.ll_freq[i] : S.d_freq[i - 286];
@@ -1279,8 +1283,9 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 			assign_codes(H, H.d_len, 30, H.d_code);
 			if (threadIdx.x == 0) {
 				uint32_t bp = 0;
-				put_bits(H.hdr_words, bp, (is_final ? 1u : 0u) | (2u << 1), 3);
-				for (uint32_t b = 0; b < J.dht_bits; b += 8) {
+				if (!no_header)
+					put_bits(H.hdr_words, bp, (is_final ? 1u : 0u) | (2u << 1), 3);
+				for (uint32_t b = 0; b < J.dht_bits && !no_header; b += 8) {
 					uint32_t nb = min(8u, J.dht_bits - b);
 					put_bits(H.hdr_words, bp, J.dht[320 + (b >> 3)] & ((1u << nb) - 1), nb);
 				}
@@ -1310,7 +1315,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 				continue;
 			}
 		} else if (force_fixed) {
-			body_bits = fixed_cost_and_tables(S, H, true);
+			body_bits = fixed_cost_and_tables(S, H, true) - (no_header ? 3 : 0);
 			btype = 1;
 		} else {
 			const uint32_t dyn_bits = build_dynamic(S, H, is_final ? 1u : 0u);
@@ -1356,10 +1361,12 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 				copy_bits_to_stage(P, H.hdr_words, H.hdr_bits);
 				packer_flush(P, H.hdr_bits);
 			} else {
-				put_tail_bits(P, (is_final ? 1u : 0u) | (1u << 1), 3);
+				if (!no_header)
+					put_tail_bits(P, (is_final ? 1u : 0u) | (1u << 1), 3);
 			}
 			encode_tokens(S, H, P, tok, ntok);
-			put_tail_bits(P, H.ll_code[256], H.ll_len[256]);
+			if (!no_eob)
+				put_tail_bits(P, H.ll_code[256], H.ll_len[256]);
 			if (!is_final && !no_joiner) {
 				const uint32_t used = (P.words_out * 32 + P.carry);
 				const uint32_t pad = (8 - ((used + 3) & 7)) & 7;

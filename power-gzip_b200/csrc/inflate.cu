@@ -139,7 +139,9 @@ struct BitReader {
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr)
 {
 	uint32_t v;
-	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");   // ordered against the C++ stores that fill the tables
+	// (no memory clobber: every producer of these words — table build, input staging, fill_single — is
+	// separated from the readers by __syncwarp() or a call, which order a volatile asm)
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
 	return v;
 }
 __device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v)

@@ -152,9 +152,9 @@ void nxgpu_close(nxgpu_ctx *c)
 	cudaSetDevice(c->dev);
 	cudaStreamSynchronize(c->stream);
 	DevBuf *db[] = { &c->d_jobs, &c->d_outs, &c->d_tok, &c->d_slots, &c->d_ranges, &c->d_parts, &c->d_rs, &c->d_seeds,
-			 &c->d_cks, &c->d_in, &c->d_out, &c->d_offsets, &c->d_misc, &c->d_dst_ptrs, &c->d_dht, &c->d_lz, &c->d_ctr, &c->d_flags, &c->d_ijobs, &c->d_iouts };
+			 &c->d_cks, &c->d_in, &c->d_out, &c->d_offsets, &c->d_misc, &c->d_dst_ptrs, &c->d_dht, &c->d_lz, &c->d_ctr, &c->d_flags, &c->d_ijobs, &c->d_iouts, &c->d_cat, &c->d_catdesc };
 	for (DevBuf *b : db) b->release();
-	PinBuf *pb[] = { &c->h_jobs, &c->h_outs, &c->h_misc, &c->h_stage, &c->h_ones };
+	PinBuf *pb[] = { &c->h_jobs, &c->h_outs, &c->h_misc, &c->h_stage, &c->h_ones, &c->h_cat };
 	for (PinBuf *b : pb) b->release();
 	for (int f = 0; f < 3; f++)
 		for (cudaEvent_t e : c->timers[f].ev) cudaEventDestroy(e);

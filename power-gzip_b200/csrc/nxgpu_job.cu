@@ -181,7 +181,20 @@ struct JobState {
 	size_t ck = 0;                // index in the checksum batch
 	uint32_t out_len = 0;
 	bool ok = false;              // output is to be returned
+	size_t np = 1;                // compress: pieces the descriptor is cut into (one CTA each)
+	uint64_t out_bits = 0;        // compress: valid bits of the block
+	size_t cat_off = 0;           // compress, np > 1: where the joined block sits in d_cat
 };
+// A large compress descriptor is cut into pieces that separate CTAs compress with the SAME table (fixed or
+// the caller's DHT, so no table has to be agreed on): piece 0 carries the block header, the last one the
+// end-of-block, each is primed with the 32 KiB in front of it, and bitconcat_kernel joins the bit strings
+// into the single block the descriptor asks for.  One descriptor then runs at 16 SMs' speed instead of one.
+constexpr uint32_t kPiece = 65536;
+uint32_t split_min()
+{
+	static uint32_t v = [] { const char *e = getenv("NXGPU_JOB_SPLIT_MIN"); return e ? (uint32_t)strtoul(e, nullptr, 0) : 131072u; }();   // developer switch
+	return v;
+}
 } // namespace
 
 // Runs n descriptors as ONE batch: one upload of all sources, one deflate launch for every compress
@@ -233,7 +246,9 @@ void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 			if (j.hist > j.src_total) { complete(j.crb, 3, CE_TERMINATE, 0); continue; }   // history length error
 			j.n_new = (uint32_t)(j.src_total - j.hist);
 			j.kind = JobState::COMP;
-			j.idx = nd++;
+			j.np = j.n_new >= split_min() ? (j.n_new + kPiece - 1) / kPiece : 1;
+			j.idx = nd;
+			nd += j.np;
 		} else {
 			const bool resume = (j.fc & 0x04) != 0;
 			j.hist = resume ? ((w8 >> 20) & 0xfff) * 16 : 0;
@@ -276,29 +291,42 @@ void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 	for (size_t i = 0; i < n; i++) {
 		JobState &j = js[i];
 		if (j.kind == JobState::COMP) {
-			DeflateJob &job = dj[j.idx];
-			memset(&job, 0, sizeof(job));
-			job.src = d_in + j.in_off + j.hist;
-			job.src_len = j.n_new;
-			job.hist_len = j.hist > 32768 ? 32768 : j.hist;
-			job.flags = NXGPU_F_NO_JOINER | (j.use_dht ? 0 : NXGPU_F_FIXED);
+			uint32_t dhtlen = 0;
+			bool dht_ok = true;
 			if (j.use_dht) {
-				const uint32_t dhtlen = be32(j.cpb + 12) & 0xfff;
+				dhtlen = be32(j.cpb + 12) & 0xfff;
 				uint8_t *blob = h_dht + i * 1024;
 				memset(blob, 0, 320 + 288);
-				if (dhtlen < 42 || dhtlen > 288 * 8 || !dht_to_lengths(j.cpb + NXGPU_CPB_IN_DHT - NXGPU_CPB, dhtlen, blob)) {
-					complete(j.crb, 68 /* invalid DHT */, CE_TERMINATE, 0);
-					j.kind = JobState::DONE;
+				dht_ok = dhtlen >= 42 && dhtlen <= 288 * 8 && dht_to_lengths(j.cpb + NXGPU_CPB_IN_DHT - NXGPU_CPB, dhtlen, blob);
+				if (dht_ok) {
+					memcpy(blob + 320, j.cpb + NXGPU_CPB_IN_DHT - NXGPU_CPB, (dhtlen + 7) / 8);
+					any_dht = true;
+				}
+			}
+			for (size_t p = 0; p < j.np; p++) {
+				DeflateJob &job = dj[j.idx + p];
+				memset(&job, 0, sizeof(job));
+				const uint32_t off = (uint32_t)p * kPiece;
+				job.src = d_in + j.in_off + j.hist + off;
+				job.src_len = j.np == 1 ? j.n_new : (j.n_new - off < kPiece ? j.n_new - off : kPiece);
+				const uint64_t before = (uint64_t)j.hist + off;
+				job.hist_len = before > 32768 ? 32768 : (uint32_t)before;
+				job.flags = NXGPU_F_NO_JOINER | (j.use_dht ? 0 : NXGPU_F_FIXED) | (p > 0 ? NXGPU_F_NO_HEADER : 0) | (p + 1 < j.np ? NXGPU_F_NO_EOB : 0);
+				if (!dht_ok) {
 					job.src_len = 0; job.flags |= NXGPU_F_FIXED;       // keeps its slot in the launch, result ignored
 					continue;
 				}
-				memcpy(blob + 320, j.cpb + NXGPU_CPB_IN_DHT - NXGPU_CPB, (dhtlen + 7) / 8);
-				job.dht = d_dht + i * 1024;
-				job.dht_bits = dhtlen;
-				any_dht = true;
+				if (j.use_dht) {
+					job.dht = d_dht + i * 1024;
+					job.dht_bits = dhtlen;
+				}
+				if (j.count)
+					job.lzcount = static_cast<uint32_t *>(c->d_lz.p) + (j.idx + p) * 316;
 			}
-			if (j.count)
-				job.lzcount = static_cast<uint32_t *>(c->d_lz.p) + j.idx * 316;
+			if (!dht_ok) {
+				complete(j.crb, 68 /* invalid DHT */, CE_TERMINATE, 0);
+				j.kind = JobState::DONE;
+			}
 		} else if (j.kind == JobState::DECOMP) {
 			const uint32_t w8 = be32(j.cpb + 8), w12 = be32(j.cpb + 12);
 			const bool resume = (j.fc & 0x04) != 0;
@@ -360,22 +388,40 @@ void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 	if (any_count && cudaMemcpyAsync(lz, c->d_lz.p, nd * 316 * 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { fail_all(); return; }
 	if (cudaStreamSynchronize(c->stream) != cudaSuccess) { fail_all(); return; }
 
-	// ---- per-job verdict; checksums and output bytes of the good ones ----
+	// ---- per-job verdict; pieces of cut descriptors are joined on the device ----
 	std::vector<nxgpu_cksum_item> items;
+	std::vector<BitPiece> pieces;
+	std::vector<BitGroup> groups;
+	size_t cat_total = 0;
 	for (size_t i = 0; i < n; i++) {
 		JobState &j = js[i];
 		if (j.kind == JobState::WRAP) {
 			j.ok = true; j.out_len = (uint32_t)j.src_total;
-			j.ck = items.size();
-			items.push_back({ d_in + j.in_off, j.src_total, 0, 1 });
 		} else if (j.kind == JobState::COMP) {
-			const DeflateOut &o = dout[j.idx];
-			if (o.rc == 66) { complete(j.crb, 66, CE_TERMINATE, 0); continue; }            // a needed symbol has no code
-			if (o.rc != 0 || o.out_len > j.dst_total) { complete(j.crb, 13, 0, 0); continue; }  // ERR_NX_TARGET_SPACE: caller halves the input
-			j.ok = true; j.out_len = o.out_len;
-			j.ck = items.size();
-			items.push_back({ dj[j.idx].src, j.n_new, j.crc_seed, j.adler_seed });
-			if (o.out_len && cudaMemcpyAsync(ho + j.host_off, dj[j.idx].out, o.out_len, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { fail_all(); return; }
+			bool missing = false, failed = false;
+			uint64_t bits = 0;
+			for (size_t p = 0; p < j.np; p++) {
+				const DeflateOut &o = dout[j.idx + p];
+				if (o.rc == 66) missing = true;
+				else if (o.rc != 0) failed = true;
+				else if (o.out_len) bits += (uint64_t)(o.out_len - 1) * 8 + (o.tebc ? o.tebc : 8);
+			}
+			if (missing) { complete(j.crb, 66, CE_TERMINATE, 0); continue; }                    // a needed symbol has no code
+			if (failed || (bits + 7) / 8 > j.dst_total) { complete(j.crb, 13, 0, 0); continue; }  // ERR_NX_TARGET_SPACE: caller halves the input
+			j.ok = true; j.out_bits = bits; j.out_len = (uint32_t)((bits + 7) / 8);
+			if (j.np > 1) {
+				j.cat_off = cat_total;
+				cat_total += align16(j.out_len + 32);
+				BitGroup g = { nullptr, bits, (uint32_t)pieces.size(), (uint32_t)j.np };
+				uint64_t at = 0;
+				for (size_t p = 0; p < j.np; p++) {
+					const DeflateOut &o = dout[j.idx + p];
+					const uint64_t nb = o.out_len ? (uint64_t)(o.out_len - 1) * 8 + (o.tebc ? o.tebc : 8) : 0;
+					pieces.push_back({ dj[j.idx + p].out, nb, at });
+					at += nb;
+				}
+				groups.push_back(g);
+			}
 		} else if (j.kind == JobState::DECOMP) {
 			const InflateOut &o = iout[j.idx];
 			if (o.rc != 0) {
@@ -384,7 +430,38 @@ void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 				continue;
 			}
 			j.ok = true; j.out_len = o.out_len;
-			j.ck = items.size();
+		}
+	}
+	if (!groups.empty()) {
+		const size_t pb = pieces.size() * sizeof(BitPiece), gb = groups.size() * sizeof(BitGroup);
+		if (c->d_cat.reserve(cat_total + 64) || c->d_catdesc.reserve(pb + gb + 64) || c->h_cat.reserve(pb + gb + 64)) { fail_all(); return; }
+		size_t gi = 0;
+		for (size_t i = 0; i < n; i++)
+			if (js[i].ok && js[i].kind == JobState::COMP && js[i].np > 1)
+				groups[gi++].dst = static_cast<uint8_t *>(c->d_cat.p) + js[i].cat_off;
+		uint8_t *hc = static_cast<uint8_t *>(c->h_cat.p);
+		memcpy(hc, pieces.data(), pb);
+		memcpy(hc + align16(pb), groups.data(), gb);
+		if (cudaMemcpyAsync(c->d_catdesc.p, hc, align16(pb) + gb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { fail_all(); return; }
+		const uint8_t *dd = static_cast<const uint8_t *>(c->d_catdesc.p);
+		if (launch_bitconcat(reinterpret_cast<const BitPiece *>(dd), reinterpret_cast<const BitGroup *>(dd + align16(pb)),
+				     (uint32_t)groups.size(), c->stream) != cudaSuccess) { fail_all(); return; }
+		c->launches++;
+	}
+	// ---- checksums and output bytes of the good ones ----
+	for (size_t i = 0; i < n; i++) {
+		JobState &j = js[i];
+		if (!j.ok)
+			continue;
+		j.ck = items.size();
+		if (j.kind == JobState::WRAP) {
+			items.push_back({ d_in + j.in_off, j.src_total, 0, 1 });
+		} else if (j.kind == JobState::COMP) {
+			items.push_back({ dj[j.idx].src, j.n_new, j.crc_seed, j.adler_seed });
+			const uint8_t *from = j.np > 1 ? static_cast<const uint8_t *>(c->d_cat.p) + j.cat_off : dj[j.idx].out;
+			if (j.out_len && cudaMemcpyAsync(ho + j.host_off, from, j.out_len, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { fail_all(); return; }
+		} else {
+			const InflateOut &o = iout[j.idx];
 			items.push_back({ ij[j.idx].dst, o.out_len, j.crc_seed, j.adler_seed });
 			if (o.out_len && cudaMemcpyAsync(ho + j.host_off, ij[j.idx].dst, o.out_len, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { fail_all(); return; }
 			if ((o.sfbt & 0xe) == 0xc &&
@@ -412,22 +489,26 @@ void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 			put_be32(cpb + NXGPU_CPB_OUT_SPBC_COMP - NXGPU_CPB, (uint32_t)j.src_total);
 			complete(j.crb, 0, 0, (uint32_t)j.src_total);
 		} else if (j.kind == JobState::COMP) {
-			const DeflateOut &o = dout[j.idx];
-			scatter(j.dst, ho + j.host_off, o.out_len);
-			put_be32(cpb + NXGPU_CPB_OUT_TEBC - NXGPU_CPB, (o.tebc & 7) << 16);
+			scatter(j.dst, ho + j.host_off, j.out_len);
+			put_be32(cpb + NXGPU_CPB_OUT_TEBC - NXGPU_CPB, (uint32_t)(j.out_bits & 7) << 16);
 			if (j.count) {
 				// 286 + 30 symbol counts, big-endian like every other field (lib/nx_dht.c:187-199 detects the
-				// byte order by looking at the end-of-block count, which is always 1)
+				// byte order by looking at the end-of-block count, which is always 1); pieces add up
 				uint8_t *p = cpb + NXGPU_CPB_OUT_LZCOUNT - NXGPU_CPB;
-				const uint32_t *l = lz + j.idx * 316;
-				for (int k = 0; k < 316; k++)
-					put_be32(p + 4 * k, l[k] > 0xffffff ? 0xffffff : l[k]);
+				for (int k = 0; k < 316; k++) {
+					uint64_t v = 0;
+					for (size_t q = 0; q < j.np; q++)
+						v += lz[(j.idx + q) * 316 + k];
+					if (k == 256)
+						v = 1;
+					put_be32(p + 4 * k, v > 0xffffff ? 0xffffff : (uint32_t)v);
+				}
 				put_be32(cpb + NXGPU_CPB_OUT_SPBC_COMP_WITH_COUNT - NXGPU_CPB, (uint32_t)j.src_total);
 			} else {
 				put_be32(cpb + NXGPU_CPB_OUT_SPBC_COMP - NXGPU_CPB, (uint32_t)j.src_total);
 			}
 			// manual Table 6-8: the target came out larger than the source
-			complete(j.crb, o.out_len > j.src_total ? 64 : 0, 0, o.out_len);
+			complete(j.crb, j.out_len > j.src_total ? 64 : 0, 0, j.out_len);
 		} else {
 			const InflateOut &o = iout[j.idx];
 			scatter(j.dst, ho + j.host_off, o.out_len);

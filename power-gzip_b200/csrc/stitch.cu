@@ -105,7 +105,54 @@ __global__ void finish_stream_kernel(const uint64_t *__restrict__ offsets, uint3
 	*d_total = p;
 }
 
+// Joins the bit strings of the pieces of one deflate block (a large nxu_run_job descriptor is cut into
+// pieces that separate CTAs compress with the same table, nxgpu_job.cu) into one: piece i holds `nbits`
+// valid bits in a 16-byte aligned slot and starts at bit `dst_bit` of the group's output.  One CTA per
+// group; every thread assembles whole output words (no atomics, coalesced stores).
+__global__ void __launch_bounds__(1024)
+bitconcat_kernel(const BitPiece *__restrict__ pieces, const BitGroup *__restrict__ groups)
+{
+	const BitGroup G = groups[blockIdx.x];
+	const BitPiece *P = pieces + G.first_piece;
+	uint32_t *out32 = reinterpret_cast<uint32_t *>(G.dst);
+	const uint64_t nwords = (G.total_bits + 31) >> 5;
+	for (uint64_t j = threadIdx.x; j < nwords; j += blockDim.x) {
+		const uint64_t bit0 = j << 5;
+		// the piece holding bit0: pieces are few (<= 64) and in order
+		uint32_t lo = 0, hi = G.n_pieces;
+		while (hi - lo > 1) {
+			const uint32_t mid = (lo + hi) >> 1;
+			if (P[mid].dst_bit <= bit0) lo = mid; else hi = mid;
+		}
+		uint32_t i = lo, word = 0, filled = 0;
+		while (filled < 32 && i < G.n_pieces) {
+			const uint64_t off = bit0 + filled - P[i].dst_bit;
+			const uint64_t avail = P[i].nbits - off;
+			if (avail == 0) { i++; continue; }
+			const uint32_t take = (uint32_t)(avail < 32 - filled ? avail : 32 - filled);
+			const uint32_t *s32 = reinterpret_cast<const uint32_t *>(P[i].src);
+			const uint32_t w0 = s32[off >> 5], w1 = s32[(off >> 5) + 1];      // slots are padded: reading one word on is safe
+			uint32_t v = __funnelshift_r(w0, w1, (uint32_t)(off & 31));
+			if (take < 32)
+				v &= (1u << take) - 1;
+			word |= v << filled;
+			filled += take;
+			if (take == avail)
+				i++;
+		}
+		out32[j] = word;
+	}
+}
+
 } // namespace
+
+cudaError_t launch_bitconcat(const BitPiece *pieces, const BitGroup *groups, uint32_t n_groups, cudaStream_t s)
+{
+	if (n_groups == 0)
+		return cudaSuccess;
+	bitconcat_kernel<<<n_groups, 1024, 0, s>>>(pieces, groups);
+	return cudaGetLastError();
+}
 
 cudaError_t launch_scan_offsets(const DeflateOut *outs, uint32_t n, uint64_t base, uint64_t *offsets, cudaStream_t s)
 {

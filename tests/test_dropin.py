@@ -403,3 +403,46 @@ def test_dhtgen_against_the_reference_tables(engines, pg, alice):
             j = run(Job(0x02, [text], 300000, rem_or_dhtlen=bits, dht=dht))
             assert j.cc() == 0, j.cc()
             assert zlib.decompress(_decode_one_block(0x02, j), -15) == text
+
+
+@pytest.mark.gpu
+def test_large_compress_descriptors_are_cut_into_pieces(engines, pg, alice):
+    """A compress descriptor of 128 KiB or more is compressed by several CTAs (64 KiB pieces, same table, each
+    primed with the 32 KiB in front of it) and the bit strings are joined into the ONE block the descriptor asks
+    for: it must decode to the source for FHT / DHT / COUNT / RESUME, with spbc, checksums, lzcounts and the
+    completion code as for a single piece; a table lacking a needed symbol still gives CC=66."""
+    gpu, cpu = engines
+    data = pg.makedata(4, 20, alice)[:1000003] + alice[:70001]            # 1,070,004 bytes: 17 pieces, ragged tail
+    hist = alice[100000:100000 + 32768]
+    for fc in (0x00, 0x04):                                                   # FHT, FHT + COUNT
+        j = gpu(Job(fc, [data], 2 * len(data)))
+        assert j.cc() == 0 and j.spbc_comp(fc == 0x04) == len(data)
+        assert zlib.decompress(_decode_one_block(fc, j), -15) == data
+        assert j.crc() == zlib.crc32(data) and j.adler() == zlib.adler32(data)
+        if fc == 0x04:
+            lz = [int.from_bytes(j.get(256 + 400 + 4 * i, 4), "big") for i in range(316)]
+            assert lz[256] == 1 and sum(lz[257:286]) == sum(lz[286:316]) > 0      # one distance per length
+            # the histogram is the histogram of the emitted block: a table made from it costs what the block costs
+            with pg.Engine(0) as eng:
+                dht, bits = eng.dhtgen([max(1, x) for x in lz[:286]], [max(1, x) for x in lz[286:]])
+            jd = gpu(Job(0x02, [data], 2 * len(data), rem_or_dhtlen=bits, dht=dht))
+            assert jd.cc() == 0 and zlib.decompress(_decode_one_block(0x02, jd), -15) == data
+            assert jd.tpbc() < j.tpbc()                                       # dynamic beats fixed on this text
+            jc = cpu(Job(0x02, [data[:300000]], 600000, rem_or_dhtlen=bits, dht=dht))
+            assert jc.cc() == 0                                               # the CPU engine accepts the same table
+    # resume with history in front: pieces further in use the source itself as their window
+    j2 = gpu(Job(0x08, [hist, data], 2 * len(data), histlen_qw=len(hist) // 16, crc=zlib.crc32(b"abc"), adler=zlib.adler32(b"abc")))
+    assert j2.cc() == 0 and j2.spbc_comp(False) == len(hist) + len(data)
+    assert zlib.decompressobj(-15, zdict=hist).decompress(_decode_one_block(0x08, j2)) == data
+    assert j2.crc() == zlib.crc32(data, zlib.crc32(b"abc"))
+    # target too small: CC=13, nothing written past the target
+    j3 = gpu(Job(0x00, [data], 50000))
+    assert j3.cc() == 13
+    # a table without codes for bytes that occur: CC=66 like a single piece
+    with pg.Engine(0) as eng:
+        dht, bits = eng.dhtgen([1 if 97 <= s <= 122 or s >= 256 else 0 for s in range(286)], [1] * 30)
+    j4 = gpu(Job(0x02, [data], 2 * len(data), rem_or_dhtlen=bits, dht=dht))
+    assert j4.cc() == 66
+    # through the reference's own host code: deflate() of a multi-MiB buffer issues such descriptors
+    rep = _drive(REF_GPU, 22) if os.path.exists(REF_GPU) else None
+    assert rep is None or rep["cases"]["text"]["compress2"] > 0

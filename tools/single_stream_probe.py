@@ -25,3 +25,24 @@ for level in (1, 6):
         res = eng.deflate_stream_device(ds.ptr, len(one), dd.ptr, 2 << 20, level=level, wrap=pg.WRAP_RAW, chunk=1 << 20)
         kms, _ = eng.kernel_time("deflate")
     print(f"one 1 MiB deflate job on one CTA, level {level}: {kms:.2f} ms = {len(one)/kms/1e3:.1f} MB/s")
+# one compress descriptor (nxu_run_job, host buffers, wall clock): cut into 64 KiB pieces above 128 KiB
+import ctypes as C
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from test_dropin import Job
+lib = pg.load_library()
+
+
+class Dev(C.Structure):
+    _fields_ = [("i", C.c_int * 8), ("paste_addr", C.c_void_p), ("fd", C.c_int), ("function", C.c_int), ("pad", C.c_char * 256)]
+
+
+dev = Dev()
+assert lib.nx_function_begin(2, -1, C.byref(dev)) == 0
+for size in (65536, 131072, 1 << 20):
+    best = 1e9
+    for it in range(5):
+        j = Job(0x00, [data[:size]], 2 * size)
+        t0 = time.perf_counter()
+        assert lib.nxu_run_job(j.addr, C.byref(dev)) == 0
+        best = min(best, time.perf_counter() - t0)
+    print(f"one FHT compress descriptor of {size >> 10} KiB through nxu_run_job (host to host): {best * 1e3:.2f} ms = {size / best / 1e6:.0f} MB/s, cc {j.cc()}, {j.tpbc()} bytes out")
