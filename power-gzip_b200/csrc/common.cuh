@@ -126,12 +126,24 @@ __host__ __device__ inline LevelParams level_params(int level)
 #define NXGPU_CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { nxgpu::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); return NXGPU_E_NODEV; } } while (0)
 void set_error(const char *fmt, ...);
 
+// Stitching fused into the deflate kernel (nxgpu_deflate_stream): a chunk's CTA learns where its bytes go from
+// its predecessor (chain[k] = end offset of chunk k + 1, 0 = not known yet), publishes its own end and copies its
+// slot there itself — to device memory or straight into pinned host memory, so the device-to-host transfer of
+// the compressed stream overlaps the compression of later chunks.
+struct StreamOut {
+	uint8_t *dst = nullptr;               // final stream (device pointer, may alias pinned host memory); nullptr = off
+	uint64_t cap = 0;
+	uint64_t base = 0;                    // bytes of container header in front of chunk 0
+	uint64_t *offsets = nullptr;          // n + 1 entries: start of every chunk, end of the last
+	unsigned long long *chain = nullptr;  // n entries, zeroed before the launch
+};
+
 // kernel launchers (defined in the .cu files)
 size_t deflate_smem_bytes();
 size_t deflate_scratch_words(uint32_t tok_stride);   // per-CTA token scratch (u32 words)
 cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_jobs, int level,
 			   uint32_t *tok_scratch, uint32_t tok_stride, int grid, cudaStream_t s,
-			   uint32_t *job_counter, const uint32_t *ready, uint32_t jobs_per_flag);
+			   uint32_t *job_counter, const uint32_t *ready, uint32_t jobs_per_flag, const StreamOut *so = nullptr);
 cudaError_t launch_dhtgen(const uint32_t *counts, uint32_t n, uint8_t *dht_out, uint32_t *dht_bits, cudaStream_t s);
 cudaError_t launch_inflate(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s);
 // checksum.cu

@@ -81,7 +81,7 @@ struct nxgpu_ctx {
 	uint32_t jobs_per_flag = 0;
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
 	uint64_t launches = 0;
-	DevBuf d_jobs, d_outs, d_tok, d_slots, d_ranges, d_parts, d_rs, d_seeds, d_cks, d_in, d_out, d_offsets, d_misc, d_dst_ptrs, d_dht, d_lz, d_ctr, d_flags, d_ijobs, d_iouts, d_cat, d_catdesc;
+	DevBuf d_jobs, d_outs, d_tok, d_slots, d_ranges, d_parts, d_rs, d_seeds, d_cks, d_in, d_out, d_offsets, d_misc, d_dst_ptrs, d_dht, d_lz, d_ctr, d_flags, d_ijobs, d_iouts, d_cat, d_catdesc, d_chain;
 	PinBuf h_jobs, h_outs, h_misc, h_stage, h_ones, h_cat;
 	KernelTimer timers[3];           // 0 deflate, 1 inflate, 2 checksum
 	bool timing = true;
@@ -90,7 +90,7 @@ struct nxgpu_ctx {
 
 namespace nxgpu {
 // nxgpu_api.cu: device-resident cores of the batch calls (pointers are device pointers)
-int deflate_device(nxgpu_ctx *c, DeflateJob *jobs_h, size_t n, int level, bool want_cksum);
+int deflate_device(nxgpu_ctx *c, DeflateJob *jobs_h, size_t n, int level, bool want_cksum, const StreamOut *so = nullptr);
 int checksum_device(nxgpu_ctx *c, const nxgpu_cksum_item *items, size_t n, int which);
 void timer_begin(nxgpu_ctx *c, int fam);
 void timer_end(nxgpu_ctx *c, int fam);

@@ -1030,10 +1030,54 @@ constexpr int kMeta = 8;     // per sub-block: tokens, end position, tokens drop
 enum { M_CNT = 0, M_END = 1, M_SKIP = 2, M_NEW = 3, M_OFF = 4, M_TAILN = 5, M_TAIL0 = 6, M_TAIL1 = 7 };
 __host__ __device__ inline size_t scratch_words(uint32_t tok_stride) { return 2 * (size_t)tok_stride + kMeta * (size_t)scratch_nsub(tok_stride) + 32 * (size_t)(kSub + 32); }
 
+// ---- fused stitch (StreamOut): wait for the predecessor's end offset, publish ours, copy the slot there ----
+__device__ void stream_out(Smem &S, const StreamOut &so, const DeflateJob &J, uint32_t job, uint32_t n_jobs, uint32_t len)
+{
+	if (threadIdx.x == 0) {
+		unsigned long long start = so.base;
+		if (job > 0) {
+			volatile unsigned long long *prev = so.chain + (job - 1);
+			unsigned long long v;
+			while ((v = *prev) == 0)
+				__nanosleep(200);                 // chunk job-1 is on another SM and, like us, only waits on lower chunks
+			start = v - 1;
+		}
+		*reinterpret_cast<volatile unsigned long long *>(so.chain + job) = start + len + 1;
+		so.offsets[job] = start;
+		if (job + 1 == n_jobs)
+			so.offsets[n_jobs] = start + len;
+		S.misc[4] = (uint32_t)start;
+		S.misc[5] = (uint32_t)(start >> 32);
+	}
+	__syncthreads();
+	const uint64_t off = (uint64_t)S.misc[4] | (uint64_t)S.misc[5] << 32;
+	if (len == 0 || off + len > so.cap)
+		return;
+	const uint8_t *src = J.out;                       // 16-byte aligned slot
+	uint8_t *d = so.dst + off;
+	// head bytes until d is 16-byte aligned, 16-byte vectors assembled from the aligned source, tail bytes
+	const uint32_t head = min(len, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15));
+	if (threadIdx.x < head)
+		d[threadIdx.x] = src[threadIdx.x];
+	const uint32_t nvec = (len - head) >> 4;
+	const uint32_t sh = (head & 3) * 8;
+	const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src) + (head >> 2);
+	uint4 *d128 = reinterpret_cast<uint4 *>(d + head);
+	for (uint32_t v = threadIdx.x; v < nvec; v += kThreads) {
+		const uint32_t *p = s32 + 4 * v;
+		const uint32_t a = p[0], b = p[1], c = p[2], e = p[3], f = sh ? p[4] : 0;
+		d128[v] = sh ? make_uint4(__funnelshift_r(a, b, sh), __funnelshift_r(b, c, sh), __funnelshift_r(c, e, sh), __funnelshift_r(e, f, sh))
+			     : make_uint4(a, b, c, e);
+	}
+	const uint32_t done = head + nvec * 16;
+	if (threadIdx.x < len - done)
+		d[done + threadIdx.x] = src[done + threadIdx.x];
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ outs, uint32_t n_jobs,
 	       int depth, int lazy, int nice, uint32_t *tok_scratch, uint32_t tok_stride, uint32_t parser_mask,
-	       uint32_t *job_counter, const volatile uint32_t *ready, uint32_t jobs_per_flag, int d1)
+	       uint32_t *job_counter, const volatile uint32_t *ready, uint32_t jobs_per_flag, int d1, StreamOut so)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -1312,6 +1356,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 			if (any_missing) {
 				if (threadIdx.x == 0) { DeflateOut o = {}; o.rc = 66; o.n_tokens = ntok; outs[job] = o; }
 				__syncthreads();
+				if (so.dst) stream_out(S, so, J, job, n_jobs, 0);
 				continue;
 			}
 		} else if (force_fixed) {
@@ -1343,6 +1388,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 		if (total_bytes > J.out_cap) {
 			if (threadIdx.x == 0) { DeflateOut o = {}; o.rc = NXGPU_E_BUF; o.out_len = total_bytes; o.n_tokens = ntok; outs[job] = o; }
 			__syncthreads();
+			if (so.dst) stream_out(S, so, J, job, n_jobs, 0);
 			continue;
 		}
 
@@ -1393,6 +1439,10 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 			outs[job] = o;
 		}
 		__syncthreads();
+		if (so.dst) {
+			stream_out(S, so, J, job, n_jobs, total_bytes);
+			__syncthreads();
+		}
 	}
 }
 
@@ -1469,7 +1519,7 @@ size_t deflate_scratch_words(uint32_t tok_stride) { return scratch_words(tok_str
 
 cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_jobs, int level,
 			   uint32_t *tok_scratch, uint32_t tok_stride, int grid, cudaStream_t s,
-			   uint32_t *job_counter, const uint32_t *ready, uint32_t jobs_per_flag)
+			   uint32_t *job_counter, const uint32_t *ready, uint32_t jobs_per_flag, const StreamOut *so)
 {
 	static bool configured = false;
 	if (!configured) {
@@ -1501,7 +1551,7 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 	if (me != cudaSuccess)
 		return me;
 	deflate_kernel<<<grid, kThreads, sizeof(Smem), s>>>(jobs, outs, n_jobs, lp.depth, lp.lazy, lp.nice, tok_scratch, tok_stride, parser_mask,
-							    job_counter, ready, jobs_per_flag ? jobs_per_flag : 1, lp.d1);
+							    job_counter, ready, jobs_per_flag ? jobs_per_flag : 1, lp.d1, so ? *so : StreamOut());
 	cudaError_t e = cudaGetLastError();
 	if (dbg) {
 		std::vector<unsigned long long> h((size_t)grid * 8);

@@ -152,7 +152,7 @@ void nxgpu_close(nxgpu_ctx *c)
 	cudaSetDevice(c->dev);
 	cudaStreamSynchronize(c->stream);
 	DevBuf *db[] = { &c->d_jobs, &c->d_outs, &c->d_tok, &c->d_slots, &c->d_ranges, &c->d_parts, &c->d_rs, &c->d_seeds,
-			 &c->d_cks, &c->d_in, &c->d_out, &c->d_offsets, &c->d_misc, &c->d_dst_ptrs, &c->d_dht, &c->d_lz, &c->d_ctr, &c->d_flags, &c->d_ijobs, &c->d_iouts, &c->d_cat, &c->d_catdesc };
+			 &c->d_cks, &c->d_in, &c->d_out, &c->d_offsets, &c->d_misc, &c->d_dst_ptrs, &c->d_dht, &c->d_lz, &c->d_ctr, &c->d_flags, &c->d_ijobs, &c->d_iouts, &c->d_cat, &c->d_catdesc, &c->d_chain };
 	for (DevBuf *b : db) b->release();
 	PinBuf *pb[] = { &c->h_jobs, &c->h_outs, &c->h_misc, &c->h_stage, &c->h_ones, &c->h_cat };
 	for (PinBuf *b : pb) b->release();
@@ -383,7 +383,7 @@ int nxgpu_adler32(nxgpu_ctx *c, uint32_t seed, const void *src, uint64_t len, in
 
 // Core: all pointers in `jobs_h` are device pointers except `out`, which this routine assigns to
 // private 16-byte aligned slots.  Leaves DeflateOut[n] in d_outs and per-item crc/adler in d_cks.
-extern "C++" int nxgpu::deflate_device(nxgpu_ctx *c, DeflateJob *jobs_h, size_t n, int level, bool want_cksum)
+extern "C++" int nxgpu::deflate_device(nxgpu_ctx *c, DeflateJob *jobs_h, size_t n, int level, bool want_cksum, const StreamOut *so)
 {
 	int rc;
 	if (level <= 0) level = 6;       // lib/nx_deflate.c:655-658 maps level 0 to 6 as well
@@ -419,7 +419,7 @@ extern "C++" int nxgpu::deflate_device(nxgpu_ctx *c, DeflateJob *jobs_h, size_t 
 	timer_begin(c, 0);
 	NXGPU_CUDA_OK(launch_deflate(static_cast<const DeflateJob *>(c->d_jobs.p), static_cast<DeflateOut *>(c->d_outs.p),
 				     (uint32_t)n, level, static_cast<uint32_t *>(c->d_tok.p), tok_stride, grid, c->stream,
-				     static_cast<uint32_t *>(c->d_ctr.p), c->ready_flags, c->jobs_per_flag));
+				     static_cast<uint32_t *>(c->d_ctr.p), c->ready_flags, c->jobs_per_flag, so));
 	timer_end(c, 0);
 	if (want_cksum) {
 		std::vector<nxgpu_cksum_item> it(n);
@@ -575,16 +575,6 @@ int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *
 		jh[i].hist_len = independent ? 0 : (uint32_t)(o < 32768 ? o : 32768);
 		jh[i].flags = (i + 1 == n && !cont) ? NXGPU_F_FINAL : 0;
 	}
-	rc = deflate_device(c, jh, n, level, false);
-	if (c->ready_flags) {
-		// everything behind the kernel (checksums, a later call's uploads) must see the whole input
-		c->ready_flags = nullptr;
-		cudaStreamWaitEvent(c->stream, c->ev_copy, 0);
-	}
-	if (rc) return rc;
-	// whole-stream checksums: chunks are the ranges of one job
-	nxgpu_cksum_item whole = { dsrc, src_len, 0, 1 };
-	if ((rc = checksum_device(c, &whole, 1, 3))) return rc;
 	// header
 	uint64_t hdr = 0; int hdr_len = 0;
 	if (wrap == NXGPU_WRAP_GZIP) {
@@ -598,22 +588,56 @@ int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *
 		hdr = (h >> 8) | ((h & 0xff) << 8); hdr_len = 2;
 	}
 	const uint64_t hdr_total = wrap == NXGPU_WRAP_GZIP ? 10 : hdr_len;
-	if (dst_cap < hdr_total) return NXGPU_E_BUF;
+	if (dst_cap < hdr_total) { c->ready_flags = nullptr; return NXGPU_E_BUF; }
+	// the stitch is fused into the kernel: every chunk's CTA copies its bytes to their final place as soon as its
+	// predecessor has published where that is.  When the caller's host buffer is pinned (cudaHostAlloc /
+	// cudaHostRegister) the kernel writes straight into it, so the device-to-host transfer of the compressed stream
+	// overlaps the compression of later chunks.
+	static const bool fused = !(getenv("NXGPU_FUSED_STITCH") && atoi(getenv("NXGPU_FUSED_STITCH")) == 0);   // developer switch
+	bool zero_copy = false;
+	if (mem == NXGPU_MEM_HOST && fused) {
+		cudaPointerAttributes pa;
+		if (cudaPointerGetAttributes(&pa, dst) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
+			ddst = static_cast<uint8_t *>(pa.devicePointer);
+			zero_copy = true;
+		} else {
+			cudaGetLastError();
+		}
+	}
+	if ((rc = c->d_offsets.reserve((n + 2) * 8))) { c->ready_flags = nullptr; return rc; }
+	if ((rc = c->d_chain.reserve((n + 1) * 8))) { c->ready_flags = nullptr; return rc; }
+	uint64_t *d_off = static_cast<uint64_t *>(c->d_offsets.p);
+	StreamOut so;
+	if (fused) {
+		NXGPU_CUDA_OK(cudaMemsetAsync(c->d_chain.p, 0, (n + 1) * 8, c->stream));
+		so.dst = ddst; so.cap = dst_cap; so.base = hdr_total; so.offsets = d_off;
+		so.chain = static_cast<unsigned long long *>(c->d_chain.p);
+	}
+	rc = deflate_device(c, jh, n, level, false, fused ? &so : nullptr);
+	if (c->ready_flags) {
+		// everything behind the kernel (checksums, a later call's uploads) must see the whole input
+		c->ready_flags = nullptr;
+		cudaStreamWaitEvent(c->stream, c->ev_copy, 0);
+	}
+	if (rc) return rc;
+	// whole-stream checksums: chunks are the ranges of one job
+	nxgpu_cksum_item whole = { dsrc, src_len, 0, 1 };
+	if ((rc = checksum_device(c, &whole, 1, 3))) return rc;
 	if (hdr_len) {
 		write_bytes_kernel<<<1, 1, 0, c->stream>>>(ddst, hdr, hdr_len);
 		if (wrap == NXGPU_WRAP_GZIP)
 			write_bytes_kernel<<<1, 1, 0, c->stream>>>(ddst + 8, 0x0300ull, 2);
 		c->launches += 1;
 	}
-	if ((rc = c->d_offsets.reserve((n + 2) * 8))) return rc;
-	uint64_t *d_off = static_cast<uint64_t *>(c->d_offsets.p);
 	const DeflateJob *dj = static_cast<const DeflateJob *>(c->d_jobs.p);
 	const DeflateOut *dout = static_cast<const DeflateOut *>(c->d_outs.p);
-	NXGPU_CUDA_OK(launch_scan_offsets(dout, (uint32_t)n, hdr_total, d_off, c->stream));
-	NXGPU_CUDA_OK(launch_gather(dj, dout, d_off, (uint32_t)n, ddst, dst_cap, c->stream));
+	if (!fused) {
+		NXGPU_CUDA_OK(launch_scan_offsets(dout, (uint32_t)n, hdr_total, d_off, c->stream));
+		NXGPU_CUDA_OK(launch_gather(dj, dout, d_off, (uint32_t)n, ddst, dst_cap, c->stream));
+	}
 	const uint32_t *d_crc = static_cast<const uint32_t *>(c->d_cks.p);
 	NXGPU_CUDA_OK(launch_finish_stream(dout, d_off, (uint32_t)n, ddst, dst_cap, wrap, d_crc, d_crc + 1, src_len, d_off + n + 1, c->stream));
-	c->launches += 3;
+	c->launches += fused ? 1 : 3;
 	// results back
 	if ((rc = c->h_outs.reserve(n * sizeof(DeflateOut) + (n + 2) * 8 + 16))) return rc;
 	DeflateOut *oh = static_cast<DeflateOut *>(c->h_outs.p);
@@ -631,7 +655,7 @@ int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *
 	const uint64_t total = offh[n + 1];
 	const uint64_t need = offh[n] + (wrap == NXGPU_WRAP_GZIP ? 8 : wrap == NXGPU_WRAP_ZLIB ? 4 : 0);
 	if (need > dst_cap) { set_error("output needs %llu bytes, capacity %llu", (unsigned long long)need, (unsigned long long)dst_cap); return NXGPU_E_BUF; }
-	if (mem == NXGPU_MEM_HOST) {
+	if (mem == NXGPU_MEM_HOST && !zero_copy) {
 		NXGPU_CUDA_OK(cudaMemcpyAsync(dst, ddst, total, cudaMemcpyDeviceToHost, c->stream));
 		NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
 	}
