@@ -189,11 +189,18 @@ struct JobState {
 // the caller's DHT, so no table has to be agreed on): piece 0 carries the block header, the last one the
 // end-of-block, each is primed with the 32 KiB in front of it, and bitconcat_kernel joins the bit strings
 // into the single block the descriptor asks for.  One descriptor then runs at 16 SMs' speed instead of one.
-constexpr uint32_t kPiece = 65536;
-uint32_t split_min()
+// The piece size follows the load: the pieces of one batch should fill the GPU without drowning in per-piece
+// fixed cost — total compress bytes / 148 SMs, rounded up to a power of two within [8 KiB, 64 KiB].  A lone 64 KiB
+// descriptor is cut into eight pieces (0.48 -> 0.23 ms), a batch of many MiB keeps 64 KiB pieces.
+uint32_t piece_bytes(uint64_t batch_bytes)
 {
-	static uint32_t v = [] { const char *e = getenv("NXGPU_JOB_SPLIT_MIN"); return e ? (uint32_t)strtoul(e, nullptr, 0) : 131072u; }();   // developer switch
-	return v;
+	static const uint32_t forced = [] { const char *e = getenv("NXGPU_JOB_PIECE"); return e ? (uint32_t)strtoul(e, nullptr, 0) : 0u; }();   // developer switch
+	if (forced)
+		return forced;
+	uint32_t p = 8192;
+	while (p < 65536 && (uint64_t)p * kNumSMs < batch_bytes)
+		p *= 2;
+	return p;
 }
 } // namespace
 
@@ -215,6 +222,7 @@ void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 	}
 	// ---- parse ----
 	size_t in_total = 0, out_total = 0, nd = 0, ni = 0;
+	uint64_t comp_bytes = 0;
 	for (size_t i = 0; i < n; i++) {
 		JobState &j = js[i];
 		j.crb = crbs[i];
@@ -246,9 +254,7 @@ void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 			if (j.hist > j.src_total) { complete(j.crb, 3, CE_TERMINATE, 0); continue; }   // history length error
 			j.n_new = (uint32_t)(j.src_total - j.hist);
 			j.kind = JobState::COMP;
-			j.np = j.n_new >= split_min() ? (j.n_new + kPiece - 1) / kPiece : 1;
-			j.idx = nd;
-			nd += j.np;
+			comp_bytes += j.n_new;
 		} else {
 			const bool resume = (j.fc & 0x04) != 0;
 			j.hist = resume ? ((w8 >> 20) & 0xfff) * 16 : 0;
@@ -262,6 +268,15 @@ void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 		}
 		j.in_off = in_total;
 		in_total += align16(j.src_total + 48);
+	}
+	const uint32_t kPiece = piece_bytes(comp_bytes);
+	for (size_t i = 0; i < n; i++) {
+		JobState &j = js[i];
+		if (j.kind != JobState::COMP)
+			continue;
+		j.np = j.n_new >= 2 * kPiece ? (j.n_new + kPiece - 1) / kPiece : 1;
+		j.idx = nd;
+		nd += j.np;
 	}
 	if (in_total == 0 && nd == 0 && ni == 0)
 		return;

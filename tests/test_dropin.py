@@ -407,7 +407,7 @@ def test_dhtgen_against_the_reference_tables(engines, pg, alice):
 
 @pytest.mark.gpu
 def test_large_compress_descriptors_are_cut_into_pieces(engines, pg, alice):
-    """A compress descriptor of 128 KiB or more is compressed by several CTAs (64 KiB pieces, same table, each
+    """A large compress descriptor is compressed by several CTAs (pieces of 8-64 KiB, same table, each
     primed with the 32 KiB in front of it) and the bit strings are joined into the ONE block the descriptor asks
     for: it must decode to the source for FHT / DHT / COUNT / RESUME, with spbc, checksums, lzcounts and the
     completion code as for a single piece; a table lacking a needed symbol still gives CC=66."""
