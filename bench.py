@@ -472,6 +472,14 @@ def main():
                                           "note": "compress()/uncompress() of 4 KiB-1 MiB buffers from 64 threads via libnxz host code + nxu_run_job, Python harness"}
             except Exception as e:                      # noqa: BLE001 - an extra, never fatal
                 extra["zstream_storm"] = {"error": repr(e)[:200]}
+            try:
+                # samples/bench_initend.c: deflateInit2/deflateEnd and inflateInit2/inflateEnd pairs over the GPU engine
+                p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "nx_dropin_driver.py"), gpu_nxz, "initend", "1000"],
+                                   capture_output=True, text=True, timeout=300, env=env)
+                ie = json.loads(p.stdout.strip().splitlines()[-1])
+                extra["zstream_init_end"] = {k: round(v, 2) for k, v in ie.items() if k.endswith(("_us", "_ms"))}
+            except Exception as e:                      # noqa: BLE001
+                extra["zstream_init_end"] = {"error": repr(e)[:200]}
 
     if rank == 0:
         threads = os.cpu_count() or 1

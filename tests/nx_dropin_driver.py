@@ -12,6 +12,7 @@ the nx deflate must inflate with system zlib, and streams made by system zlib mu
 nx, in one shot and in small pieces.
 usage: nx_dropin_driver.py <libnxz .so> [size_log2]
        nx_dropin_driver.py <libnxz .so> stress <threads> <iterations>
+       nx_dropin_driver.py <libnxz .so> initend [pairs]
 The stress mode follows the reference's test/test_multithread_stress.c:26-120: every thread runs
 compress()/uncompress() over the same ten buffers (4 KiB .. 1 MiB of the 33-symbol alphabet of
 test/test_utils.c:22-28, srand(1)) and checks the round trip; it also reports how many descriptors
@@ -32,7 +33,7 @@ if os.environ.get("NX_DRIVER_WATCHDOG"):
     faulthandler.dump_traceback_later(int(os.environ["NX_DRIVER_WATCHDOG"]), exit=True)
 lib = C.CDLL(sys.argv[1], mode=C.RTLD_GLOBAL)
 STRESS = len(sys.argv) > 2 and sys.argv[2] == "stress"
-log2 = int(sys.argv[2]) if len(sys.argv) > 2 and not STRESS else 20
+log2 = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 20
 
 
 class ZStream(C.Structure):
@@ -182,9 +183,68 @@ def stress(n_threads, iterations):
     print(json.dumps(rep))
 
 
+def initend(n):
+    """samples/bench_initend.c: cost of deflateInit2/deflateEnd and inflateInit2/inflateEnd pairs.
+    The fifos and DHT tables are the reference's host code; the engine's share is nx_function_begin on first use."""
+    import time
+    t0 = time.perf_counter()
+    nx_compress2(b"warm up the device handle", 6)
+    first = time.perf_counter() - t0
+    out = {"first_use_ms": first * 1e3}
+    for name, init, end, args in (("deflate", lib.deflateInit2_, lib.deflateEnd, (6, 8, 31, 8, 0, VER, C.sizeof(ZStream))),
+                                  ("inflate", lib.inflateInit2_, lib.inflateEnd, (31, VER, C.sizeof(ZStream)))):
+        t0 = time.perf_counter()
+        for _ in range(n):
+            s = ZStream()
+            assert init(C.byref(s), *args) == 0
+            end(C.byref(s))
+        out[f"{name}_init_end_us"] = (time.perf_counter() - t0) / n * 1e6
+    print(json.dumps({"lib": os.path.basename(sys.argv[1]), "pairs": n, **out}))
+
+
 if STRESS:
     stress(int(sys.argv[3]), int(sys.argv[4]))
     sys.exit(0)
+if len(sys.argv) > 2 and sys.argv[2] == "initend":
+    initend(int(sys.argv[3]) if len(sys.argv) > 3 else 1000)
+    sys.exit(0)
+
+def gz_file_roundtrip(data):
+    """The reference's gz* file layer (lib/nx_gzlib.c:130-351: gzopen / gzwrite / gzread / gzclose) over the engine:
+    a file it writes must gunzip with Python, a file Python wrote must read back through it."""
+    import tempfile
+    # the nx_-prefixed entry points, as in the reference's test/test_gz.c:15-60
+    gzopen, gzwrite, gzread, gzclose = lib.nx_gzopen, lib.nx_gzwrite, lib.nx_gzread, lib.nx_gzclose
+    gzopen.restype = C.c_void_p
+    gzopen.argtypes = [C.c_char_p, C.c_char_p]
+    gzwrite.argtypes = [C.c_void_p, C.c_char_p, C.c_uint]
+    gzread.argtypes = [C.c_void_p, C.c_void_p, C.c_uint]
+    gzclose.argtypes = [C.c_void_p]
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "w.gz").encode()
+        f = gzopen(path, b"wb6")
+        assert f, "gzopen(wb6) failed"
+        for o in range(0, len(data), 50000):
+            piece = data[o:o + 50000]
+            assert gzwrite(f, piece, len(piece)) == len(piece)
+        gzclose(f)
+        assert gzip.decompress(open(path, "rb").read()) == data, "gunzip of a file written by gzwrite differs"
+        size = os.path.getsize(path)
+        path2 = os.path.join(td, "r.gz").encode()
+        with open(path2, "wb") as fh:
+            fh.write(gzip.compress(data, 6))
+        f = gzopen(path2, b"rb")
+        assert f, "gzopen(rb) failed"
+        got = bytearray()
+        buf = C.create_string_buffer(65536)
+        while len(got) < len(data):
+            n = gzread(f, buf, 65536)
+            assert n > 0, f"gzread returned {n} after {len(got)} bytes"
+            got += buf.raw[:n]
+        gzclose(f)
+        assert bytes(got) == data, "gzread of a foreign gzip file differs"
+    return size
+
 
 alice = gzip.decompress(open(os.path.join(ROOT, "tests", "golden", "alice29.txt.gz"), "rb").read())
 rnd = random.Random(7)
@@ -226,4 +286,6 @@ for name, data in cases.items():
     blob = fx.compress(data) + fx.flush()
     assert nx_inflate_stream(blob, -15, 5000, 9000, len(data)) == data
     report["cases"][name] = r
+print("gz file layer", file=sys.stderr, flush=True)
+report["gz_file"] = gz_file_roundtrip(alice[:60000])
 print(json.dumps(report))

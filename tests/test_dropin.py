@@ -34,6 +34,7 @@ def _drive(lib, log2):
 def test_reference_host_code_over_cpu_engine():
     rep = _drive(REF_CPU, 18)
     assert set(rep["cases"]) == {"alice", "text", "zeros", "random", "tiny"}
+    assert rep["gz_file"] > 0                     # gzopen / gzwrite / gzread / gzclose (lib/nx_gzlib.c) round trip
 
 
 @pytest.mark.gpu
@@ -42,6 +43,7 @@ def test_reference_host_code_over_gpu_engine():
     rep = _drive(REF_GPU, 20)
     # the GPU engine's jobs compress for real: the reference's compress2 over it lands near zlib
     assert rep["cases"]["alice"]["compress2"] < 70000, rep
+    assert 0 < rep["gz_file"] < 40000, rep        # the gz* file layer over the GPU engine; 60 000 bytes of text
 
 
 def _stress(lib, threads, iterations):
