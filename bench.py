@@ -385,6 +385,22 @@ def main():
         extra["inflate_64KiB_members_GBps"] = world * nm * M / (sum(pi) / len(pi)) / 1e6
         extra["inflate_kernel_GBps"] = nm * M / (ki / max(kni, 1)) / 1e6
         extra["inflate_roofline_frac"] = (nm * M + len(packed)) / (ki / max(kni, 1)) / 1e6 / hbm_peak
+        # ---- the same members WITHOUT their index: one concatenated multi-member buffer, members discovered on the
+        # device (candidate headers, dry decoding run, chain from offset 0), then inflated as one batch ----
+        if world == 1:
+            ng = min(nm, 32768)
+            glen = sum(lens[:ng])
+            tot, mem_n = C.c_uint64(), C.c_uint32()
+
+            def gunzip_step():
+                eng.timer_start()
+                eng._check(lib.nxgpu_gunzip_concat(eng.ctx, comp.data_ptr(), glen, out.data_ptr(), ng * M, C.byref(tot), C.byref(mem_n),
+                                                   pg.MEM_DEVICE), "gunzip_concat")
+                return eng.timer_stop()
+            pgz = timed(gunzip_step, 2, 1)
+            assert tot.value == ng * M and mem_n.value == ng
+            extra["gunzip_concat_GBps"] = {"value": ng * M / (sum(pgz) / len(pgz)) / 1e6, "members": ng,
+                                           "note": "members discovered on the device, no index given"}
         del comp, out
         # ---- the same members end to end through the host-pointer call: pinned host buffers, H2D of the compressed
         # bytes and D2H of the inflated ones inside the timed region (wall clock) ----

@@ -246,6 +246,13 @@ typedef struct {
 int nxgpu_inflate_batch(nxgpu_ctx *ctx, const nxgpu_inflate_item *items, size_t n,
 			nxgpu_inflate_result *results, int mem);
 
+/* A buffer of concatenated gzip members (multi-member .gz files; what gunzip, samples/gunzip_nx.c and the gz* layer
+ * read) inflated as one batch; the members are discovered on the device (candidate headers, a dry decoding run, the
+ * chain from offset 0).  *out_len receives the total (also on NXGPU_E_BUF: the capacity needed), *n_members the count.
+ * Every member's CRC-32 and ISIZE are verified.  Members must be smaller than 4 GiB on both sides. */
+int nxgpu_gunzip_concat(nxgpu_ctx *ctx, const void *src, uint64_t src_len, void *dst, uint64_t dst_cap,
+			uint64_t *out_len, uint32_t *n_members, int mem);
+
 /* --- makedata-style synthetic text (reference samples/makedata.c:35-70):
  * byte-for-byte the stream `makedata -s seed -b log2size < seedfile` writes
  * (host-side generator; inputs for bench and tests).  Returns bytes written. */

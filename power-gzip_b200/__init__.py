@@ -74,7 +74,7 @@ EXPORTS = [
     "nxgpu_checksum_batch", "nxgpu_crc32", "nxgpu_adler32", "nxgpu_crc32_combine", "nxgpu_adler32_combine",
     "nxgpu_deflate_batch", "nxgpu_deflate_bound", "nxgpu_deflate_stream", "nxgpu_deflate_stream_bound",
     "nxgpu_inflate_batch", "nxgpu_inflate_stream", "nxgpu_makedata", "nxgpu_job_stats",
-    "nxgpu_dhtgen", "nxgpu_dhtgen_batch",
+    "nxgpu_dhtgen", "nxgpu_dhtgen_batch", "nxgpu_gunzip_concat",
 ]
 
 _lib = None
@@ -118,6 +118,7 @@ def load_library() -> C.CDLL:
         "nxgpu_deflate_stream_bound": (u64, [u64, u32]),
         "nxgpu_inflate_batch": (i32, [vp, P(InflateItem), sz, P(InflateResult), i32]),
         "nxgpu_inflate_stream": (i32, [vp, vp, u64, vp, u64, i32, P(u64), u32, u32, P(StreamResult), i32]),
+        "nxgpu_gunzip_concat": (i32, [vp, vp, u64, vp, u64, P(u64), P(u32), i32]),
         "nxgpu_makedata": (u64, [i32, i32, vp, u64, vp, u64]),
         "nxgpu_job_stats": (None, [i32, P(u64), P(u64), P(u64)]),
         "nxgpu_dhtgen": (i32, [vp, P(u32), i32, P(u32), i32, C.c_char_p, P(i32), P(i32), i32]),
@@ -337,6 +338,15 @@ class Engine:
         self._check(self.lib.nxgpu_inflate_stream(self.ctx, src_ptr, n, dst_ptr, cap, wrap, index, n_chunks, chunk,
                                                   C.byref(res), MEM_DEVICE), "nxgpu_inflate_stream")
         return res
+
+    def gunzip(self, blob, max_out: int) -> Tuple[bytes, int]:
+        """All members of a concatenated gzip buffer, inflated as one batch -> (bytes, number of members)."""
+        a, n, keep = _addr(blob)
+        out = (C.c_char * max(max_out, 1))()
+        total, members = C.c_uint64(), C.c_uint32()
+        self._check(self.lib.nxgpu_gunzip_concat(self.ctx, a, n, C.addressof(out), max_out, C.byref(total), C.byref(members),
+                                                 MEM_HOST), "nxgpu_gunzip_concat")
+        return bytes(memoryview(out)[: total.value]), members.value
 
     def uncompress(self, blob, out_len: int, wrap: int = WRAP_AUTO) -> bytes:
         """libnxz.h ``uncompress`` (lib/nx_uncompr.c:91) for one member."""

@@ -68,6 +68,7 @@ struct DeflateOut {
 	uint32_t reserved[3];
 };
 
+constexpr uint32_t kWrapDry = 0x100;     // InflateJob::wrap flag: decode and count only, write nothing (member discovery)
 constexpr uint32_t kWrapJob = 4;         // InflateJob::wrap: NX decompress job semantics (nxu_run_job), raw deflate
 struct InflateJob {
 	const uint8_t *src;
@@ -145,6 +146,7 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 			   uint32_t *tok_scratch, uint32_t tok_stride, int grid, cudaStream_t s,
 			   uint32_t *job_counter, const uint32_t *ready, uint32_t jobs_per_flag, const StreamOut *so = nullptr);
 cudaError_t launch_dhtgen(const uint32_t *counts, uint32_t n, uint8_t *dht_out, uint32_t *dht_bits, cudaStream_t s);
+cudaError_t launch_gzip_candidates(const uint8_t *src, uint64_t len, uint64_t *cand, uint32_t max_cand, uint32_t *count, cudaStream_t s);
 cudaError_t launch_inflate(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s);
 // checksum.cu
 cudaError_t checksum_init_tables();

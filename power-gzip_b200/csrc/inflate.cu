@@ -297,7 +297,10 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 	br.setup(J.src, J.src_len, T.in);   // every lane knows the geometry; the read position lives in lane 0
 	int rc = 0;                      // uniform after each broadcast
 	uint32_t out = 0;
-	uint32_t start = 0, wrap = J.wrap;
+	// dry run (kWrapDry): walk the Huffman stream and count, write nothing — finds where a member ends and how
+	// long its output is (nxgpu_gunzip_concat discovers the members of a concatenated file this way)
+	const bool dry = (J.wrap & kWrapDry) != 0;
+	uint32_t start = 0, wrap = J.wrap & ~kWrapDry;
 	uint32_t tr_crc = 0, tr_isize = 0, flags = 0;
 	// job mode: set when the source ran out (or the final EOB was seen); lane 0 holds the details
 	bool suspended = false;
@@ -423,7 +426,7 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 				n = J.src_len > stored_at ? J.src_len - stored_at : 0;   // copy what is there, resume later
 			}
 			if (n > J.dst_cap - out) { rc = job ? 13 : NXGPU_E_BUF; break; }
-			for (uint32_t i = lane; i < n; i += 32)
+			for (uint32_t i = lane; i < n && !dry; i += 32)
 				J.dst[out + i] = J.src[stored_at + i];
 			out += n;
 			if (n < stored_len) {
@@ -605,6 +608,11 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 			const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
 			const uint32_t my_out = out + incl - mylen;
 			if (total > J.dst_cap - out) { rc = job ? 13 : NXGPU_E_BUF; break; }
+			if (dry) {
+				if (__any_sync(0xffffffffu, is_m && tok_dist(t) > my_out + J.hist_len)) { rc = NXGPU_E_DATA; break; }
+				out += total;
+				continue;
+			}
 			const bool bad = is_m && tok_dist(t) > my_out + J.hist_len;
 			if (__any_sync(0xffffffffu, bad)) { rc = job ? 67 : NXGPU_E_DATA; break; }
 			// A match whose source ends in front of this batch's output (distance >= the bytes the batch
@@ -763,7 +771,31 @@ inflate_kernel(const InflateJob *__restrict__ jobs, InflateOut *__restrict__ out
 	}
 }
 
+// every offset where a gzip member COULD start: 1f 8b 08 and a flag byte without reserved bits (RFC 1952 §2.3);
+// the list is unordered, false positives (the pattern inside compressed or stored data) are weeded out by decoding
+__global__ void gzip_candidates_kernel(const uint8_t *__restrict__ src, uint64_t len, uint64_t *__restrict__ cand, uint32_t max_cand,
+				       uint32_t *__restrict__ count)
+{
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p + 18 <= len; p += stride) {
+		if (src[p] == 0x1f && src[p + 1] == 0x8b && src[p + 2] == 8 && (src[p + 3] & 0xe0) == 0) {
+			const uint32_t k = atomicAdd(count, 1u);
+			if (k < max_cand)
+				cand[k] = p;
+		}
+	}
+}
+
 } // namespace
+
+cudaError_t launch_gzip_candidates(const uint8_t *src, uint64_t len, uint64_t *cand, uint32_t max_cand, uint32_t *count, cudaStream_t s)
+{
+	cudaError_t e = cudaMemsetAsync(count, 0, sizeof(uint32_t), s);
+	if (e != cudaSuccess)
+		return e;
+	gzip_candidates_kernel<<<kNumSMs * 8, 256, 0, s>>>(src, len, cand, max_cand, count);
+	return cudaGetLastError();
+}
 
 template <int kMinCtas>
 static cudaError_t launch_inflate_t(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s)

@@ -922,6 +922,118 @@ int nxgpu_inflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *
 	return 0;
 }
 
+/* A file of concatenated gzip members (`cat a.gz b.gz`, bgzip, the output of pigz -i ...) inflated as ONE batch —
+ * the member-indexed reader of SURVEY.md §8f rank 2 (the reference's nx_gzread, lib/nx_gzlib.c:220-263, stops after
+ * the first member and pulls 10 bytes per read()).  Members carry no index, so they are discovered on the device:
+ * (1) every offset that looks like a member header becomes a candidate, (2) a dry run decodes all candidates at
+ * once — no output, only "where does it end, how many bytes does it make" —, (3) the true members are the chain from
+ * offset 0 (each must start where the previous one ended; ISIZE must match), (4) their output offsets are the prefix
+ * sums and nxgpu_inflate_batch inflates and CRC-checks them all. */
+int nxgpu_gunzip_concat(nxgpu_ctx *c, const void *src, uint64_t src_len, void *dst, uint64_t dst_cap,
+			uint64_t *out_len, uint32_t *n_members, int mem)
+{
+	if (!c || !src || (!dst && dst_cap) || !out_len) return NXGPU_E_ARG;
+	NXGPU_LOCK(c);
+	*out_len = 0;
+	if (n_members) *n_members = 0;
+	if (src_len < 18) { set_error("shorter than one gzip member"); return NXGPU_E_DATA; }
+	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
+	int rc;
+	const uint8_t *dsrc = static_cast<const uint8_t *>(src);
+	uint8_t *ddst = static_cast<uint8_t *>(dst);
+	if (mem == NXGPU_MEM_HOST) {
+		if ((rc = c->d_in.reserve(src_len + 64))) return rc;
+		NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_in.p, src, src_len, cudaMemcpyHostToDevice, c->stream));
+		dsrc = static_cast<const uint8_t *>(c->d_in.p);
+	}
+	// (1) candidates
+	const uint32_t max_cand = 1u << 22;
+	if ((rc = c->d_cat.reserve((size_t)max_cand * 8))) return rc;
+	if ((rc = c->d_misc.reserve(64))) return rc;
+	uint64_t *d_cand = static_cast<uint64_t *>(c->d_cat.p);
+	uint32_t *d_count = static_cast<uint32_t *>(c->d_misc.p) + 8;
+	NXGPU_CUDA_OK(launch_gzip_candidates(dsrc, src_len, d_cand, max_cand, d_count, c->stream));
+	c->launches++;
+	uint32_t n_cand = 0;
+	NXGPU_CUDA_OK(cudaMemcpyAsync(&n_cand, d_count, 4, cudaMemcpyDeviceToHost, c->stream));
+	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	if (n_cand == 0) { set_error("no gzip member header found"); return NXGPU_E_DATA; }
+	if (n_cand > max_cand) { set_error("more than %u candidate member headers", max_cand); return NXGPU_E_MEM; }
+	std::vector<uint64_t> cand(n_cand);
+	NXGPU_CUDA_OK(cudaMemcpy(cand.data(), d_cand, (size_t)n_cand * 8, cudaMemcpyDeviceToHost));
+	std::sort(cand.begin(), cand.end());
+	// (2) dry run of every candidate
+	if ((rc = c->h_jobs.reserve((size_t)n_cand * sizeof(InflateJob)))) return rc;
+	if ((rc = c->d_ijobs.reserve((size_t)n_cand * sizeof(InflateJob)))) return rc;
+	if ((rc = c->d_iouts.reserve((size_t)n_cand * sizeof(InflateOut)))) return rc;
+	InflateJob *jh = static_cast<InflateJob *>(c->h_jobs.p);
+	memset(jh, 0, (size_t)n_cand * sizeof(InflateJob));
+	for (uint32_t i = 0; i < n_cand; i++) {
+		const uint64_t rest = src_len - cand[i];
+		jh[i].src = dsrc + cand[i];
+		jh[i].src_len = (uint32_t)(rest < 0xfffffff0ull ? rest : 0xfffffff0ull);
+		jh[i].wrap = NXGPU_WRAP_GZIP | kWrapDry;
+		jh[i].dst = nullptr;
+		jh[i].dst_cap = 0xffffffffu;
+	}
+	NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_ijobs.p, jh, (size_t)n_cand * sizeof(InflateJob), cudaMemcpyHostToDevice, c->stream));
+	timer_begin(c, 1);
+	NXGPU_CUDA_OK(launch_inflate(static_cast<const InflateJob *>(c->d_ijobs.p), static_cast<InflateOut *>(c->d_iouts.p), n_cand,
+				     static_cast<uint32_t *>(c->d_misc.p), c->stream));
+	timer_end(c, 1);
+	c->launches++;
+	std::vector<InflateOut> dry(n_cand);
+	NXGPU_CUDA_OK(cudaMemcpyAsync(dry.data(), c->d_iouts.p, (size_t)n_cand * sizeof(InflateOut), cudaMemcpyDeviceToHost, c->stream));
+	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	// (3) the chain of true members from offset 0
+	std::vector<nxgpu_inflate_item> items;
+	uint64_t p = 0, total = 0;
+	while (p < src_len) {
+		const auto it = std::lower_bound(cand.begin(), cand.end(), p);
+		if (it == cand.end() || *it != p) {
+			bool zeros = mem == NXGPU_MEM_HOST;                 // gzip tolerates zero padding behind the last member
+			for (uint64_t q = p; zeros && q < src_len; q++) zeros = static_cast<const uint8_t *>(src)[q] == 0;
+			if (zeros && !items.empty()) break;
+			set_error("no gzip member starts at offset %llu", (unsigned long long)p);
+			return NXGPU_E_DATA;
+		}
+		const InflateOut &o = dry[it - cand.begin()];
+		if (o.rc != 0 || o.in_used == 0 || o.trailer_isize != o.out_len) {
+			set_error("member at offset %llu does not decode (rc %d)", (unsigned long long)p, o.rc);
+			return NXGPU_E_DATA;
+		}
+		nxgpu_inflate_item m;
+		m.src = dsrc + p; m.src_len = o.in_used;
+		m.dst = reinterpret_cast<void *>(total);                 // offset for now, pointer once the buffer is known
+		m.dst_cap = o.out_len; m.wrap = NXGPU_WRAP_GZIP; m.hist_len = 0;
+		items.push_back(m);
+		total += o.out_len;
+		p += o.in_used;
+	}
+	*out_len = total;
+	if (n_members) *n_members = (uint32_t)items.size();
+	if (total > dst_cap) { set_error("output needs %llu bytes, capacity %llu", (unsigned long long)total, (unsigned long long)dst_cap); return NXGPU_E_BUF; }
+	// (4) the real thing
+	if (mem == NXGPU_MEM_HOST) {
+		if ((rc = c->d_out.reserve(total + 64))) return rc;
+		ddst = static_cast<uint8_t *>(c->d_out.p);
+	}
+	for (nxgpu_inflate_item &m : items)
+		m.dst = ddst + reinterpret_cast<uintptr_t>(m.dst);
+	std::vector<nxgpu_inflate_result> rs(items.size());
+	if ((rc = nxgpu_inflate_batch(c, items.data(), items.size(), rs.data(), NXGPU_MEM_DEVICE))) return rc;
+	for (size_t i = 0; i < rs.size(); i++)
+		if (rs[i].rc != 0 || !(rs[i].flags & 2)) {
+			set_error("member %zu: rc %d, trailer %s", i, rs[i].rc, (rs[i].flags & 2) ? "ok" : "mismatch");
+			return NXGPU_E_DATA;
+		}
+	if (mem == NXGPU_MEM_HOST && total) {
+		NXGPU_CUDA_OK(cudaMemcpyAsync(dst, ddst, total, cudaMemcpyDeviceToHost, c->stream));
+		NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	}
+	return 0;
+}
+
 /* ------------------------------ makedata ------------------------------- */
 
 // Same draw order as reference samples/makedata.c:35-70 (srand48/lrand48).  A draw of dist == 0

@@ -443,3 +443,41 @@ def test_one_context_shared_by_threads(engine, pg, alice):
         t.join()
     assert not errs, errs
     assert out == datas
+
+
+def test_gunzip_of_concatenated_members(engine, pg, alice):
+    """SURVEY.md §8f rank 2 (gz* / gunzip: multi-member files).  The members of a concatenated gzip buffer are
+    discovered on the device and inflated as one batch; the result must equal what gzip.decompress (which
+    also walks all members) returns, including members with optional header fields, empty members, and data
+    that contains byte patterns looking like member headers."""
+    import io
+    rnd = random.Random(21)
+    fake = b"\x1f\x8b\x08\x00" + bytes(14)
+    parts = [alice[:70000], b"", fake * 50, rnd.randbytes(5000) + fake + rnd.randbytes(100), _text(123456), bytes(100000),
+             alice[70000:], b"x"]
+    blobs = []
+    for i, d in enumerate(parts):
+        buf = io.BytesIO()
+        with gzip.GzipFile(filename=f"part{i}.txt" if i % 2 else "", mode="wb", fileobj=buf, compresslevel=(0, 1, 6, 9)[i % 4], mtime=i) as g:
+            g.write(d)                                   # level 0 = stored blocks: the fake headers appear verbatim in the file
+        blobs.append(buf.getvalue())
+    for i in range(300):                                 # many small members, bgzip style
+        d = _text(rnd.randrange(0, 3000), seed=i)
+        parts.append(d)
+        blobs.append(gzip.compress(d, 6, mtime=0))
+    blob, want = b"".join(blobs), b"".join(parts)
+    assert gzip.decompress(blob) == want
+    got, members = engine.gunzip(blob, len(want))
+    assert members == len(parts) and got == want
+    # one member, zero padding behind the last member
+    assert engine.gunzip(blobs[0], len(parts[0])) == (parts[0], 1)
+    assert engine.gunzip(blobs[0] + bytes(512), len(parts[0])) == (parts[0], 1)
+    # too small a target: the needed size is reported
+    with pytest.raises(pg.NxGpuError) as e:
+        engine.gunzip(blob, len(want) - 1)
+    assert e.value.rc == pg.E_BUF
+    # garbage between members, a damaged member, a truncated tail
+    for bad in (blobs[0] + b"garbage!" * 4 + blobs[2], blobs[0] + blobs[4][:-9] + bytes([blobs[4][-9] ^ 1]) + blobs[4][-8:], blob[:-5]):
+        with pytest.raises(pg.NxGpuError) as e:
+            engine.gunzip(bad, len(want))
+        assert e.value.rc == pg.E_DATA
