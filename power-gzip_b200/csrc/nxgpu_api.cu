@@ -751,15 +751,30 @@ int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n,
 				dst_contig = false;
 			if (items[i].hist_len) dst_contig = false;
 		}
-		if ((rc = c->d_in.reserve(in_total + 16))) return rc;
+		// sources that already sit back to back in pinned host memory (a file read into a pinned buffer) go up as they
+		// are; anything else is packed through pinned staging first: one H2D instead of n small ones either way
+		bool src_direct = true;
+		const uint8_t *s0 = static_cast<const uint8_t *>(items[0].src);
+		for (size_t i = 1; i < n && src_direct; i++)
+			src_direct = static_cast<const uint8_t *>(items[i].src) >= static_cast<const uint8_t *>(items[i - 1].src) + items[i - 1].src_len;
+		const uint64_t src_span = src_direct ? (static_cast<const uint8_t *>(items[n - 1].src) - s0) + items[n - 1].src_len : 0;
+		if (src_direct) {
+			cudaPointerAttributes pa;
+			src_direct = src_span <= 2 * in_total + 4096 && cudaPointerGetAttributes(&pa, s0) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+			cudaGetLastError();
+		}
+		if ((rc = c->d_in.reserve((src_direct ? src_span : in_total) + 16))) return rc;
 		if ((rc = c->d_out.reserve(out_total + 16))) return rc;
-		// pack sources through pinned staging: one H2D instead of n small ones
-		if ((rc = c->h_stage.reserve(in_total + 16))) return rc;
+		if (!src_direct && (rc = c->h_stage.reserve(in_total + 16))) return rc;
 		uint64_t io = 0, oo = 0;
 		uint8_t *hs = static_cast<uint8_t *>(c->h_stage.p);
 		for (size_t i = 0; i < n; i++) {
-			memcpy(hs + io, items[i].src, items[i].src_len);
-			jh[i].src = static_cast<uint8_t *>(c->d_in.p) + io;
+			if (src_direct) {
+				jh[i].src = static_cast<uint8_t *>(c->d_in.p) + (static_cast<const uint8_t *>(items[i].src) - s0);
+			} else {
+				memcpy(hs + io, items[i].src, items[i].src_len);
+				jh[i].src = static_cast<uint8_t *>(c->d_in.p) + io;
+			}
 			jh[i].src_len = items[i].src_len; jh[i].wrap = items[i].wrap;
 			jh[i].hist_len = items[i].hist_len; jh[i].dst_cap = items[i].dst_cap;
 			if (dst_contig) {
@@ -773,7 +788,10 @@ int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n,
 			io += align_up(items[i].src_len, 16);
 			oo += align_up((uint64_t)items[i].hist_len + items[i].dst_cap, 16);
 		}
-		NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_in.p, hs, in_total, cudaMemcpyHostToDevice, c->stream));
+		if (src_direct)
+			NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_in.p, s0, src_span, cudaMemcpyHostToDevice, c->stream));
+		else
+			NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_in.p, hs, in_total, cudaMemcpyHostToDevice, c->stream));
 	} else {
 		for (size_t i = 0; i < n; i++) {
 			jh[i].src = static_cast<const uint8_t *>(items[i].src); jh[i].src_len = items[i].src_len; jh[i].wrap = items[i].wrap;
