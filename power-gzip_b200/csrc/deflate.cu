@@ -578,13 +578,16 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 
 	// ---- final parse over the stored per-position results ----
 	uint32_t n = 0, head = 0;
+	uint32_t t_next = lane < npos ? __ldcg(&pres[lane]) : 0;          // results are read one window ahead (L2 latency)
 	for (uint32_t w0 = 0; w0 < npos; w0 += 32) {
 		const uint32_t nlive = min(32u, npos - w0);
+		const uint32_t t = t_next;
+		if (w0 + 32 + lane < npos)
+			t_next = __ldcg(&pres[w0 + 32 + lane]);
 		if (head >= w0 + nlive)
 			continue;
 		const bool live = lane < nlive;
 		const uint32_t pos = sub_lo + w0 + lane;
-		const uint32_t t = live ? __ldcg(&pres[w0 + lane]) : 0;
 		const uint32_t len = (live && tok_is_match(t)) ? tok_len(t) : 0;
 		bool take; uint32_t J, Rl;
 		window_parse(lane, nlive, len, lazy, take, J, Rl);
