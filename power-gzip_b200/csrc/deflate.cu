@@ -438,9 +438,15 @@ __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, ui
 // tools/lzsim.c (two=2): same or better ratio than full depth everywhere at a third of the hops.
 
 // one lane's chain walk: longest match for `pos` among the first `depth` chain candidates
+// (seed: a match already known for this position — the shallow pass's result when the deep pass walks the same
+// chain again; only strictly longer matches replace it, so the 4-byte filter rejects the candidates that
+// produced it without a full compare and the result is the same as walking from scratch)
 __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, uint32_t pos, uint32_t maxl, uint32_t maxdist,
-					   int depth, uint32_t nice, uint32_t &bl, uint32_t &bd)
+					   int depth, uint32_t nice, uint32_t &bl, uint32_t &bd, uint32_t seed = 0,
+					   uint32_t *cursor = nullptr, uint32_t resume = 0xffffffffu)
 {
+	// cursor: where this walk stopped in the chain (distance walked << 16 | next link), so that a later, deeper
+	// walk of the same position (resume) continues there instead of repeating the first hops
 	uint32_t P0, P1, P2, P3;
 	{
 		const uint32_t o = pos & kRingMask, a = o & ~3u, sh = (o & 3) * 8;
@@ -452,6 +458,17 @@ __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, 
 	uint32_t acc = 0;
 	uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;
 	uint32_t endw = __funnelshift_r(P0, P1, 8);                  // the 4 bytes ending at offset bl = 4
+	if (tok_is_match(seed) && tok_len(seed) <= maxl) {
+		bl = tok_len(seed); bd = tok_dist(seed);
+		if (bl >= nice || bl >= maxl)
+			d = 0;
+		else
+			endw = load4(ring8, pos + bl - 3);
+	}
+	if (resume != 0xffffffffu && d) {
+		acc = resume >> 16;
+		d = resume & 0xffffu;
+	}
 	for (int hop = 0; hop < depth; hop++) {
 		if (!__any_sync(0xffffffffu, d != 0))
 			break;
@@ -475,6 +492,8 @@ __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, 
 			}
 		}
 	}
+	if (cursor)
+		*cursor = acc << 16 | d;
 }
 
 // greedy / lazy choice per position of one window, then pointer jumping: every lane ends up with
@@ -506,7 +525,7 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 	const uint32_t lt = (1u << lane) - 1;
 	const uint8_t *ring8 = reinterpret_cast<const uint8_t *>(S.ring32);
 	const uint32_t npos = sub_hi - sub_lo;
-	uint32_t qpos = 0, qn = 0;                                 // pass-2 queue: one position per lane
+	uint32_t qpos = 0, qtok = 0, qcur = 0, qn = 0;             // pass-2 queue: one position (its shallow result, its chain cursor) per lane
 	uint32_t headA = 0;                                        // pass-1 parse: next token start (relative to sub_lo)
 	uint32_t carry = 0;                                        // mark for lane 0 of the next window
 
@@ -524,7 +543,7 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 		const uint32_t pos = act ? qpos : sub_lo;
 		const uint32_t maxl = act ? min((uint32_t)kMaxMatch, PE - pos) : 0;
 		uint32_t bl, bd;
-		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), depth, (uint32_t)nice, bl, bd);
+		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), max(1, depth - d1), (uint32_t)nice, bl, bd, act ? qtok : 0, nullptr, act ? qcur : 0);   // the first d1 hops were walked by the shallow pass
 		if (act && bl >= (uint32_t)kMinMatch)
 			__stcg(&pres[pos - sub_lo], tok_match(bl, bd));
 	};
@@ -537,10 +556,12 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 		const bool live = lane < nlive;
 		const uint32_t maxl = live ? min((uint32_t)kMaxMatch, PE - pos) : 0;
 		uint32_t bl, bd;
-		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), d1, (uint32_t)nice, bl, bd);
+		uint32_t mycur;
+		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), d1, (uint32_t)nice, bl, bd, 0, &mycur);
 		const uint32_t len = bl >= (uint32_t)kMinMatch ? bl : 0;
+		const uint32_t mytok = len ? tok_match(len, bd) : 0;
 		if (live)
-			__stcg(&pres[w0 + lane], len ? tok_match(len, bd) : (uint32_t)ring8[pos & kRingMask]);
+			__stcg(&pres[w0 + lane], len ? mytok : (uint32_t)ring8[pos & kRingMask]);
 		uint32_t M = carry;
 		carry = 0;
 		if (headA < w0 + nlive) {
@@ -558,8 +579,14 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 			M &= (1u << nlive) - 1;
 		while (M) {
 			const uint32_t cnt = __popc(M), room = 32 - qn, tk_n = min(cnt, room);
-			if (lane >= qn && lane < qn + tk_n)
-				qpos = sub_lo + w0 + __fns(M, 0, (int)(lane - qn + 1));
+			const uint32_t from = __fns(M, 0, (int)(lane - qn + 1)) & 31;        // the window lane whose position this queue slot takes
+			const uint32_t ftok = __shfl_sync(0xffffffffu, mytok, from);
+			const uint32_t fcur = __shfl_sync(0xffffffffu, mycur, from);
+			if (lane >= qn && lane < qn + tk_n) {
+				qpos = sub_lo + w0 + from;
+				qtok = ftok;
+				qcur = fcur;
+			}
 			qn += tk_n;
 			if (tk_n == cnt)
 				M = 0;
