@@ -116,11 +116,11 @@ __host__ __device__ inline LevelParams level_params(int level)
 	case 3: return { 4, 0, 128, 0 };
 	case 4: return { 4, 16, 128, 0 };
 	case 5: return { 12, 32, 258, 2 };
-	case 6: return { 32, 32, 258, 2 };
+	case 6: return { 32, 16, 258, 2 };
 	case 7: return { 32, 64, 258, 3 };
 	case 8: return { 48, 258, 258, 3 };
 	case 9: return { 96, 258, 258, 4 };
-	default: return { 32, 32, 258, 2 };
+	default: return { 32, 16, 258, 2 };
 	}
 }
 
