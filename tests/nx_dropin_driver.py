@@ -209,6 +209,61 @@ if len(sys.argv) > 2 and sys.argv[2] == "initend":
     initend(int(sys.argv[3]) if len(sys.argv) > 3 else 1000)
     sys.exit(0)
 
+def dictionary_roundtrip(data, dictionary):
+    """Preset dictionaries through the zlib surface (test/test_dict.c:40-140): the dictionary travels as job history.
+    zlib mode: FDICT set, DICTID = adler32(dict), trailer = adler32(data); raw mode: no header.  Both directions:
+    nx deflate -> system zlib inflate, system zlib deflate -> nx inflate (Z_NEED_DICT, then inflateSetDictionary)."""
+    lib.deflateSetDictionary.argtypes = [C.POINTER(ZStream), C.c_char_p, C.c_uint]
+    lib.inflateSetDictionary.argtypes = [C.POINTER(ZStream), C.c_char_p, C.c_uint]
+    Z_NEED_DICT = 2
+    sizes = {}
+    for wbits in (15, -15):
+        s = ZStream()
+        assert lib.deflateInit2_(C.byref(s), 6, 8, wbits, 8, 0, VER, C.sizeof(ZStream)) == 0
+        assert lib.deflateSetDictionary(C.byref(s), dictionary, len(dictionary)) == 0
+        if wbits > 0:
+            assert s.adler == zlib.adler32(dictionary), "deflateSetDictionary must leave the dictionary's adler32 in strm.adler"
+        src = C.create_string_buffer(data, len(data))
+        out = C.create_string_buffer(2 * len(data) + 1024)
+        s.next_in, s.avail_in = C.addressof(src), len(data)
+        s.next_out, s.avail_out = C.addressof(out), len(out)
+        assert lib.deflate(C.byref(s), Z_FINISH) == Z_STREAM_END
+        blob = out.raw[: s.total_out]
+        lib.deflateEnd(C.byref(s))
+        if wbits > 0:
+            assert blob[1] & 0x20, "FLG.FDICT not set"
+            assert int.from_bytes(blob[2:6], "big") == zlib.adler32(dictionary), "wrong DICTID"
+            assert int.from_bytes(blob[-4:], "big") == zlib.adler32(data), "trailer must be the adler32 of the data alone"
+        d = zlib.decompressobj(wbits, zdict=dictionary)
+        assert d.decompress(blob) == data, f"zlib cannot decode nx deflate with a dictionary (wbits {wbits})"
+        sizes[wbits] = len(blob)
+        # the other direction
+        co = zlib.compressobj(6, zlib.DEFLATED, wbits, zdict=dictionary)
+        foreign = co.compress(data) + co.flush()
+        s = ZStream()
+        assert lib.inflateInit2_(C.byref(s), wbits, VER, C.sizeof(ZStream)) == 0
+        fsrc = C.create_string_buffer(foreign, len(foreign))
+        back = C.create_string_buffer(len(data) + 64)
+        s.next_in, s.avail_in = C.addressof(fsrc), len(foreign)
+        s.next_out, s.avail_out = C.addressof(back), len(back)
+        if wbits < 0:
+            assert lib.inflateSetDictionary(C.byref(s), dictionary, len(dictionary)) == 0
+        rc = lib.inflate(C.byref(s), Z_NO_FLUSH)
+        if wbits > 0:
+            assert rc == Z_NEED_DICT, f"expected Z_NEED_DICT, got {rc}"
+            assert s.adler == zlib.adler32(dictionary)
+            assert lib.inflateSetDictionary(C.byref(s), dictionary, len(dictionary)) == 0
+            rc = lib.inflate(C.byref(s), Z_NO_FLUSH)
+        guard = 0
+        while rc == Z_OK and guard < 1000:
+            rc = lib.inflate(C.byref(s), Z_NO_FLUSH)
+            guard += 1
+        assert rc == Z_STREAM_END, f"inflate with dictionary ended with {rc}"
+        assert back.raw[: s.total_out] == data
+        lib.inflateEnd(C.byref(s))
+    return sizes[15]
+
+
 def gz_file_roundtrip(data):
     """The reference's gz* file layer (lib/nx_gzlib.c:130-351: gzopen / gzwrite / gzread / gzclose) over the engine:
     a file it writes must gunzip with Python, a file Python wrote must read back through it."""
@@ -286,6 +341,10 @@ for name, data in cases.items():
     blob = fx.compress(data) + fx.flush()
     assert nx_inflate_stream(blob, -15, 5000, 9000, len(data)) == data
     report["cases"][name] = r
+print("dictionary", file=sys.stderr, flush=True)
+# sizes: one job, and a first job that yields more than the 32 KiB window — the reference's host code hands the
+# dictionary to the first decompress job only (lib/nx_inflate.c:1711-1712), whatever engine sits below it
+report["dictionary"] = [dictionary_roundtrip(alice[40000:45000], alice[:32768]), dictionary_roundtrip(alice[40000:150000], alice[:20000])]
 print("gz file layer", file=sys.stderr, flush=True)
 report["gz_file"] = gz_file_roundtrip(alice[:60000])
 print(json.dumps(report))

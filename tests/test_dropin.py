@@ -35,6 +35,7 @@ def test_reference_host_code_over_cpu_engine():
     rep = _drive(REF_CPU, 18)
     assert set(rep["cases"]) == {"alice", "text", "zeros", "random", "tiny"}
     assert rep["gz_file"] > 0                     # gzopen / gzwrite / gzread / gzclose (lib/nx_gzlib.c) round trip
+    assert all(x > 0 for x in rep["dictionary"])  # deflate/inflateSetDictionary both ways (test/test_dict.c)
 
 
 @pytest.mark.gpu
@@ -44,6 +45,7 @@ def test_reference_host_code_over_gpu_engine():
     # the GPU engine's jobs compress for real: the reference's compress2 over it lands near zlib
     assert rep["cases"]["alice"]["compress2"] < 70000, rep
     assert 0 < rep["gz_file"] < 40000, rep        # the gz* file layer over the GPU engine; 60 000 bytes of text
+    assert all(x > 0 for x in rep["dictionary"]), rep
 
 
 def _stress(lib, threads, iterations):
