@@ -264,6 +264,55 @@ def dictionary_roundtrip(data, dictionary):
     return sizes[15]
 
 
+def zero_input_and_reset(data):
+    """test/test_zeroinput.c:39-60: an empty stream finished with every flush mode must be a valid zlib stream of zero
+    bytes; test/test_reset.c:69-140: deflateReset / inflateReset give a stream that works again, several times."""
+    lib.deflateReset.argtypes = [C.POINTER(ZStream)]
+    lib.inflateReset.argtypes = [C.POINTER(ZStream)]
+    out = C.create_string_buffer(2 * len(data) + 1024)
+    for flush in (Z_NO_FLUSH, 1, Z_SYNC_FLUSH, Z_FULL_FLUSH, Z_FINISH):
+        s = ZStream()
+        assert lib.deflateInit2_(C.byref(s), 6, 8, 15, 8, 0, VER, C.sizeof(ZStream)) == 0
+        s.next_in, s.avail_in = C.addressof(out), 0
+        s.next_out, s.avail_out = C.addressof(out), len(out)
+        rc = lib.deflate(C.byref(s), flush)
+        assert rc == (Z_STREAM_END if flush == Z_FINISH else Z_OK), f"empty deflate, flush {flush}: {rc}"
+        if flush != Z_FINISH:
+            assert lib.deflate(C.byref(s), Z_FINISH) == Z_STREAM_END
+        assert zlib.decompress(out.raw[: s.total_out]) == b"", f"empty stream (flush {flush}) is not a valid zlib stream"
+        lib.deflateEnd(C.byref(s))
+    # the sequence of test/test_reset.c:80-140: reset between init and the first call is fine, the stream works, and a
+    # reset afterwards zeroes the counters (re-using a deflate stream after a reset that follows data trips an assertion
+    # in the reference's own host code, lib/nx_deflate.c:843, on any engine — the reference's test never does that)
+    back = C.create_string_buffer(len(data) + 64)
+    src = C.create_string_buffer(data, len(data))
+    s = ZStream()
+    assert lib.deflateInit2_(C.byref(s), 6, 8, 31, 8, 0, VER, C.sizeof(ZStream)) == 0
+    assert lib.deflateReset(C.byref(s)) == 0
+    s.next_in, s.avail_in = C.addressof(src), len(data)
+    s.next_out, s.avail_out = C.addressof(out), len(out)
+    assert lib.deflate(C.byref(s), Z_FINISH) == Z_STREAM_END
+    blob = out.raw[: s.total_out]
+    assert gzip.decompress(blob) == data
+    assert lib.deflateReset(C.byref(s)) == 0 and s.total_in == 0 and s.total_out == 0
+    lib.deflateEnd(C.byref(s))
+    d = ZStream()
+    assert lib.inflateInit2_(C.byref(d), 31, VER, C.sizeof(ZStream)) == 0
+    assert lib.inflateReset(C.byref(d)) == 0
+    for k in range(3):                               # an inflate stream is re-used after every reset
+        zs = C.create_string_buffer(blob, len(blob))
+        d.next_in, d.avail_in = C.addressof(zs), len(blob)
+        d.next_out, d.avail_out = C.addressof(back), len(back)
+        rc, guard = Z_OK, 0
+        while rc == Z_OK and guard < 1000:
+            rc = lib.inflate(C.byref(d), Z_NO_FLUSH)
+            guard += 1
+        assert rc == Z_STREAM_END and back.raw[: d.total_out] == data, f"round {k}: inflate after inflateReset differs ({rc})"
+        assert lib.inflateReset(C.byref(d)) == 0 and d.total_out == 0
+    lib.inflateEnd(C.byref(d))
+    return True
+
+
 def gz_file_roundtrip(data):
     """The reference's gz* file layer (lib/nx_gzlib.c:130-351: gzopen / gzwrite / gzread / gzclose) over the engine:
     a file it writes must gunzip with Python, a file Python wrote must read back through it."""
@@ -341,6 +390,8 @@ for name, data in cases.items():
     blob = fx.compress(data) + fx.flush()
     assert nx_inflate_stream(blob, -15, 5000, 9000, len(data)) == data
     report["cases"][name] = r
+print("zero input, reset", file=sys.stderr, flush=True)
+report["zero_input_and_reset"] = zero_input_and_reset(alice[:70000])
 print("dictionary", file=sys.stderr, flush=True)
 # sizes: one job, and a first job that yields more than the 32 KiB window — the reference's host code hands the
 # dictionary to the first decompress job only (lib/nx_inflate.c:1711-1712), whatever engine sits below it

@@ -36,6 +36,7 @@ def test_reference_host_code_over_cpu_engine():
     assert set(rep["cases"]) == {"alice", "text", "zeros", "random", "tiny"}
     assert rep["gz_file"] > 0                     # gzopen / gzwrite / gzread / gzclose (lib/nx_gzlib.c) round trip
     assert all(x > 0 for x in rep["dictionary"])  # deflate/inflateSetDictionary both ways (test/test_dict.c)
+    assert rep["zero_input_and_reset"]            # test/test_zeroinput.c, test/test_reset.c
 
 
 @pytest.mark.gpu
@@ -45,7 +46,7 @@ def test_reference_host_code_over_gpu_engine():
     # the GPU engine's jobs compress for real: the reference's compress2 over it lands near zlib
     assert rep["cases"]["alice"]["compress2"] < 70000, rep
     assert 0 < rep["gz_file"] < 40000, rep        # the gz* file layer over the GPU engine; 60 000 bytes of text
-    assert all(x > 0 for x in rep["dictionary"]), rep
+    assert all(x > 0 for x in rep["dictionary"]) and rep["zero_input_and_reset"], rep
 
 
 def _stress(lib, threads, iterations):
