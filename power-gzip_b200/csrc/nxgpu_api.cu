@@ -802,33 +802,55 @@ int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n,
 	if ((rc = c->d_outs.reserve(n * sizeof(InflateOut)))) return rc;
 	if ((rc = c->d_misc.reserve(64))) return rc;
 	const size_t rb = checksum_range_bytes(), pb = checksum_partial_bytes();
-	if ((rc = c->d_ranges.reserve(n * rb + (n + 1) * 4))) return rc;
+	// A large host-memory batch with one contiguous target runs as up to four groups of members: the device-to-host
+	// copy of a group's output goes to the copy stream as soon as the group is inflated and overlaps the next group
+	// (a group is at least one full wave of warps, so the kernel loses nothing)
+	const size_t wave = 4 * 7 * (size_t)kNumSMs;
+	const size_t n_groups = (mem == NXGPU_MEM_HOST && dst_contig && n >= 2 * wave) ? std::min<size_t>(4, n / wave) : 1;
+	if ((rc = c->d_ranges.reserve(n * rb + (n + n_groups + 1) * 4))) return rc;
 	if ((rc = c->d_parts.reserve(n * pb))) return rc;
 	if ((rc = c->d_cks.reserve(n * 8 + 16))) return rc;
 	NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_jobs.p, jh, n * sizeof(InflateJob), cudaMemcpyHostToDevice, c->stream));
 	const InflateJob *dj = static_cast<const InflateJob *>(c->d_jobs.p);
 	InflateOut *dout = static_cast<InflateOut *>(c->d_outs.p);
-	timer_begin(c, 1);
-	NXGPU_CUDA_OK(launch_inflate(dj, dout, (uint32_t)n, static_cast<uint32_t *>(c->d_misc.p), c->stream));
-	timer_end(c, 1);
-	// crc32 / adler32 of every output, lengths taken from the device results
-	uint32_t *d_rs = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(c->d_ranges.p) + n * rb);
-	NXGPU_CUDA_OK(launch_ranges_from_inflate(dj, dout, (uint32_t)n, c->d_ranges.p, d_rs, c->stream));
+	uint8_t *d_rng = static_cast<uint8_t *>(c->d_ranges.p);
+	uint8_t *d_prt = static_cast<uint8_t *>(c->d_parts.p);
+	uint32_t *d_rs_all = reinterpret_cast<uint32_t *>(d_rng + n * rb);
 	uint32_t *d_crc = static_cast<uint32_t *>(c->d_cks.p), *d_adler = d_crc + n;
-	timer_begin(c, 2);
-	NXGPU_CUDA_OK(launch_checksum_ranges(c->d_ranges.p, (uint32_t)n, c->d_parts.p, 3, c->stream));
-	timer_end(c, 2);
-	NXGPU_CUDA_OK(launch_checksum_combine(c->d_ranges.p, c->d_parts.p, d_rs, (uint32_t)n, nullptr, nullptr, d_crc, d_adler, c->stream));
-	c->launches += 2;
+	for (size_t g = 0; g < n_groups; g++) {
+		const size_t g0 = g * n / n_groups, g1 = (g + 1) * n / n_groups, ng = g1 - g0;
+		timer_begin(c, 1);
+		NXGPU_CUDA_OK(launch_inflate(dj + g0, dout + g0, (uint32_t)ng, static_cast<uint32_t *>(c->d_misc.p), c->stream));
+		timer_end(c, 1);
+		// crc32 / adler32 of every output, lengths taken from the device results
+		uint32_t *d_rs = d_rs_all + g0 + g;
+		NXGPU_CUDA_OK(launch_ranges_from_inflate(dj + g0, dout + g0, (uint32_t)ng, d_rng + g0 * rb, d_rs, c->stream));
+		timer_begin(c, 2);
+		NXGPU_CUDA_OK(launch_checksum_ranges(d_rng + g0 * rb, (uint32_t)ng, d_prt + g0 * pb, 3, c->stream));
+		timer_end(c, 2);
+		NXGPU_CUDA_OK(launch_checksum_combine(d_rng + g0 * rb, d_prt + g0 * pb, d_rs, (uint32_t)ng, nullptr, nullptr, d_crc + g0, d_adler + g0, c->stream));
+		c->launches += 2;
+		if (mem == NXGPU_MEM_HOST && dst_contig) {
+			uint8_t *h0 = static_cast<uint8_t *>(items[g0].dst);
+			const uint64_t off = h0 - static_cast<uint8_t *>(items[0].dst);
+			const uint64_t span = (static_cast<uint8_t *>(items[g1 - 1].dst) - h0) + items[g1 - 1].dst_cap;
+			cudaStream_t cs = n_groups > 1 ? c->copy_stream : c->stream;
+			if (n_groups > 1) {
+				NXGPU_CUDA_OK(cudaEventRecord(c->ev_main, c->stream));
+				NXGPU_CUDA_OK(cudaStreamWaitEvent(cs, c->ev_main, 0));
+			}
+			NXGPU_CUDA_OK(cudaMemcpyAsync(h0, static_cast<uint8_t *>(c->d_out.p) + off, span, cudaMemcpyDeviceToHost, cs));
+		}
+	}
+	if (n_groups > 1) {
+		NXGPU_CUDA_OK(cudaEventRecord(c->ev_copy, c->copy_stream));
+		NXGPU_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+	}
 	if ((rc = c->h_outs.reserve(n * sizeof(InflateOut) + n * 8))) return rc;
 	InflateOut *oh = static_cast<InflateOut *>(c->h_outs.p);
 	uint32_t *ck = reinterpret_cast<uint32_t *>(oh + n);
 	NXGPU_CUDA_OK(cudaMemcpyAsync(oh, dout, n * sizeof(InflateOut), cudaMemcpyDeviceToHost, c->stream));
 	NXGPU_CUDA_OK(cudaMemcpyAsync(ck, d_crc, n * 8, cudaMemcpyDeviceToHost, c->stream));
-	if (mem == NXGPU_MEM_HOST && dst_contig) {
-		const uint64_t span = (static_cast<uint8_t *>(items[n - 1].dst) - static_cast<uint8_t *>(items[0].dst)) + items[n - 1].dst_cap;
-		NXGPU_CUDA_OK(cudaMemcpyAsync(items[0].dst, c->d_out.p, span, cudaMemcpyDeviceToHost, c->stream));
-	}
 	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
 	for (size_t i = 0; i < n; i++) {
 		nxgpu_inflate_result &r = results[i];
