@@ -58,15 +58,26 @@ def stitch_to_rank0(dist, torch, local: "torch.Tensor", local_size: int, local_c
     total = offs[-1] + 8
     crc = fold_crc32(combine, [r[1] for r in rows], [r[2] for r in rows])
     isize = sum(r[2] for r in rows) & 0xffffffff
+    batched = hasattr(dist, "batch_isend_irecv") and hasattr(dist, "P2POp")
     if rank != 0:
         if local_size:
-            dist.send(local[:local_size], dst=0)
+            if batched:
+                # one grouped launch per rank: NCCL runs the seven transfers into rank 0 concurrently instead of one
+                # after the other (unbatched point-to-point ops are serialised on the process group)
+                for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, local[:local_size], 0)]):
+                    q.wait()
+            else:
+                dist.send(local[:local_size], dst=0)
         return None, total, crc, isize
     if out is None or out.numel() < total:
         out = torch.empty(total, dtype=torch.uint8, device=local.device)
     out[:len(GZIP_HEADER)] = torch.tensor(list(GZIP_HEADER), dtype=torch.uint8, device=local.device)
     out[offs[0]:offs[1]].copy_(local[:sizes[0]])
-    reqs = [dist.irecv(out[offs[r]:offs[r + 1]], src=r) for r in range(1, world) if sizes[r]]
+    if batched:
+        ops = [dist.P2POp(dist.irecv, out[offs[r]:offs[r + 1]], r) for r in range(1, world) if sizes[r]]
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+    else:
+        reqs = [dist.irecv(out[offs[r]:offs[r + 1]], src=r) for r in range(1, world) if sizes[r]]
     for q in reqs:
         q.wait()
     trailer = list(crc.to_bytes(4, "little") + isize.to_bytes(4, "little"))
