@@ -112,10 +112,6 @@ __device__ __forceinline__ uint32_t hash5(const uint8_t *ring8, uint32_t pos)
 	const uint32_t b4 = __funnelshift_r(w1, w2, sh) & 0xffu;
 	return ((lo * 0x9E3779B1u) ^ (b4 * 0x85EBCA6Bu + (lo >> 15))) * 0x2545F491u >> (32 - kHashBits);
 }
-__device__ __forceinline__ uint32_t ring_byte(const uint8_t *ring8, uint32_t pos)
-{
-	return ring8[pos & kRingMask];
-}
 
 // ---- mbarrier + TMA bulk copy (global -> shared) ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

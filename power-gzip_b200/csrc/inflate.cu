@@ -304,7 +304,7 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 	uint32_t tr_crc = 0, tr_isize = 0, flags = 0;
 	// job mode: set when the source ran out (or the final EOB was seen); lane 0 holds the details
 	bool suspended = false;
-	uint32_t o_sfbt = 0, o_subc = 0, o_rem = 0, o_dhtlen = 0;
+	uint32_t o_sfbt = 0, o_subc = 0, o_rem = 0;
 	uint64_t dht_from = 0;           // where the current dynamic header starts (bit offset in dht_src)
 	uint32_t dht_len = 0;
 	bool dht_saved = false;          // the current dynamic table came from J.dht, not from the stream
@@ -693,7 +693,6 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 				}
 				J.out_dht[i] = (uint8_t)v;
 			}
-			o_dhtlen = dht_len;
 		}
 		if (lane == 0) {
 			if (!rc && !suspended) {
@@ -713,7 +712,6 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 			O.rembytecnt = o_rem;
 			O.dhtlen = in_dyn ? dht_len : 0;
 		}
-		(void)o_dhtlen;
 		return;
 	}
 
