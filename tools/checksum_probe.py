@@ -6,7 +6,7 @@ spec = importlib.util.spec_from_file_location("power_gzip_b200", os.path.join(RO
 pg = importlib.util.module_from_spec(spec); spec.loader.exec_module(pg)
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 n = 1 << lg
-data = os.urandom(1 << 20) * (n >> 20)
+data = (os.urandom(1 << 20) * max(1, n >> 20))[:n]
 eng = pg.Engine(0)
 d = eng.alloc(n); d.upload(data)
 for it in range(4):
