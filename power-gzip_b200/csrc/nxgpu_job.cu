@@ -388,6 +388,7 @@ void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 		js[i].host_off = res_bytes + data_total;
 		if (js[i].kind == JobState::COMP) data_total += align16(2 * (size_t)js[i].n_new + 2048);
 		else if (js[i].kind == JobState::DECOMP) data_total += align16(js[i].dst_total + 64);
+		else if (js[i].kind == JobState::WRAP) data_total += align16(js[i].src_total + 64);
 	}
 	if (c->h_outs.reserve(res_bytes + data_total + 64)) { fail_all(); return; }
 	uint8_t *ho = static_cast<uint8_t *>(c->h_outs.p);
@@ -470,7 +471,9 @@ void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 			continue;
 		j.ck = items.size();
 		if (j.kind == JobState::WRAP) {
+			// the copy goes through the engine like every other function code: up with the batch, back from the device
 			items.push_back({ d_in + j.in_off, j.src_total, 0, 1 });
+			if (j.src_total && cudaMemcpyAsync(ho + j.host_off, d_in + j.in_off, j.src_total, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { fail_all(); return; }
 		} else if (j.kind == JobState::COMP) {
 			items.push_back({ dj[j.idx].src, j.n_new, j.crc_seed, j.adler_seed });
 			const uint8_t *from = j.np > 1 ? static_cast<const uint8_t *>(c->d_cat.p) + j.cat_off : dj[j.idx].out;
@@ -500,7 +503,7 @@ void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 		put_be32(cpb + NXGPU_CPB_OUT_ADLER - NXGPU_CPB, ck[nck + j.ck]);
 		put_le32(cpb + NXGPU_CPB_OUT_CRC - NXGPU_CPB, ck[j.ck]);
 		if (j.kind == JobState::WRAP) {
-			scatter(j.dst, hs + j.in_off, j.src_total);
+			scatter(j.dst, ho + j.host_off, j.src_total);
 			put_be32(cpb + NXGPU_CPB_OUT_SPBC_COMP - NXGPU_CPB, (uint32_t)j.src_total);
 			complete(j.crb, 0, 0, (uint32_t)j.src_total);
 		} else if (j.kind == JobState::COMP) {
