@@ -474,7 +474,7 @@ def main():
     if rank == 0 and world == 1 and not args.skip_extra:
         # ---- many concurrent small z_streams through the UNCHANGED zlib surface (configs[4]): the reference's host
         # code over the GPU engine, test/test_multithread_stress.c pattern; descriptors coalesce inside nxu_run_job ----
-        gpu_nxz = os.path.join(ROOT, "oracle", "_ref", "libnxz_gpu.so")
+        gpu_nxz = os.path.join(ROOT, "power-gzip_b200", "libnxz_gpu.so")
         if os.path.exists(gpu_nxz):
             import subprocess
             try:

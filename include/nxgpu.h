@@ -243,6 +243,9 @@ typedef struct {
 	uint32_t flags;        /* bit0: final block seen; bit1: trailer verified;
 	                          bit2: source ended on a block boundary, no final block (rc = NXGPU_E_DATA) */
 } nxgpu_inflate_result;
+/* NXGPU_MEM_HOST: when the items' targets lie back to back in one host buffer the outputs return in a few large
+ * copies, so the bytes of dst[out_len .. dst_cap) of every item are UNSPECIFIED after the call (as are all dst_cap
+ * bytes of an item whose rc != 0); only dst[0 .. out_len) is the result. */
 int nxgpu_inflate_batch(nxgpu_ctx *ctx, const nxgpu_inflate_item *items, size_t n,
 			nxgpu_inflate_result *results, int mem);
 

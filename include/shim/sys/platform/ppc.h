@@ -1,6 +1,6 @@
-/* x86 stand-in for glibc's POWER-only <sys/platform/ppc.h>, so the reference's
- * host code (inc_nx/nxu.h:63, lib/nx_zlib.h:56) compiles in place for oracle/_ref.
- * Test infrastructure only. */
+/* x86 stand-in for glibc's POWER-only <sys/platform/ppc.h>: the one header the reference's host
+ * code (inc_nx/nxu.h:63, lib/nx_zlib.h:56) needs to compile unmodified on the B200 box's host
+ * (INTEGRATION.md).  The timebase is the 512 MHz tick the library's wait loops are written for. */
 #ifndef NXGPU_SHIM_PPC_H
 #define NXGPU_SHIM_PPC_H
 #include <stdint.h>

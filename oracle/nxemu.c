@@ -219,7 +219,7 @@ int oracle_nxemu_run_job(void *crb_cpb)
 	int ret = 0;
 	uint8_t *in = NULL, *out = NULL;
 	if (dde_segments(crb + NXGPU_CRB_SRC_DDE, src) || dde_segments(crb + NXGPU_CRB_DST_DDE, dst)) {
-		complete(crb, 9, 2, 0);
+		complete(crb, 30, 2, 0);                 /* ERR_NX_INVALID_DDE, inc_nx/nxu.h:843 */
 		goto done;
 	}
 	const uint32_t w8 = be32(cpb + 8), w12 = be32(cpb + 12);
@@ -276,11 +276,15 @@ int oracle_nxemu_run_job(void *crb_cpb)
 		scatter(dst, out + hist, j.out_len);
 		put_be32(cpb + 384, oracle_adler32(adler_seed, out + hist, j.out_len));
 		put_le32(cpb + 388, oracle_crc32(crc_seed, out + hist, j.out_len));
-		put_be32(cpb + 392, j.out_subc & 0xffff);
+		if (j.out_subc > 0xffff) abort();          /* SUBC is a 16-bit field and never wraps (Table 5-3 bounds) */
+		put_be32(cpb + 392, j.out_subc);
 		const int in_dyn = (j.out_sfbt & 0xe) == 0xc;
 		put_be32(cpb + 396, (j.out_sfbt & 0xf) << 16 | (in_dyn ? (j.out_dhtlen & 0xfff) : (j.out_rembytecnt & 0xffff)));
 		if (in_dyn) memcpy(cpb + 400, j.out_dht, 288);
-		put_be32(cpb + 688, (uint32_t)src->total);
+		put_be32(cpb + 688, (uint32_t)(hist + j.src_read));
+		/* Always CC=3 + "partial completion" (manual Table 5-3 allows it for every row; the one CC=0 row -
+		 * final block, no byte of source behind it - is a case the host code does not finish a stream on:
+		 * lib/nx_inflate.c:1426-1436 takes no is_final from it) */
 		complete(crb, 3, 4 | 1, (uint32_t)j.out_len);
 	}
 done:

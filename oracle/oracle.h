@@ -40,6 +40,7 @@ enum {
 	ORA_SFBT_FINAL_EOB = 0x0,
 	ORA_SFBT_LIT = 0x8, ORA_SFBT_FHT = 0xa, ORA_SFBT_DHT = 0xc, ORA_SFBT_HDR = 0xe
 };
+#define ORA_READ_AHEAD 8
 typedef struct {
 	/* in */
 	const uint8_t *src; size_t src_len;     /* compressed bytes (no history)        */
@@ -52,6 +53,9 @@ typedef struct {
 	int single_block;                       /* stop after one block (FC 0x12/0x16)   */
 	/* out */
 	size_t out_len;                         /* tpbc                                  */
+	size_t src_read;                        /* source bytes the engine read (spbc - history): all of it when
+	                                           the source ran out, else at most ORA_READ_AHEAD bytes behind
+	                                           the last processed bit                                     */
 	uint64_t bits_used;                     /* from bit 0 of src[0]                  */
 	unsigned out_sfbt, out_subc, out_rembytecnt;
 	uint8_t out_dht[288]; unsigned out_dhtlen;

@@ -187,7 +187,7 @@ int oracle_inflate_run(oracle_inflate_job *j)
 	int rc;
 
 	j->out_len = 0; j->bits_used = b.bp; j->out_sfbt = 0; j->out_subc = 0; j->out_rembytecnt = 0;
-	j->out_dhtlen = 0; j->final_seen = 0; j->err = 0;
+	j->out_dhtlen = 0; j->final_seen = 0; j->err = 0; j->src_read = j->src_len;
 
 	if (b.bp > b.nbits) { j->err = 3; return 3; }
 
@@ -319,15 +319,21 @@ int oracle_inflate_run(oracle_inflate_job *j)
 		}
 		/* end of block */
 		kind = 0;
-		if (bfinal) {
-			j->final_seen = 1;
-			j->out_sfbt = ORA_SFBT_FINAL_EOB;
-			j->out_subc = (unsigned)(b.nbits - b.bp);
-			break;
-		}
-		if (j->single_block || b.bp == b.nbits) {
-			j->out_sfbt = ORA_SFBT_HDR;
-			j->out_subc = (unsigned)(b.nbits - b.bp);
+		if (bfinal || j->single_block || b.bp == b.nbits) {
+			/* The engine stops by itself here, with source possibly left.  The manual (§2.4): "SPBC
+			 * indicates the number of compressed source bytes READ by the accelerator, SUBC the number of
+			 * source bits that the accelerator discarded because they were past the stream end" - a gzip
+			 * trailer gives SUBC 64..71, a zlib trailer 32..39 (inc_nx/nxu.h:454-465).  Model: the engine
+			 * has read at most 8 bytes behind the byte that holds the last processed bit; the host
+			 * computes the stream end as spbc - histlen - subc/8 (lib/nx_inflate.c:1452-1472). */
+			uint64_t end_byte = (b.bp + 7) >> 3, rd = end_byte + ORA_READ_AHEAD;
+			if (rd > j->src_len) rd = j->src_len;
+			j->src_read = (size_t)rd;
+			j->out_subc = (unsigned)(rd * 8 - b.bp);
+			j->final_seen = bfinal ? 1 : 0;
+			/* Table 5-3: 0000 final EOB; 1110 a block with BFINAL=0 ended (single-block suspend, or the
+			 * source ended exactly on the block boundary) */
+			j->out_sfbt = bfinal ? ORA_SFBT_FINAL_EOB : ORA_SFBT_HDR;
 			break;
 		}
 	}

@@ -315,7 +315,7 @@ __global__ void ranges_from_inflate_kernel(const InflateJob *jobs, const Inflate
 		rs[i] = i;
 }
 
-bool g_tables_ready = false;
+PerDeviceOnce g_tables_once;
 
 uint32_t host_x8n(uint64_t n, const uint32_t *x2n)
 {
@@ -346,11 +346,9 @@ void make_shift_table(uint32_t op, uint32_t out[4][256])
 
 } // namespace
 
-cudaError_t checksum_init_tables()
+static cudaError_t upload_tables()
 {
-	if (g_tables_ready)
-		return cudaSuccess;
-	static CkTables T;
+	static CkTables T;            // the caller holds g_tables_once's lock
 	static CkConst C;
 	for (uint32_t n = 0; n < 256; n++) {
 		uint32_t c = n;
@@ -382,9 +380,10 @@ cudaError_t checksum_init_tables()
 	if (e != cudaSuccess) return e;
 	e = cudaFuncSetAttribute(checksum_ranges_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CkSmem));
 	if (e != cudaSuccess) return e;
-	g_tables_ready = true;
 	return cudaSuccess;
 }
+
+cudaError_t checksum_init_tables() { return g_tables_once.run(upload_tables); }
 
 size_t checksum_range_bytes() { return sizeof(Range); }
 size_t checksum_partial_bytes() { return sizeof(Partial); }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 
 namespace nxgpu {
 
@@ -84,17 +85,19 @@ struct InflateJob {
 	uint32_t start_bit;     // bits of src[0] already consumed (0..7)
 	uint32_t sfbt;          // 0xxx fresh block header; 100x stored, 101x fixed, 110x dynamic; bit0 = BFINAL
 	uint32_t rembytecnt;    // stored bytes still to copy (sfbt 100x)
+	uint32_t single_block;  // FC 0x12 / 0x16: suspend at the end of the first block that completes
+	uint32_t pad_;
 };
 struct InflateOut {
 	int32_t rc;             // job mode: NX completion code (0/3 ok, 13 target full, 66/67/68 data)
 	uint32_t out_len;
-	uint32_t in_used;
+	uint32_t in_used;       // job mode: source bytes the engine READ (SPBC minus history, manual §2.4)
 	uint32_t flags;
 	uint32_t trailer_crc;   // from the stream (gzip) / adler (zlib)
 	uint32_t trailer_isize;
 	// --- NX job mode ---
 	uint32_t sfbt;          // manual Table 5-3 / 6-4
-	uint32_t subc;          // source bits supplied but not processed
+	uint32_t subc;          // source bits read but not processed (16-bit field: Table 5-3 bounds it by 2285)
 	uint32_t rembytecnt;
 	uint32_t dhtlen;        // valid bits in out_dht
 	uint32_t reserved[2];
@@ -137,6 +140,29 @@ struct StreamOut {
 	uint64_t base = 0;                    // bytes of container header in front of chunk 0
 	uint64_t *offsets = nullptr;          // n + 1 entries: start of every chunk, end of the last
 	unsigned long long *chain = nullptr;  // n entries, zeroed before the launch
+};
+
+// One-time setup that CUDA keeps PER DEVICE (cudaFuncSetAttribute, __device__ / __constant__ symbol uploads): a process may
+// open contexts on several GPUs (nx_function_begin maps pri % ndev), so "done" is tracked per device ordinal, under a lock.
+struct PerDeviceOnce {
+	std::mutex m;
+	bool done[64] = {};
+	template <class F> cudaError_t run(F f)
+	{
+		int dev = 0;
+		cudaError_t e = cudaGetDevice(&dev);
+		if (e != cudaSuccess)
+			return e;
+		std::lock_guard<std::mutex> g(m);
+		if (dev < 0 || dev >= 64)
+			return f();
+		if (done[dev])
+			return cudaSuccess;
+		e = f();
+		if (e == cudaSuccess)
+			done[dev] = true;
+		return e;
+	}
 };
 
 // kernel launchers (defined in the .cu files)

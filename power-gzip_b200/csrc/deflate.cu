@@ -1529,13 +1529,10 @@ dhtgen_kernel(const uint32_t *__restrict__ counts, uint32_t n, uint8_t *__restri
 
 cudaError_t launch_dhtgen(const uint32_t *counts, uint32_t n, uint8_t *dht_out, uint32_t *dht_bits, cudaStream_t s)
 {
-	static bool configured = false;
-	if (!configured) {
-		cudaError_t e = cudaFuncSetAttribute(dhtgen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-		if (e != cudaSuccess)
-			return e;
-		configured = true;
-	}
+	static PerDeviceOnce once;
+	cudaError_t e0 = once.run([] { return cudaFuncSetAttribute(dhtgen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)); });
+	if (e0 != cudaSuccess)
+		return e0;
 	dhtgen_kernel<<<n < (uint32_t)kNumSMs ? n : kNumSMs, kThreads, sizeof(Smem), s>>>(counts, n, dht_out, dht_bits);
 	return cudaGetLastError();
 }
@@ -1547,13 +1544,10 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 			   uint32_t *tok_scratch, uint32_t tok_stride, int grid, cudaStream_t s,
 			   uint32_t *job_counter, const uint32_t *ready, uint32_t jobs_per_flag, const StreamOut *so)
 {
-	static bool configured = false;
-	if (!configured) {
-		cudaError_t e = cudaFuncSetAttribute(deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-		if (e != cudaSuccess)
-			return e;
-		configured = true;
-	}
+	static PerDeviceOnce once;
+	cudaError_t e0 = once.run([] { return cudaFuncSetAttribute(deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)); });
+	if (e0 != cudaSuccess)
+		return e0;
 	LevelParams lp = level_params(level);
 	if (const char *ov = getenv("NXGPU_LZ_PARAMS")) {         // developer override: "depth,lazy,nice"
 		int a, b, c;

@@ -22,6 +22,7 @@ namespace {
 constexpr int kWarpsPerCta = 4;
 constexpr int kLitBits = 10, kDistBits = 9;
 constexpr uint32_t kInWords = 128;         // per-warp staging ring for the compressed input (512 B)
+constexpr uint32_t kReadAhead = 8;         // job mode: source bytes the engine has read behind the point where it stopped by itself
 constexpr uint32_t kInAhead = 64;          // the warp tops the ring up while fewer words than this lie ahead
 
 struct WarpTables {
@@ -304,6 +305,7 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 	uint32_t tr_crc = 0, tr_isize = 0, flags = 0;
 	// job mode: set when the source ran out (or the final EOB was seen); lane 0 holds the details
 	bool suspended = false;
+	bool self_stop = false;          // stopped at the end of a BFINAL=0 block with nothing decoded behind it
 	uint32_t o_sfbt = 0, o_subc = 0, o_rem = 0;
 	uint64_t dht_from = 0;           // where the current dynamic header starts (bit offset in dht_src)
 	uint32_t dht_len = 0;
@@ -347,7 +349,17 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 	rc = __shfl_sync(0xffffffffu, rc, 0);
 
 	bool final_block = false;
+	bool block_ended = false;
 	while (!rc && !final_block && !suspended) {
+		if (job && block_ended) {
+			// A block with BFINAL=0 just ended.  Manual Table 5-3, SFBT 1110: the engine suspends here by
+			// itself for the single-block function codes (inc_nx/nxu.h:813,815), and also when the source
+			// ends exactly on the block boundary (SUBC=0, "the next byte will contain a block header").
+			if (J.single_block != 0 || __shfl_sync(0xffffffffu, (int)(br.bits_used() == total_bits), 0) != 0) {
+				self_stop = true;
+				break;
+			}
+		}
 		// ---- block header (lane 0) ----
 		uint32_t btype = 0, stored_len = 0, stored_at = 0;
 		int hlit = 0, hdist = 0;
@@ -440,6 +452,7 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 			if (lane == 0)
 				br.seek(stored_at + stored_len);
 			__syncwarp();
+			block_ended = true;
 			continue;
 		}
 
@@ -669,6 +682,7 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 		}
 		if (suspended)
 			final_block = false;
+		block_ended = true;
 	}
 
 	if (job) {
@@ -695,15 +709,26 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 			}
 		}
 		if (lane == 0) {
+			uint32_t src_read = J.src_len;      // the source ran out: all of it was read
 			if (!rc && !suspended) {
-				// final EOB seen: sfbt 0000, subc = bits supplied behind it
-				o_sfbt = 0;
-				o_subc = (uint32_t)(total_bits - br.bits_used());
-				flags |= 1;
+				// The engine stopped by itself - final EOB (sfbt 0000) or the end of a BFINAL=0 block (1110) -
+				// with source possibly left.  "SPBC indicates the number of compressed source bytes read by the
+				// accelerator, SUBC the number of source bits that the accelerator discarded because they were
+				// past the stream end" (manual §2.4): a gzip trailer reads as SUBC 64..71, a zlib one as 32..39
+				// (inc_nx/nxu.h:454-465).  The engine has read at most kReadAhead bytes behind the byte holding
+				// the last processed bit; the host finds the stream end at spbc - histlen - subc/8
+				// (lib/nx_inflate.c:1452-1472).  SUBC is a 16-bit field: counting everything supplied wraps it.
+				const uint64_t used = br.bits_used();
+				uint64_t rd = ((used + 7) >> 3) + kReadAhead;
+				if (rd > J.src_len) rd = J.src_len;
+				src_read = (uint32_t)rd;
+				o_sfbt = self_stop ? 0xe : 0;
+				o_subc = (uint32_t)(rd * 8 - used);
+				if (!self_stop) flags |= 1;
 			}
 			O.rc = rc;
 			O.out_len = out;
-			O.in_used = J.src_len;
+			O.in_used = src_read;
 			O.flags = flags | (wrap << 8);
 			O.trailer_crc = 0;
 			O.trailer_isize = 0;
@@ -798,15 +823,12 @@ cudaError_t launch_gzip_candidates(const uint8_t *src, uint64_t len, uint64_t *c
 template <int kMinCtas>
 static cudaError_t launch_inflate_t(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s)
 {
-	static bool configured = false;
+	static PerDeviceOnce once;
 	const size_t smem = sizeof(WarpTables) * kWarpsPerCta;
-	if (!configured) {
-		cudaError_t e = cudaFuncSetAttribute(inflate_kernel<kMinCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess)
-			return e;
-		configured = true;
-	}
-	cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
+	cudaError_t e = once.run([smem] { return cudaFuncSetAttribute(inflate_kernel<kMinCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+	if (e != cudaSuccess)
+		return e;
+	e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
 	if (e != cudaSuccess)
 		return e;
 	// persistent grid: as many CTAs as fit an SM (registers and shared memory allow kMinCtas)

@@ -134,6 +134,7 @@ int nxgpu_open(int dev, nxgpu_ctx **out)
 	}
 	nxgpu_ctx *c = new nxgpu_ctx();
 	c->dev = dev;
+	struct OpenGuard { nxgpu_ctx *c; ~OpenGuard() { if (c) nxgpu_close(c); } } open_guard{ c };    // no leak on the error returns below
 	NXGPU_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	NXGPU_CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 	NXGPU_CUDA_OK(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
@@ -141,6 +142,7 @@ int nxgpu_open(int dev, nxgpu_ctx **out)
 	NXGPU_CUDA_OK(cudaEventCreate(&c->t0));
 	NXGPU_CUDA_OK(cudaEventCreate(&c->t1));
 	NXGPU_CUDA_OK(checksum_init_tables());
+	open_guard.c = nullptr;
 	*out = c;
 	return 0;
 }
@@ -435,6 +437,9 @@ int nxgpu_deflate_batch(nxgpu_ctx *c, const nxgpu_deflate_item *items, size_t n,
 	if (!c || (!items && n) || (!results && n)) return NXGPU_E_ARG;
 	NXGPU_LOCK(c);
 	if (n == 0) return 0;
+	// per-item sizes are 32-bit; the worst-case slot (2 x source + 1 KiB) must stay below 4 GiB too
+	for (size_t i = 0; i < n; i++)
+		if (items[i].src_len > 0x7fff0000u) { set_error("item %zu: src_len %u exceeds the 2 GiB item limit", i, items[i].src_len); return NXGPU_E_ARG; }
 	NXGPU_CUDA_OK(cudaSetDevice(c->dev));
 	int rc;
 	if ((rc = c->h_jobs.reserve(n * sizeof(DeflateJob)))) return rc;
@@ -524,6 +529,8 @@ int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *
 {
 	if (!c || (!src && src_len) || !dst || !res) return NXGPU_E_ARG;
 	NXGPU_LOCK(c);
+	// whatever path leaves this function, the next launch on the context must not wait on this call's upload flags
+	struct FlagGuard { nxgpu_ctx *c; ~FlagGuard() { c->ready_flags = nullptr; } } flag_guard{ c };
 	// true Z_FULL_FLUSH semantics: no chunk looks back into the previous one, so the chunks of the
 	// index can be inflated in parallel (nxgpu_inflate_stream)
 	const bool independent = (wrap & NXGPU_STREAM_INDEPENDENT) != 0;

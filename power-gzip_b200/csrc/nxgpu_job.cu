@@ -229,7 +229,7 @@ void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 		j.cpb = j.crb + NXGPU_CPB;
 		j.fc = be32(j.crb + NXGPU_CRB_FC) & 0xff;
 		if (!dde_segments(j.crb + NXGPU_CRB_SRC_DDE, j.src, j.src_total) || !dde_segments(j.crb + NXGPU_CRB_DST_DDE, j.dst, j.dst_total)) {
-			complete(j.crb, 9 /* ERR_NX_BAD_DDE */, CE_TERMINATE, 0);
+			complete(j.crb, 30 /* ERR_NX_INVALID_DDE, inc_nx/nxu.h:843 */, CE_TERMINATE, 0);
 			continue;
 		}
 		if (j.src_total > 0xffffff00ull || j.dst_total > 0xffffff00ull) {
@@ -358,6 +358,7 @@ void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 			job.start_bit = (8 - in_subc) & 7;
 			job.sfbt = sfbt;
 			job.rembytecnt = w12 & 0xffff;
+			job.single_block = (j.fc & 0x02) != 0;      // GZIP_FC_DECOMPRESS[_RESUME]_SINGLE_BLK_N_SUSPEND
 			job.out_dht = d_dht + i * 1024 + 640;
 			if ((sfbt & 0xe) == 0xc) {
 				job.dht_bits = w12 & 0xfff;
@@ -530,12 +531,13 @@ void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 		} else {
 			const InflateOut &o = iout[j.idx];
 			scatter(j.dst, ho + j.host_off, o.out_len);
-			put_be32(cpb + NXGPU_CPB_OUT_TEBC - NXGPU_CPB, o.subc & 0xffff);                   // out_subc: low half of this word
+			put_be32(cpb + NXGPU_CPB_OUT_TEBC - NXGPU_CPB, o.subc > 0xffff ? 0xffff : o.subc);  // out_subc: low half of this word; never wraps
 			const bool in_dyn = (o.sfbt & 0xe) == 0xc;
 			put_be32(cpb + NXGPU_CPB_OUT_SFBT - NXGPU_CPB, (o.sfbt & 0xf) << 16 | (in_dyn ? (o.dhtlen & 0xfff) : (o.rembytecnt & 0xffff)));
 			if (in_dyn)
 				memcpy(cpb + NXGPU_CPB_OUT_DHT - NXGPU_CPB, odht + i * 288, 288);
-			put_be32(cpb + NXGPU_CPB_OUT_SPBC_DECOMP - NXGPU_CPB, (uint32_t)j.src_total);
+			// source bytes the engine read, history included (inc_nx/nxu.h:454-465, lib/nx_inflate.c:1452-1472)
+			put_be32(cpb + NXGPU_CPB_OUT_SPBC_DECOMP - NXGPU_CPB, j.hist + o.in_used);
 			// CC=3 with CE "partial completion" is the normal way a decompress job ends (lib/nx_inflate.c:1372-1390)
 			complete(j.crb, 3, CE_PARTIAL | CE_TPBC_VALID, o.out_len);
 		}

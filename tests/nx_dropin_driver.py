@@ -4,7 +4,7 @@ uncompress / deflate / inflate / crc32 / adler32) in NX mode (NX_GZIP_TYPE_SELEC
 build of its host code whose six boundary symbols come from either engine:
 
     oracle/_ref/libnxz_ref.so   nxu_run_job = oracle/nxemu.c (CPU, the checker)
-    oracle/_ref/libnxz_gpu.so   nxu_run_job = power-gzip_b200/libnxgpu.so (the product)
+    power-gzip_b200/libnxz_gpu.so   nxu_run_job = power-gzip_b200/libnxgpu.so (the product)
 
 Run as a subprocess (the selector is read when the library is loaded).  Prints one JSON line.
 Mirrors the round trips of the reference's test/test_deflate.c and test/test_inflate.c: output of
@@ -264,6 +264,68 @@ def dictionary_roundtrip(data, dictionary):
     return sizes[15]
 
 
+def trailing_data(data):
+    """Bytes BEHIND the end of a stream inside the same job (concatenated gzip members, a tar of .gz, PNG chunks, HTTP):
+    the engine reports the source bytes it read (SPBC) and the bits behind the final end-of-block it discarded (SUBC,
+    16 bits wide; 32..39 / 64..71 for a bare zlib / gzip trailer, inc_nx/nxu.h:454-465) and the host finds the trailer at
+    spbc - histlen - subc/8 (lib/nx_inflate.c:1452-1472).  Round 1 counted everything supplied in SUBC, which wrapped
+    at 8 KiB.  Done = Z_STREAM_END with total_in == the stream's own length for 0 .. 100 000 appended bytes."""
+    rnd = random.Random(11)
+    checked = 0
+    for wbits, blob in ((15, zlib.compress(data, 6)), (31, gzip.compress(data, 6)), (-15, zlib.compress(data, 6)[2:-4])):
+        for extra in (0, 1, 7, 8, 9, 100, 8100, 8191, 8192, 8193, 8300, 9000, 20000, 65536, 70000, 100000):
+            buf = blob + rnd.randbytes(extra)
+            for hold_back in (0, 300):
+                if hold_back >= len(blob):
+                    continue
+                s = ZStream()
+                assert lib.inflateInit2_(C.byref(s), wbits, VER, C.sizeof(ZStream)) == 0
+                src = C.create_string_buffer(buf, len(buf))
+                out = C.create_string_buffer(len(data) + 64)
+                s.next_out, s.avail_out = C.addressof(out), len(out)
+                first = len(blob) - hold_back if hold_back else len(buf)
+                s.next_in, s.avail_in = C.addressof(src), first
+                rc = lib.inflate(C.byref(s), Z_NO_FLUSH)
+                guard = 0
+                while rc == Z_OK and guard < 100:
+                    if s.avail_in == 0 and first < len(buf):
+                        s.next_in, s.avail_in = C.addressof(src) + first, len(buf) - first
+                        first = len(buf)
+                    rc = lib.inflate(C.byref(s), Z_NO_FLUSH)
+                    guard += 1
+                assert rc == Z_STREAM_END, f"wbits {wbits}, {extra} bytes behind the stream, hold back {hold_back}: rc {rc}, total_in {s.total_in}"
+                # a second piece below cache_threshold (8 KiB) is swallowed whole into fifo_in by the host code before
+                # any job runs (lib/nx_inflate.c:1197-1205): total_in then counts it, on any engine
+                if hold_back == 0 or hold_back + extra >= 8192:
+                    assert s.total_in == len(blob), f"wbits {wbits}, {extra} trailing: total_in {s.total_in} != {len(blob)}"
+                assert out.raw[: s.total_out] == data
+                lib.inflateEnd(C.byref(s))
+                checked += 1
+    # concatenated gzip members in one buffer, inflateReset between them (what gunzip does with `cat a.gz b.gz`)
+    lib.inflateReset.argtypes = [C.POINTER(ZStream)]
+    parts = [data[:50000], data[50000:50010], b"", data[60000:]]
+    cat = b"".join(gzip.compress(p, 6) for p in parts)
+    src = C.create_string_buffer(cat, len(cat))
+    out = C.create_string_buffer(len(data) + 64)
+    s = ZStream()
+    assert lib.inflateInit2_(C.byref(s), 31, VER, C.sizeof(ZStream)) == 0
+    s.next_in, s.avail_in = C.addressof(src), len(cat)
+    got = []
+    for k in range(len(parts)):
+        s.next_out, s.avail_out = C.addressof(out), len(out)
+        before = s.avail_out
+        rc, guard = Z_OK, 0
+        while rc == Z_OK and guard < 100:
+            rc = lib.inflate(C.byref(s), Z_NO_FLUSH)
+            guard += 1
+        assert rc == Z_STREAM_END, f"member {k}: rc {rc}"
+        got.append(out.raw[: before - s.avail_out])
+        assert lib.inflateReset(C.byref(s)) == 0
+    assert got == parts and s.avail_in == 0, "concatenated members do not come back one by one"
+    lib.inflateEnd(C.byref(s))
+    return checked
+
+
 def zero_input_and_reset(data):
     """test/test_zeroinput.c:39-60: an empty stream finished with every flush mode must be a valid zlib stream of zero
     bytes; test/test_reset.c:69-140: deflateReset / inflateReset give a stream that works again, several times."""
@@ -392,6 +454,8 @@ for name, data in cases.items():
     report["cases"][name] = r
 print("zero input, reset", file=sys.stderr, flush=True)
 report["zero_input_and_reset"] = zero_input_and_reset(alice[:70000])
+print("trailing data", file=sys.stderr, flush=True)
+report["trailing_data"] = trailing_data(alice)
 print("dictionary", file=sys.stderr, flush=True)
 # sizes: one job, and a first job that yields more than the 32 KiB window — the reference's host code hands the
 # dictionary to the first decompress job only (lib/nx_inflate.c:1711-1712), whatever engine sits below it

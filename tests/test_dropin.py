@@ -21,7 +21,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DRIVER = os.path.join(ROOT, "tests", "nx_dropin_driver.py")
 REF_CPU = os.path.join(ROOT, "oracle", "_ref", "libnxz_ref.so")
-REF_GPU = os.path.join(ROOT, "oracle", "_ref", "libnxz_gpu.so")
+REF_GPU = os.path.join(ROOT, "power-gzip_b200", "libnxz_gpu.so")
 
 
 def _drive(lib, log2):
@@ -40,7 +40,7 @@ def test_reference_host_code_over_cpu_engine():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.path.exists(REF_GPU), reason="oracle/_ref/libnxz_gpu.so not built (needs /root/reference at build time)")
+@pytest.mark.skipif(not os.path.exists(REF_GPU), reason="power-gzip_b200/libnxz_gpu.so not built (needs /root/reference at build time)")
 def test_reference_host_code_over_gpu_engine():
     rep = _drive(REF_GPU, 20)
     # the GPU engine's jobs compress for real: the reference's compress2 over it lands near zlib
@@ -63,7 +63,7 @@ def test_multithread_stress_over_cpu_engine():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.path.exists(REF_GPU), reason="oracle/_ref/libnxz_gpu.so not built (needs /root/reference at build time)")
+@pytest.mark.skipif(not os.path.exists(REF_GPU), reason="power-gzip_b200/libnxz_gpu.so not built (needs /root/reference at build time)")
 def test_multithread_stress_is_coalesced_on_the_gpu():
     # descriptors from concurrent z_streams share GPU launches, results stay per stream
     rep = _stress(REF_GPU, 32, 2)
@@ -76,62 +76,7 @@ def test_multithread_stress_is_coalesced_on_the_gpu():
 # ---------------------------------------------------------------------------------------------
 # single descriptors
 # ---------------------------------------------------------------------------------------------
-def _be32(v):
-    return int(v).to_bytes(4, "big")
-
-
-class Job:
-    """A 2048-byte nx_gzip_crb_cpb_t (inc_nx/nxu.h:286-616) with direct or indirect DDEs."""
-
-    def __init__(self, fc, src_parts, dst_cap, histlen_qw=0, subc=0, sfbt=0, rem_or_dhtlen=0, dht=b"", crc=0, adler=1, split_dst=False):
-        raw = C.create_string_buffer(2048 + 2048)
-        base = (C.addressof(raw) + 2047) & ~2047
-        self.keep = [raw]
-        self.buf = (C.c_uint8 * 2048).from_address(base)
-        self.addr = base
-        self.put(0, _be32(fc))
-        self.put(8, (base + 240).to_bytes(8, "big"))
-        self.srcs = [C.create_string_buffer(p, len(p)) for p in src_parts]
-        self.dst_bufs = [C.create_string_buffer(dst_cap // 2 + 1), C.create_string_buffer(dst_cap - dst_cap // 2 - 1)] if split_dst and dst_cap > 2 \
-            else [C.create_string_buffer(max(dst_cap, 1))]
-        self.dst_caps = [dst_cap // 2 + 1, dst_cap - dst_cap // 2 - 1] if split_dst and dst_cap > 2 else [dst_cap]
-        self.dde(16, [(C.addressof(b), len(p)) for b, p in zip(self.srcs, src_parts)])
-        self.dde(32, [(C.addressof(b), n) for b, n in zip(self.dst_bufs, self.dst_caps)])
-        self.put(256 + 0, _be32(adler))
-        self.put(256 + 4, int(crc).to_bytes(4, "little"))
-        self.put(256 + 8, _be32((histlen_qw & 0xfff) << 20 | (subc & 7)))
-        self.put(256 + 12, _be32((sfbt & 0xf) << 16 | (rem_or_dhtlen & 0xffff)))
-        self.put(256 + 16, dht[:288])
-
-    def put(self, off, b):
-        for i, x in enumerate(b):
-            self.buf[off + i] = x
-
-    def get(self, off, n):
-        return bytes(self.buf[off:off + n])
-
-    def dde(self, off, segs):
-        if len(segs) == 1:
-            self.put(off, _be32(0) + _be32(segs[0][1]) + segs[0][0].to_bytes(8, "big"))
-            return
-        lst = C.create_string_buffer(16 * len(segs))
-        self.keep.append(lst)
-        for i, (a, n) in enumerate(segs):
-            C.memmove(C.addressof(lst) + 16 * i, _be32(0) + _be32(n) + a.to_bytes(8, "big"), 16)
-        self.put(off, _be32(len(segs) << 8) + _be32(sum(n for _, n in segs)) + C.addressof(lst).to_bytes(8, "big"))
-
-    # outputs
-    def cc(self): return self.buf[240 + 2]
-    def ce(self): return self.buf[240 + 3] >> 5
-    def valid(self): return self.buf[240] >> 7
-    def tpbc(self): return int.from_bytes(self.get(244, 4), "big")
-    def out(self): return b"".join(b.raw[:n] for b, n in zip(self.dst_bufs, self.dst_caps))[: self.tpbc()]
-    def crc(self): return int.from_bytes(self.get(256 + 388, 4), "little")
-    def adler(self): return int.from_bytes(self.get(256 + 384, 4), "big")
-    def w392(self): return int.from_bytes(self.get(256 + 392, 4), "big")
-    def w396(self): return int.from_bytes(self.get(256 + 396, 4), "big")
-    def spbc_decomp(self): return int.from_bytes(self.get(256 + 688, 4), "big")
-    def spbc_comp(self, count): return int.from_bytes(self.get(256 + (1664 if count else 400), 4), "big")
+from nxjob import Job  # noqa: E402  (tests/nxjob.py: the 2048-byte descriptor)
 
 
 @pytest.fixture(scope="module")
@@ -454,7 +399,7 @@ def test_large_compress_descriptors_are_cut_into_pieces(engines, pg, alice):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.path.exists(REF_GPU), reason="oracle/_ref/libnxz_gpu.so not built (needs /root/reference at build time)")
+@pytest.mark.skipif(not os.path.exists(REF_GPU), reason="power-gzip_b200/libnxz_gpu.so not built (needs /root/reference at build time)")
 def test_ld_preload_puts_an_unmodified_program_on_the_gpu():
     """reference README.md:9-18: LD_PRELOAD libnxz under an unmodified zlib user — here CPython's own zlib module."""
     code = (
@@ -475,3 +420,68 @@ def test_ld_preload_puts_an_unmodified_program_on_the_gpu():
     size, descriptors = (int(x) for x in p.stdout.split()[-2:])
     assert descriptors >= 4 and size < 80000, (size, descriptors)
     # the same program without the preload inflates what the GPU wrote (checked inside), and system zlib agrees on the data
+
+
+# ---------------------------------------------------------------------------------------------
+# north star: "deflate output must be a valid stream that both system zlib and libnxz's own inflate decode"
+# ---------------------------------------------------------------------------------------------
+_NX_INFLATE_CHILD = r"""
+import ctypes as C, os, sys, json
+os.environ["NX_GZIP_TYPE_SELECTOR"] = "2"
+os.environ.setdefault("NX_GZIP_LOGFILE", "/tmp/nx_dropin.log")
+lib = C.CDLL(sys.argv[1])
+class ZStream(C.Structure):
+    _fields_ = [("next_in", C.c_void_p), ("avail_in", C.c_uint), ("total_in", C.c_ulong), ("next_out", C.c_void_p),
+                ("avail_out", C.c_uint), ("total_out", C.c_ulong), ("msg", C.c_char_p), ("state", C.c_void_p),
+                ("zalloc", C.c_void_p), ("zfree", C.c_void_p), ("opaque", C.c_void_p), ("data_type", C.c_int),
+                ("adler", C.c_ulong), ("reserved", C.c_ulong)]
+lib.nx_inflateInit2_.argtypes = [C.POINTER(ZStream), C.c_int, C.c_char_p, C.c_int]
+lib.nx_inflate.argtypes = [C.POINTER(ZStream), C.c_int]
+lib.nx_inflateEnd.argtypes = [C.POINTER(ZStream)]
+rep = []
+for spec in json.load(open(sys.argv[2])):
+    blob = open(spec["blob"], "rb").read()
+    s = ZStream()
+    assert lib.nx_inflateInit2_(C.byref(s), spec["wbits"], b"1.2.11", C.sizeof(ZStream)) == 0
+    src = C.create_string_buffer(blob, len(blob)); out = C.create_string_buffer(spec["n"] + 64)
+    got = bytearray(); pos = 0; rc = 0; guard = 0
+    while rc == 0 and guard < 100000:
+        if s.avail_in == 0 and pos < len(blob):
+            take = min(spec["piece"], len(blob) - pos)
+            s.next_in, s.avail_in = C.addressof(src) + pos, take
+            pos += take
+        s.next_out, s.avail_out = C.addressof(out), len(out)
+        rc = lib.nx_inflate(C.byref(s), 0)
+        got += out.raw[: len(out) - s.avail_out]
+        guard += 1
+    lib.nx_inflateEnd(C.byref(s))
+    open(spec["blob"] + ".out", "wb").write(bytes(got))
+    rep.append({"rc": rc, "total_in": s.total_in, "n": len(got)})
+print(json.dumps(rep))
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REF_CPU), reason="oracle/_ref not built (needs /root/reference)")
+def test_batch_deflate_output_decodes_with_libnxz_own_inflate(engine, pg, alice, tmp_path):
+    """Row N1: what nxgpu_deflate_stream writes (primed and independent chunks, raw / zlib / gzip wrappers, levels 1 and 6)
+    goes through nx_inflate() of the reference's own host code (lib/nx_inflate.c:277 over the CPU engine, NX mode) —
+    in one piece and in 50 000-byte pieces — and must come back bit-exact with Z_STREAM_END and total_in == its length."""
+    data = pg.makedata(4, 21, alice)[: (1 << 21) - 12345] + alice[:7777]
+    specs = []
+    for level in (1, 6):
+        for wrap, wbits in ((pg.WRAP_RAW, -15), (pg.WRAP_ZLIB, 15), (pg.WRAP_GZIP, 31)):
+            for flag in (0, pg.STREAM_INDEPENDENT):
+                blob = engine.compress(data, level=level, wrap=wrap | flag, chunk=65536 if flag else 0)
+                for piece in (len(blob), 50000):
+                    path = tmp_path / f"l{level}_w{wrap}_{flag}_{piece}.z"
+                    path.write_bytes(blob)
+                    specs.append({"blob": str(path), "wbits": wbits, "n": len(data), "piece": piece, "len": len(blob)})
+    (tmp_path / "specs.json").write_text(json.dumps(specs))
+    p = subprocess.run([sys.executable, "-c", _NX_INFLATE_CHILD, REF_CPU, str(tmp_path / "specs.json")], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-3000:]
+    rep = json.loads(p.stdout.strip().splitlines()[-1])
+    assert len(rep) == len(specs) == 24
+    for spec, r in zip(specs, rep):
+        assert r["rc"] == 1 and r["total_in"] == spec["len"] and r["n"] == len(data), (spec, r)
+        assert open(spec["blob"] + ".out", "rb").read() == data, spec
