@@ -261,6 +261,10 @@ int nxgpu_gunzip_concat(nxgpu_ctx *ctx, const void *src, uint64_t src_len, void 
  * (host-side generator; inputs for bench and tests).  Returns bytes written. */
 uint64_t nxgpu_makedata(int seed, int log2size, const void *seedfile, uint64_t seedfile_len,
 			void *out, uint64_t out_cap);
+/* bytes [from, to) of that stream, generated without holding the stream (the generator looks back at most 64 KiB):
+ * shards of the 16 GiB multi-GPU workload.  Returns bytes written. */
+uint64_t nxgpu_makedata_range(int seed, int log2size, const void *seedfile, uint64_t seedfile_len,
+			      uint64_t from, uint64_t to, void *out);
 
 /* --- DHT generation: what lib/nx_dhtgen.c:945 dhtgen() computes on the host on a
  * DHT-cache miss (call site lib/nx_dht.c:632) — 286 lit/len + 30 distance counts to a length-limited

@@ -73,7 +73,7 @@ EXPORTS = [
     "nxgpu_timer_start", "nxgpu_timer_stop", "nxgpu_launch_count", "nxgpu_kernel_time", "nxgpu_kernel_time_reset",
     "nxgpu_checksum_batch", "nxgpu_crc32", "nxgpu_adler32", "nxgpu_crc32_combine", "nxgpu_adler32_combine",
     "nxgpu_deflate_batch", "nxgpu_deflate_bound", "nxgpu_deflate_stream", "nxgpu_deflate_stream_bound",
-    "nxgpu_inflate_batch", "nxgpu_inflate_stream", "nxgpu_makedata", "nxgpu_job_stats",
+    "nxgpu_inflate_batch", "nxgpu_inflate_stream", "nxgpu_makedata", "nxgpu_makedata_range", "nxgpu_job_stats",
     "nxgpu_dhtgen", "nxgpu_dhtgen_batch", "nxgpu_gunzip_concat",
 ]
 

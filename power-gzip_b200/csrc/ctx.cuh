@@ -92,6 +92,11 @@ namespace nxgpu {
 // nxgpu_api.cu: device-resident cores of the batch calls (pointers are device pointers)
 int deflate_device(nxgpu_ctx *c, DeflateJob *jobs_h, size_t n, int level, bool want_cksum, const StreamOut *so = nullptr);
 int checksum_device(nxgpu_ctx *c, const nxgpu_cksum_item *items, size_t n, int which);
+// nxgpu_deflate_stream in two halves: enqueue (no host synchronisation, totals stay on the device) and collect
+struct StreamEnq { size_t n = 0; uint64_t *d_off = nullptr; uint32_t *d_cks = nullptr; uint8_t *ddst = nullptr; bool zero_copy = false; int wrap = 0; };
+int deflate_stream_enqueue(nxgpu_ctx *c, const void *src, uint64_t src_len, void *dst, uint64_t dst_cap,
+			   int level, int wrap, uint32_t chunk, int mem, StreamEnq *e);
+int deflate_stream_collect(nxgpu_ctx *c, const StreamEnq &e, void *dst, uint64_t dst_cap, int mem, uint64_t *chunk_offsets, nxgpu_stream_result *res);
 void timer_begin(nxgpu_ctx *c, int fam);
 void timer_end(nxgpu_ctx *c, int fam);
 // nxgpu_job.cu: NX job descriptors, one at a time or coalesced

@@ -524,10 +524,14 @@ int nxgpu_deflate_batch(nxgpu_ctx *c, const nxgpu_deflate_item *items, size_t n,
 	return 0;
 }
 
-int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *dst, uint64_t dst_cap,
-			 int level, int wrap, uint32_t chunk, uint64_t *chunk_offsets, nxgpu_stream_result *res, int mem)
+// Everything of nxgpu_deflate_stream up to (not including) the first host synchronisation: the kernels and copies are
+// enqueued on c->stream and the totals stay on the device (e->d_off[n] = end of the last chunk, e->d_off[n+1] = stream
+// length with trailer, e->d_cks[0..1] = crc32 / adler32 of the input).  nxgpu_team.cu chains the cross-GPU exchange
+// behind this without going through the host.
+extern "C++" int nxgpu::deflate_stream_enqueue(nxgpu_ctx *c, const void *src, uint64_t src_len, void *dst, uint64_t dst_cap,
+					       int level, int wrap, uint32_t chunk, int mem, StreamEnq *e)
 {
-	if (!c || (!src && src_len) || !dst || !res) return NXGPU_E_ARG;
+	if (!c || (!src && src_len) || !dst || !e) return NXGPU_E_ARG;
 	NXGPU_LOCK(c);
 	// whatever path leaves this function, the next launch on the context must not wait on this call's upload flags
 	struct FlagGuard { nxgpu_ctx *c; ~FlagGuard() { c->ready_flags = nullptr; } } flag_guard{ c };
@@ -645,6 +649,21 @@ int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *
 	const uint32_t *d_crc = static_cast<const uint32_t *>(c->d_cks.p);
 	NXGPU_CUDA_OK(launch_finish_stream(dout, d_off, (uint32_t)n, ddst, dst_cap, wrap, d_crc, d_crc + 1, src_len, d_off + n + 1, c->stream));
 	c->launches += fused ? 1 : 3;
+	e->n = n; e->d_off = d_off; e->d_cks = static_cast<uint32_t *>(c->d_cks.p); e->ddst = ddst; e->zero_copy = zero_copy; e->wrap = wrap;
+	return 0;
+}
+
+// The tail of nxgpu_deflate_stream: one synchronisation, per-chunk status, totals and (for pageable host targets) the copy back.
+extern "C++" int nxgpu::deflate_stream_collect(nxgpu_ctx *c, const StreamEnq &e, void *dst, uint64_t dst_cap, int mem,
+					       uint64_t *chunk_offsets, nxgpu_stream_result *res)
+{
+	NXGPU_LOCK(c);
+	int rc;
+	const size_t n = e.n;
+	uint64_t *d_off = e.d_off;
+	uint8_t *ddst = e.ddst;
+	const bool zero_copy = e.zero_copy;
+	const int wrap = e.wrap;
 	// results back
 	if ((rc = c->h_outs.reserve(n * sizeof(DeflateOut) + (n + 2) * 8 + 16))) return rc;
 	DeflateOut *oh = static_cast<DeflateOut *>(c->h_outs.p);
@@ -674,6 +693,17 @@ int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *
 	res->n_chunks = (uint32_t)n;
 	res->n_tokens = ntok;
 	return 0;
+}
+
+int nxgpu_deflate_stream(nxgpu_ctx *c, const void *src, uint64_t src_len, void *dst, uint64_t dst_cap,
+			 int level, int wrap, uint32_t chunk, uint64_t *chunk_offsets, nxgpu_stream_result *res, int mem)
+{
+	if (!c || (!src && src_len) || !dst || !res) return NXGPU_E_ARG;
+	NXGPU_LOCK(c);
+	StreamEnq e;
+	int rc = deflate_stream_enqueue(c, src, src_len, dst, dst_cap, level, wrap, chunk, mem, &e);
+	if (rc) return rc;
+	return deflate_stream_collect(c, e, dst, dst_cap, mem, chunk_offsets, res);
 }
 
 /* --------------------------- DHT generation --------------------------- */
@@ -1111,6 +1141,54 @@ uint64_t nxgpu_makedata(int seed, int log2size, const void *seedfile, uint64_t s
 		}
 	}
 	return idx;
+}
+
+// The bytes [from, to) of the same stream without holding the stream: the generator only ever looks back
+// 65536 bytes (dist_max, samples/makedata.c:47), so a 128 KiB ring plus the seed file reproduce any range.
+// Used to cut a 16 GiB stream (BASELINE.json configs[3]) into per-GPU shards, each rank generating its own.
+uint64_t nxgpu_makedata_range(int seed, int log2size, const void *seedfile, uint64_t seedfile_len, uint64_t from, uint64_t to, void *out_)
+{
+	uint8_t *out = static_cast<uint8_t *>(out_);
+	uint64_t bufsz = 1ull << log2size;
+	srand48(seed);
+	const long a = lrand48() % 2;
+	const long b = lrand48() % (long)(bufsz / 10);
+	bufsz += (uint64_t)a * (uint64_t)b;
+	if (to > bufsz)
+		to = bufsz;
+	if (from >= to)
+		return 0;
+	constexpr uint64_t kRing = 1ull << 17;
+	std::vector<uint8_t> ring(kRing, 0);
+	const uint8_t *sf = static_cast<const uint8_t *>(seedfile);
+	uint64_t idx = seedfile_len < bufsz / 2 ? seedfile_len : bufsz / 2;
+	for (uint64_t i = idx > kRing ? idx - kRing : 0; i < idx; i++)
+		ring[i & (kRing - 1)] = sf[i];
+	if (from < idx)
+		memcpy(out, sf + from, (idx < to ? idx : to) - from);
+	const uint64_t len_max = (uint64_t)(lrand48() % 240) + 10;
+	const uint64_t dist_max = (uint64_t)(lrand48() % (1L << 16)) + 1;
+	while (idx < to) {
+		uint64_t dist = (uint64_t)lrand48() % (idx > dist_max ? dist_max : idx);
+		uint64_t len = (uint64_t)lrand48() % len_max + 16;
+		if (dist > idx)
+			dist = idx;
+		const uint64_t n = len < bufsz - idx ? len : bufsz - idx, i0 = idx;
+		uint8_t *r = ring.data();
+		if (dist == 0) {
+			// dist 0 copies the byte onto itself: the zero the buffer was cleared to
+			for (uint64_t k = 0; k < n; k++)
+				r[(i0 + k) & (kRing - 1)] = 0;
+		} else {
+			for (uint64_t k = 0; k < n; k++)
+				r[(i0 + k) & (kRing - 1)] = r[(i0 + k - dist) & (kRing - 1)];
+		}
+		idx += n;
+		const uint64_t lo = i0 > from ? i0 : from, hi = idx < to ? idx : to;
+		for (uint64_t i = lo; i < hi; i++)
+			out[i - from] = r[i & (kRing - 1)];
+	}
+	return to - from;
 }
 
 } // extern "C"
