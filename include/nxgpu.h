@@ -249,6 +249,33 @@ typedef struct {
 int nxgpu_inflate_batch(nxgpu_ctx *ctx, const nxgpu_inflate_item *items, size_t n,
 			nxgpu_inflate_result *results, int mem);
 
+/* --- one member deflated by several GPUs of one box (BASELINE.json configs[3]) -------------------
+ * One process (or thread) per GPU opens the same named team; rank r of nranks owns a contiguous range of the
+ * stream.  nxgpu_team_deflate is collective: every rank passes its range (in rank order the ranges are the whole
+ * stream; every range but the last a multiple of `chunk`), the ranks deflate in parallel as raw deflate joined by
+ * the empty stored block of lib/nx_deflate.c:220-243, the compressed sizes are exchanged and exclusive-scanned ON
+ * THE DEVICES (through a control block in pinned shared memory — no host round trip between the deflate kernel
+ * and the copy), every GPU writes its range at its global offset straight into the destination, and rank 0 folds
+ * the per-range checksums (lib/nx_crc.c:374, lib/nx_adler32.c:154) into the trailer.
+ *   dst_mem NXGPU_MEM_HOST:   the member is assembled in shared host memory (nxgpu_team_dst() in every rank): each
+ *                             GPU writes its part over its own PCIe link.
+ *   dst_mem NXGPU_MEM_DEVICE: in rank 0's device buffer (nxgpu_team_dst() on rank 0), written by the peers over
+ *                             NVLink P2P (CUDA IPC).
+ * The destination is overwritten by the next collective call.  `name` must be unique per team on the box. */
+typedef struct nxgpu_team nxgpu_team;
+typedef struct {
+	uint64_t out_len;           /* the whole member: header + every range + trailer          */
+	uint32_t crc32, adler32;    /* of the whole uncompressed stream                          */
+	uint64_t src_len;           /* uncompressed bytes of all ranks                           */
+	uint64_t my_offset, my_size;/* where this rank's range went                              */
+	float device_ms;            /* this rank: deflate + exchange + copy, on its stream       */
+} nxgpu_team_result;
+int nxgpu_team_open(nxgpu_ctx *ctx, const char *name, int rank, int nranks, uint64_t dst_cap, int dst_mem, nxgpu_team **team);
+int nxgpu_team_deflate(nxgpu_team *team, const void *src, uint64_t src_len, int level, int wrap, uint32_t chunk,
+		       int src_mem, nxgpu_team_result *res);
+void *nxgpu_team_dst(nxgpu_team *team);
+void nxgpu_team_close(nxgpu_team *team);
+
 /* A buffer of concatenated gzip members (multi-member .gz files; what gunzip, samples/gunzip_nx.c and the gz* layer
  * read) inflated as one batch; the members are discovered on the device (candidate headers, a dry decoding run, the
  * chain from offset 0).  *out_len receives the total (also on NXGPU_E_BUF: the capacity needed), *n_members the count.

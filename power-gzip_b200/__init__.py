@@ -55,6 +55,11 @@ class StreamResult(C.Structure):
                 ("n_chunks", C.c_uint32), ("n_tokens", C.c_uint64)]
 
 
+class TeamResult(C.Structure):
+    _fields_ = [("out_len", C.c_uint64), ("crc32", C.c_uint32), ("adler32", C.c_uint32), ("src_len", C.c_uint64),
+                ("my_offset", C.c_uint64), ("my_size", C.c_uint64), ("device_ms", C.c_float)]
+
+
 class InflateItem(C.Structure):
     _fields_ = [("src", C.c_void_p), ("src_len", C.c_uint32), ("dst", C.c_void_p),
                 ("dst_cap", C.c_uint32), ("wrap", C.c_uint32), ("hist_len", C.c_uint32)]
@@ -75,6 +80,7 @@ EXPORTS = [
     "nxgpu_deflate_batch", "nxgpu_deflate_bound", "nxgpu_deflate_stream", "nxgpu_deflate_stream_bound",
     "nxgpu_inflate_batch", "nxgpu_inflate_stream", "nxgpu_makedata", "nxgpu_makedata_range", "nxgpu_job_stats",
     "nxgpu_dhtgen", "nxgpu_dhtgen_batch", "nxgpu_gunzip_concat",
+    "nxgpu_team_open", "nxgpu_team_deflate", "nxgpu_team_dst", "nxgpu_team_close",
 ]
 
 _lib = None
@@ -120,6 +126,11 @@ def load_library() -> C.CDLL:
         "nxgpu_inflate_stream": (i32, [vp, vp, u64, vp, u64, i32, P(u64), u32, u32, P(StreamResult), i32]),
         "nxgpu_gunzip_concat": (i32, [vp, vp, u64, vp, u64, P(u64), P(u32), i32]),
         "nxgpu_makedata": (u64, [i32, i32, vp, u64, vp, u64]),
+        "nxgpu_makedata_range": (u64, [i32, i32, vp, u64, u64, u64, vp]),
+        "nxgpu_team_open": (i32, [vp, C.c_char_p, i32, i32, u64, i32, P(vp)]),
+        "nxgpu_team_deflate": (i32, [vp, vp, u64, i32, i32, u32, i32, P(TeamResult)]),
+        "nxgpu_team_dst": (vp, [vp]),
+        "nxgpu_team_close": (None, [vp]),
         "nxgpu_job_stats": (None, [i32, P(u64), P(u64), P(u64)]),
         "nxgpu_dhtgen": (i32, [vp, P(u32), i32, P(u32), i32, C.c_char_p, P(i32), P(i32), i32]),
         "nxgpu_dhtgen_batch": (i32, [vp, P(u32), sz, vp, P(u32), i32]),
@@ -367,6 +378,30 @@ class Engine:
                 raise NxGpuError(r.rc, "inflate member")
             result.append(bytes(memoryview(o)[: r.out_len]))
         return result
+
+
+class Team:
+    """One member deflated by several GPUs of a box (include/nxgpu.h: nxgpu_team_*): rank `rank` of `nranks`,
+    rendezvous through the shared segment `name`.  `deflate` is collective."""
+
+    def __init__(self, eng: "Engine", name: str, rank: int, nranks: int, dst_cap: int, dst_mem: int = MEM_HOST):
+        self.eng, self.rank, self.nranks, self.dst_mem = eng, rank, nranks, dst_mem
+        h = C.c_void_p()
+        eng._check(eng.lib.nxgpu_team_open(eng.ctx, name.encode(), rank, nranks, dst_cap, dst_mem, C.byref(h)), "nxgpu_team_open")
+        self.h = h
+
+    def deflate(self, src_ptr: int, n: int, level: int = 6, wrap: int = WRAP_GZIP, chunk: int = 0, src_mem: int = MEM_DEVICE) -> TeamResult:
+        res = TeamResult()
+        self.eng._check(self.eng.lib.nxgpu_team_deflate(self.h, src_ptr, n, level, wrap, chunk, src_mem, C.byref(res)), "nxgpu_team_deflate")
+        return res
+
+    def dst(self) -> int:
+        return int(self.eng.lib.nxgpu_team_dst(self.h) or 0)
+
+    def close(self) -> None:
+        if self.h:
+            self.eng.lib.nxgpu_team_close(self.h)
+            self.h = None
 
 
 def makedata(seed: int, log2size: int, seedfile: bytes) -> bytes:

@@ -481,3 +481,82 @@ def test_gunzip_of_concatenated_members(engine, pg, alice):
         with pytest.raises(pg.NxGpuError) as e:
             engine.gunzip(bad, len(want))
         assert e.value.rc == pg.E_DATA
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dst_mem", ["host", "device"])
+def test_team_deflate_ranks_as_threads_on_one_gpu(pg, alice, dst_mem):
+    """The multi-GPU entry point (nxgpu_team_*) with its ranks as THREADS on one device: three contexts
+    deflate the three ranges of one stream, exchange sizes on the device, write their ranges at the scanned offsets and
+    rank 0 folds the checksums.  One gzip member that zlib inflates; crc32 = zlib's; twice (the destination is reused)."""
+    import threading
+    import zlib as _z
+    data = pg.makedata(5, 22, alice)[: (1 << 22) - 777]
+    nranks, chunk = 3, 65536
+    per = (len(data) // chunk // nranks) * chunk
+    cuts = [0, per, 2 * per, len(data)]
+    mem = pg.MEM_HOST if dst_mem == "host" else pg.MEM_DEVICE
+    name = f"nxgpu-test-{os.getpid()}-{dst_mem}"
+    out, errs = {}, []
+
+    def worker(r):
+        try:
+            with pg.Engine(0) as eng:
+                team = pg.Team(eng, name, r, nranks, len(data) + 4096, mem)
+                shard = data[cuts[r]: cuts[r + 1]]
+                d = eng.alloc(len(shard)); d.upload(shard)
+                for rep, wrap in enumerate((pg.WRAP_GZIP, pg.WRAP_ZLIB)):
+                    # device-resident shard, then the same from host memory
+                    res = team.deflate(d.ptr, len(shard), level=6, wrap=wrap, chunk=chunk, src_mem=pg.MEM_DEVICE)
+                    hbuf = C.create_string_buffer(shard, len(shard))
+                    res2 = team.deflate(C.addressof(hbuf), len(shard), level=6, wrap=wrap, chunk=chunk, src_mem=pg.MEM_HOST)
+                    assert (res.out_len, res.crc32, res.adler32) == (res2.out_len, res2.crc32, res2.adler32)
+                    if r == 0:
+                        if mem == pg.MEM_HOST:
+                            blob = C.string_at(team.dst(), res.out_len)
+                        else:
+                            hb = C.create_string_buffer(res.out_len)
+                            eng._check(eng.lib.nxgpu_memcpy_d2h(eng.ctx, C.addressof(hb), team.dst(), res.out_len), "d2h")
+                            blob = hb.raw
+                        out[rep] = (blob, res.crc32, res.adler32, res.src_len)
+                    barrier.wait()               # nobody starts the next collective while rank 0 reads the member
+                team.close()
+        except Exception as e:                       # noqa: BLE001
+            errs.append(repr(e))
+            barrier.abort()
+
+    barrier = threading.Barrier(nranks)
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(nranks)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    blob, crc, adler, ulen = out[0]
+    assert _z.decompress(blob, 31) == data and crc == _z.crc32(data) and ulen == len(data)
+    blob, crc, adler, ulen = out[1]
+    assert _z.decompress(blob, 15) == data and adler == _z.adler32(data)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dst_mem", ["host", "device"])
+def test_team_deflate_processes_on_two_gpus(dst_mem):
+    """nxgpu_team_* with one PROCESS per GPU (the deployment shape: torchrun ranks): the shared segment, CUDA IPC for
+    rank 0's device buffer, sizes exchanged between the GPUs, P2P / per-GPU PCIe writes at the scanned offsets."""
+    import subprocess
+    import sys
+    try:
+        ngpu = int(subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.count("GPU "))
+    except Exception:
+        ngpu = 0
+    if ngpu < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    nranks = min(ngpu, 4)
+    name = f"nxgpu-ptest-{os.getpid()}-{dst_mem}"
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "team_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, name, str(r), str(nranks), "26", dst_mem], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(nranks)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [o[1][-1500:] for o in outs]
+    rep = json.loads(outs[0][0].strip().splitlines()[-1])
+    assert rep["ok"], rep

@@ -59,8 +59,9 @@ def cpu_runs():
         return
     with tempfile.TemporaryDirectory() as wd:
         env = _env(CPU_LIB, wd)
-        env["TEST_NTHREADS"] = "4"          # test_multithread_stress: the checker is a scalar C engine on a few cores
-        procs = {t: subprocess.Popen([os.path.join(BIN, t)], cwd=wd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+        # test_multithread_stress <threads> <seconds per iteration> <iterations>: the checker is a scalar C engine on a few cores
+        procs = {t: subprocess.Popen([os.path.join(BIN, t)] + (["4", "2", "1"] if t == "test_multithread_stress" else []),
+                                     cwd=wd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
                  for t in TESTS}
         yield procs
         for p in procs.values():
@@ -83,7 +84,8 @@ def test_reference_program_over_cpu_engine(name, cpu_runs):
 def test_reference_program_over_gpu_engine(name):
     with tempfile.TemporaryDirectory() as wd:
         env = _env(GPU_LIB, wd)
-        p = subprocess.run([os.path.join(BIN, name)], cwd=wd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+        args = ["64", "3", "2"] if name == "test_multithread_stress" else []     # 64 threads, 2 x 3 s (the default is 20 threads per core for 60 s)
+        p = subprocess.run([os.path.join(BIN, name)] + args, cwd=wd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
         # the product really ran: the drop-in library maps libnxgpu.so, and nothing of the oracle
         _report(name, p.returncode, p.stdout)
 
