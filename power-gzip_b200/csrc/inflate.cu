@@ -166,8 +166,9 @@ __device__ int slow_decode(BitReader &br, const uint16_t *count, const uint16_t 
 }
 
 // warp-cooperative: lens[n] -> primary LUT + canonical arrays.  Returns false if over-subscribed.
+// strict: also refuse what zlib's inftrees.c refuses — an incomplete set unless its longest code is one bit
 __device__ bool build_table(const uint8_t *lens, int n, uint32_t *lut, int lut_bits, uint16_t *count,
-			    uint16_t *sorted, bool is_dist)
+			    uint16_t *sorted, bool is_dist, bool strict)
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t lt = (1u << lane) - 1;
@@ -193,7 +194,7 @@ __device__ bool build_table(const uint8_t *lens, int n, uint32_t *lut, int lut_b
 	}
 	// Kraft check + first code / offset per length (every lane computes the same small scan)
 	uint32_t next_code = 0, offs = 0, my_next = 0, my_offs = 0;
-	int left = 1;
+	int left = 1, max_len = 0;
 	bool over = false;
 	for (int L = 1; L <= 15; L++) {
 		const uint32_t c = __shfl_sync(0xffffffffu, my_cnt, L);
@@ -203,10 +204,14 @@ __device__ bool build_table(const uint8_t *lens, int n, uint32_t *lut, int lut_b
 		if ((int)lane == L) { my_next = next_code; my_offs = offs; }
 		next_code = (next_code + c) << 1;
 		offs += c;
+		if (c)
+			max_len = L;
 	}
 	if (lane < 16)
 		count[lane] = (lane == 0) ? 0 : (uint16_t)my_cnt;
 	if (over)
+		return false;
+	if (strict && left > 0 && max_len > 1)
 		return false;
 	for (int i = lane; i < (1 << lut_bits); i += 32)
 		lut[i] = 0;
@@ -247,7 +252,7 @@ __device__ bool build_table(const uint8_t *lens, int n, uint32_t *lut, int lut_b
 }
 
 // dynamic block header from HLIT on (RFC 1951 3.2.7), lane 0 only: code lengths into lens[0..hlit+hdist)
-__device__ int parse_dyn_header(BitReader &br, uint8_t *lens, int &hlit, int &hdist)
+__device__ int parse_dyn_header(BitReader &br, uint8_t *lens, int &hlit, int &hdist, bool strict)
 {
 	int rc = 0;
 	const uint32_t v = br.get(14);
@@ -264,6 +269,7 @@ __device__ int parse_dyn_header(BitReader &br, uint8_t *lens, int &hlit, int &hd
 	ccount[0] = 0;
 	int left = 1;
 	for (int l = 1; l <= 7; l++) { left = (left << 1) - ccount[l]; if (left < 0) rc = NXGPU_E_DATA; }
+	if (strict && left > 0) rc = NXGPU_E_DATA;       // zlib: an incomplete code-length code is "invalid code lengths set"
 	coffs[1] = 0;
 	for (int l = 1; l < 15; l++) coffs[l + 1] = coffs[l] + ccount[l];
 	for (int i = 0; i < 19; i++) if (cl[i]) csorted[coffs[cl[i]]++] = (uint16_t)i;
@@ -377,7 +383,7 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 					btype = 2;
 					BitReader dr;
 					dr.init(J.dht, (J.dht_bits + 7) >> 3, 0, T.lit);   // the LUT is not built yet: borrow it as the ring
-					rc = parse_dyn_header(dr, T.lens, hlit, hdist);
+					rc = parse_dyn_header(dr, T.lens, hlit, hdist, false);
 					if (rc || dr.bits_used() > J.dht_bits) rc = 68;
 					dht_saved = true; dht_from = 0; dht_len = J.dht_bits;
 				}
@@ -396,7 +402,7 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 					stored_at = br.byte_pos();
 				} else if (btype == 2) {
 					dht_from = br.bits_used();
-					rc = parse_dyn_header(br, T.lens, hlit, hdist);
+					rc = parse_dyn_header(br, T.lens, hlit, hdist, !job);
 					dht_len = (uint32_t)(br.bits_used() - dht_from);
 					dht_saved = false;
 				} else if (btype == 3) {
@@ -467,8 +473,10 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 			hdist = __shfl_sync(0xffffffffu, hdist, 0);
 		}
 		__syncwarp();
-		bool ok = build_table(T.lens, hlit, T.lit, kLitBits, T.lit_count, T.lit_sorted, false);
-		ok = build_table(T.lens + hlit, hdist, T.dist, kDistBits, T.dist_count, T.dist_sorted, true) && ok;
+		// members are judged like zlib judges them; NX job descriptors keep the engine's lenient rule (over-subscription only).
+		// The fixed code's 30 five-bit distance codes are an incomplete set by construction.
+		bool ok = build_table(T.lens, hlit, T.lit, kLitBits, T.lit_count, T.lit_sorted, false, !job && btype == 2);
+		ok = build_table(T.lens + hlit, hdist, T.dist, kDistBits, T.dist_count, T.dist_sorted, true, !job && btype == 2) && ok;
 		if (!ok) { rc = job ? 68 : NXGPU_E_DATA; break; }
 
 		// ---- symbols ----

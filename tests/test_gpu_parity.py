@@ -560,3 +560,135 @@ def test_team_deflate_processes_on_two_gpus(dst_mem):
     assert all(p.returncode == 0 for p in procs), [o[1][-1500:] for o in outs]
     rep = json.loads(outs[0][0].strip().splitlines()[-1])
     assert rep["ok"], rep
+
+
+def _member_zoo(pg, alice):
+    """many small members of every shape: wrappers, levels, block types, header fields, sizes around the copy-loop edges"""
+    rnd = random.Random(77)
+    md = pg.makedata(4, 21, alice)
+    datas = [b"", b"a", b"abc", b"ab" * 5, bytes(70000), rnd.randbytes(5000), bytes(range(256)) * 20, alice[:50000], alice[60000:60007]]
+    datas += [md[i * 65536:(i + 1) * 65536] for i in range(8)]
+    datas += [alice[o:o + n] for o, n in ((0, 1), (5, 2), (9, 3), (100, 4), (200, 5), (300, 31), (400, 32), (500, 33), (700, 257), (900, 258), (1100, 259), (2000, 4097))]
+    datas += [(b"x" * k + alice[1000:1200]) * 7 for k in (1, 2, 3, 4, 5, 6, 7, 8)]          # distances 1..8 and their multiples
+    out = []
+    for i, d in enumerate(datas):
+        for lvl in (0, 1, 6, 9):
+            out.append((zlib.compress(d, lvl), d))
+            out.append((zlib.compress(d, lvl, wbits=31), d))
+            out.append((zlib.compress(d, lvl, wbits=-15), d))
+        fx = zlib.compressobj(6, zlib.DEFLATED, -15, 8, zlib.Z_FIXED)
+        out.append((fx.compress(d) + fx.flush(), d))
+        co = zlib.compressobj(6, zlib.DEFLATED, 31)
+        out.append((b"".join(co.compress(d[k:k + 9000]) + co.flush(zlib.Z_FULL_FLUSH) for k in range(0, len(d), 9000)) + co.flush(), d))
+        # gzip header with FEXTRA, FNAME, FCOMMENT, FHCRC
+        raw = zlib.compress(d, 6, wbits=-15)
+        hdr = bytes([0x1f, 0x8b, 8, 4 | 8 | 16 | 2, 0, 0, 0, 0, 0, 3]) + (5).to_bytes(2, "little") + b"extra" + b"name\0" + b"comment\0"
+        hdr += (zlib.crc32(hdr) & 0xffff).to_bytes(2, "little")
+        out.append((hdr + raw + zlib.crc32(d).to_bytes(4, "little") + (len(d) & 0xffffffff).to_bytes(4, "little"), d))
+    return out
+
+
+def _run_members(engine, pg, members, lanes_min):
+    os.environ["NXGPU_INFLATE_LANES_MIN"] = str(lanes_min)
+    try:
+        # packed back to back (arbitrary alignment of every member and of every output)
+        blob = b"".join(m for m, _ in members)
+        src = C.create_string_buffer(blob, len(blob))
+        caps = [len(d) for _, d in members]
+        outb = (C.c_char * (sum(caps) + 64))()
+        items, so, do = [], 0, 0
+        for (m, d), cap in zip(members, caps):
+            items.append(pg.InflateItem(C.addressof(src) + so, len(m), C.addressof(outb) + do, cap, pg.WRAP_AUTO, 0))
+            so += len(m); do += cap
+        res = engine.inflate_batch(items, mem=pg.MEM_HOST)
+        outs, do = [], 0
+        for r, cap in zip(res, caps):
+            outs.append(bytes(memoryview(outb)[do: do + min(r.out_len, cap)]))
+            do += cap
+        return [(r.rc, r.out_len, r.in_used, r.flags, r.crc32, r.adler32) for r in res], outs
+    finally:
+        os.environ.pop("NXGPU_INFLATE_LANES_MIN", None)
+
+
+@pytest.mark.gpu
+def test_inflate_lane_per_member_kernel_is_bit_exact(engine, pg, alice):
+    """inflate_lanes.cu (one lane per member, the kernel large batches run on) against zlib and against the warp-per-member
+    kernel on the same members: output bytes, lengths, bytes consumed, flags and both checksums."""
+    members = _member_zoo(pg, alice)
+    assert len(members) > 450
+    lanes, louts = _run_members(engine, pg, members, 0)
+    warp, wouts = _run_members(engine, pg, members, -1)
+    for i, ((m, d), lr, lo, wr, wo) in enumerate(zip(members, lanes, louts, warp, wouts)):
+        assert lr[0] == 0, (i, len(d), lr, m[:16].hex())
+        assert lo == d and lr[1] == len(d) and lr[2] == len(m), (i, len(d), lr)
+        assert lr[4] == zlib.crc32(d) and lr[5] == zlib.adler32(d)
+        assert lr == wr and wo == d, (i, lr, wr)
+
+
+def _zlib_verdict(stream, cap):
+    """(accepted, output) of system zlib for a raw deflate stream"""
+    d = zlib.decompressobj(-15)
+    try:
+        out = d.decompress(stream, cap + 1)
+    except zlib.error:
+        return False, b""
+    if not d.eof or len(out) > cap:
+        return False, out
+    return True, out
+
+
+@pytest.mark.gpu
+def test_inflate_malformed_streams_like_zlib(engine, pg, alice):
+    """Corrupt raw streams (bit flips in headers and bodies, truncations, hand-made over-subscribed / incomplete code sets,
+    bad stored lengths, reserved block type, distances in front of the window): both kernels must reject exactly the
+    streams zlib rejects, and reproduce zlib's output for the ones it accepts."""
+    rnd = random.Random(5)
+    base = [zlib.compress(alice[:3000], 6, wbits=-15), zlib.compress(bytes(500) + alice[:700], 9, wbits=-15),
+            zlib.compress(rnd.randbytes(300), 0, wbits=-15), zlib.compress(b"abcabcabc" * 50, 1, wbits=-15)]
+    fx = zlib.compressobj(6, zlib.DEFLATED, -15, 8, zlib.Z_FIXED)
+    base.append(fx.compress(alice[:2000]) + fx.flush())
+    cases = []
+    for s in base:
+        for _ in range(60):
+            b = bytearray(s)
+            pos = rnd.randrange(min(len(b), 120)) if rnd.random() < 0.7 else rnd.randrange(len(b))
+            b[pos] ^= 1 << rnd.randrange(8)
+            cases.append(bytes(b))
+        for cut in (1, 2, 3, len(s) // 2, len(s) - 1):
+            cases.append(s[:cut])
+    # hand-made headers: BFINAL=1, BTYPE=10, then HLIT/HDIST/HCLEN and code lengths
+    def bits(*fields):
+        v, n = 0, 0
+        for val, w in fields:
+            v |= val << n; n += w
+        return v.to_bytes((n + 7) // 8 + 4, "little")
+    cases.append(bits((1, 1), (2, 2), (0, 5), (0, 5), (15, 4), *[(1, 3)] * 19))                 # over-subscribed code-length code
+    cases.append(bits((1, 1), (2, 2), (0, 5), (0, 5), (0, 4), (1, 3), (0, 3), (0, 3), (0, 3)))    # incomplete code-length code
+    cases.append(bits((1, 1), (2, 2), (29, 5), (0, 5), (0, 4)))                                    # HLIT too large
+    cases.append(bits((1, 1), (3, 2)))                                                             # reserved block type
+    cases.append(bits((1, 1), (0, 2), (0, 5), (5, 16), (5, 16)))                                   # stored: LEN != ~NLEN
+    cases.append(bytes([0x4b, 0x04, 0x00]) + b"")                                                  # fixed block, valid: "a"
+    cases.append(bytes([0x63, 0x00, 0x02, 0x00]))                                                  # fixed: distance in front of the window
+    cap = 5000
+    members = []
+    verdicts = [_zlib_verdict(s, cap) for s in cases]
+    for lanes_min in (0, -1):
+        os.environ["NXGPU_INFLATE_LANES_MIN"] = str(lanes_min)
+        try:
+            keep, items = [], []
+            for s in cases:
+                sb = C.create_string_buffer(s, len(s)); ob = (C.c_char * cap)()
+                keep.append((sb, ob))
+                items.append(pg.InflateItem(C.addressof(sb), len(s), C.addressof(ob), cap, pg.WRAP_RAW, 0))
+            res = engine.inflate_batch(items, mem=pg.MEM_HOST)
+        finally:
+            os.environ.pop("NXGPU_INFLATE_LANES_MIN", None)
+        n_rej = 0
+        for i, (s, (ok, want), r, (sb, ob)) in enumerate(zip(cases, verdicts, res, keep)):
+            if ok:
+                assert r.rc == 0 and bytes(memoryview(ob)[: r.out_len]) == want, (lanes_min, i, r.rc, r.out_len, len(want), s[:12].hex())
+            else:
+                assert r.rc != 0, (lanes_min, i, "zlib rejects this stream, the engine accepted it", s[:12].hex(), r.out_len)
+                n_rej += 1
+        assert 50 < n_rej < len(cases)
+    del members
