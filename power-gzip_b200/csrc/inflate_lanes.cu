@@ -185,6 +185,74 @@ __device__ __forceinline__ int decode_long(const Tab &T, const Bits &B, int root
 	return -1;
 }
 
+// o[0..len) = o[-dist..): the LZ77 copy of one lane.  Every load is a round trip to L2 (the bytes were written by this
+// lane a moment ago), so the loop moves 16 or 32 bytes per trip with all loads of a step in flight, and a short
+// distance is first widened: once k*dist bytes of a period exist, copying from k*dist back is the same copy.
+__device__ __forceinline__ uint32_t ldv(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ void copy_match(uint8_t *o, uint32_t dist, uint32_t len)
+{
+	if (dist < 16) {
+		uint32_t wide = dist;
+		while (wide < 16) wide += dist;
+		const uint32_t pre = min(len, wide - dist);
+		for (uint32_t k = 0; k < pre; k++)
+			o[k] = *(volatile const uint8_t *)(o + k - dist);
+		o += pre; len -= pre; dist = wide;
+	}
+	// bytes, then words, until the destination is 16-byte aligned (dist >= 16: a source word never overlaps its destination)
+	while (len && (reinterpret_cast<uintptr_t>(o) & 3)) { *o = *(volatile const uint8_t *)(o - dist); o++; len--; }
+	if (len < 4) {
+		while (len) { *o = *(volatile const uint8_t *)(o - dist); o++; len--; }
+		return;
+	}
+	const uint8_t *sp = o - dist;
+	const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 3) * 8;
+	const uint32_t *s32 = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)3);
+	uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
+	uint32_t nw = len >> 2;
+	while (nw && (reinterpret_cast<uintptr_t>(o32) & 15)) {
+		const uint32_t a = ldv(s32), b = sh ? ldv(s32 + 1) : 0;
+		*o32 = sh ? __funnelshift_r(a, b, sh) : a;
+		o32++; s32++; nw--;
+	}
+	if (dist >= 32) {
+		while (nw >= 8) {
+			uint32_t w[9];
+#pragma unroll
+			for (int k = 0; k < 8; k++) w[k] = ldv(s32 + k);
+			w[8] = sh ? ldv(s32 + 8) : 0;
+			uint4 x, y;
+			if (sh) {
+				x = make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh));
+				y = make_uint4(__funnelshift_r(w[4], w[5], sh), __funnelshift_r(w[5], w[6], sh), __funnelshift_r(w[6], w[7], sh), __funnelshift_r(w[7], w[8], sh));
+			} else {
+				x = make_uint4(w[0], w[1], w[2], w[3]); y = make_uint4(w[4], w[5], w[6], w[7]);
+			}
+			reinterpret_cast<uint4 *>(o32)[0] = x;
+			reinterpret_cast<uint4 *>(o32)[1] = y;
+			o32 += 8; s32 += 8; nw -= 8;
+		}
+	}
+	while (nw >= 4) {
+		uint32_t w[5];
+#pragma unroll
+		for (int k = 0; k < 4; k++) w[k] = ldv(s32 + k);
+		w[4] = sh ? ldv(s32 + 4) : 0;
+		const uint4 x = sh ? make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh))
+				   : make_uint4(w[0], w[1], w[2], w[3]);
+		*reinterpret_cast<uint4 *>(o32) = x;
+		o32 += 4; s32 += 4; nw -= 4;
+	}
+	while (nw) {
+		const uint32_t a = ldv(s32), b = sh ? ldv(s32 + 1) : 0;
+		*o32 = sh ? __funnelshift_r(a, b, sh) : a;
+		o32++; s32++; nw--;
+	}
+	o = reinterpret_cast<uint8_t *>(o32);
+	len &= 3;
+	while (len) { *o = *(volatile const uint8_t *)(o - dist); o++; len--; }
+}
+
 __device__ __forceinline__ void put_result(InflateOut &O, int rc, uint32_t out_len, uint32_t in_used, uint32_t flags, uint32_t tcrc, uint32_t tsize)
 {
 	O.rc = rc; O.out_len = out_len; O.in_used = in_used; O.flags = flags; O.trailer_crc = tcrc; O.trailer_isize = tsize;
@@ -442,35 +510,7 @@ inflate_lanes_kernel(const InflateJob *__restrict__ jobs, InflateOut *__restrict
 				if (len > ocap - op) { rc = NXGPU_E_BUF; state = ST_FINISH; break; }
 				uint8_t *o = out + op;
 				op += len;
-				if (dist >= 4) {
-					// bytes until the destination is 4-byte aligned, then words: source word = two aligned loads joined by a funnel shift
-					while (len && (reinterpret_cast<uintptr_t>(o) & 3)) { *o = *(o - dist); o++; len--; }
-					if (len >= 4) {
-						const uint8_t *sp = o - dist;
-						const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 3) * 8;
-						const uint32_t *s32 = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)3);
-						uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
-						uint32_t w0 = *reinterpret_cast<const volatile uint32_t *>(s32);
-						const uint32_t nw = len >> 2;
-						if (sh == 0) {
-							for (uint32_t k = 0; k < nw; k++) {
-								o32[k] = w0;
-								w0 = *reinterpret_cast<const volatile uint32_t *>(s32 + k + 1);     // may be a word this loop wrote (dist 4..7): program order
-							}
-						} else {
-							for (uint32_t k = 0; k < nw; k++) {
-								const uint32_t w1 = *reinterpret_cast<const volatile uint32_t *>(s32 + k + 1);
-								o32[k] = __funnelshift_r(w0, w1, sh);
-								w0 = w1;
-							}
-						}
-						o += nw * 4; len &= 3;
-					}
-					while (len) { *o = *(o - dist); o++; len--; }
-				} else {
-					for (uint32_t k = 0; k < len; k++)
-						o[k] = *(volatile const uint8_t *)(o + k - dist);
-				}
+				copy_match(o, dist, len);
 			}
 		}
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Developer probe: batched inflate of distinct 64 KiB gzip members of the seed-4 stream (BASELINE.json configs[2]),
-lane-per-member kernel against the warp-per-member kernel.  usage: inflate_members_probe.py [members=16384]"""
+lane-per-member kernel against the warp-per-member kernel.  usage: inflate_members_probe.py [members=16384] [seed=4] [log2=33]"""
 import ctypes as C, gzip, importlib.util, os, sys, time, zlib
 from concurrent.futures import ThreadPoolExecutor
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -8,10 +8,12 @@ spec = importlib.util.spec_from_file_location("power_gzip_b200", os.path.join(RO
 pg = importlib.util.module_from_spec(spec); spec.loader.exec_module(pg)
 alice = gzip.decompress(open(os.path.join(ROOT, "tests/golden/alice29.txt.gz"), "rb").read())
 nm = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+log2 = int(sys.argv[3]) if len(sys.argv) > 3 else 33
 M = 65536
 lib = pg.load_library()
 raw = C.create_string_buffer(nm * M)
-lib.nxgpu_makedata_range(4, 33, alice, len(alice), 0, nm * M, raw)
+lib.nxgpu_makedata_range(seed, log2, alice, len(alice), 0, nm * M, raw)
 mv = memoryview(raw).cast("B")
 with ThreadPoolExecutor(os.cpu_count()) as ex:
     blobs = list(ex.map(lambda i: zlib.compress(mv[i * M:(i + 1) * M], 6, wbits=31), range(nm)))
@@ -33,4 +35,4 @@ for name, lm in (("warp-per-member", "-1"), ("lane-per-member", "0")):
         ms, k = eng.kernel_time("inflate")
         best = min(best, ms)
     ok = all(r.rc == 0 and r.out_len == M for r in res) and res[nm - 1].crc32 == zlib.crc32(mv[(nm - 1) * M: nm * M])
-    print(f"{name}: {nm} members, kernel {best:.2f} ms = {nm * M / best / 1e6:.1f} GB/s out, compressed {len(packed) / nm:.0f} B/member, ok={ok}", flush=True)
+    print(f"seed {seed} -b {log2} {name}: {nm} members, kernel {best:.2f} ms = {nm * M / best / 1e6:.1f} GB/s out, compressed {len(packed) / nm:.0f} B/member, ok={ok}", flush=True)
