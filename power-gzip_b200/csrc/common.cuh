@@ -174,8 +174,6 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 cudaError_t launch_dhtgen(const uint32_t *counts, uint32_t n, uint8_t *dht_out, uint32_t *dht_bits, cudaStream_t s);
 cudaError_t launch_gzip_candidates(const uint8_t *src, uint64_t len, uint64_t *cand, uint32_t max_cand, uint32_t *count, cudaStream_t s);
 cudaError_t launch_inflate(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s);
-// inflate_lanes.cu: one lane per member (large batches of plain members)
-cudaError_t launch_inflate_lanes(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s);
 // checksum.cu
 cudaError_t checksum_init_tables();
 size_t checksum_range_bytes();

@@ -857,19 +857,7 @@ int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n,
 	for (size_t g = 0; g < n_groups; g++) {
 		const size_t g0 = g * n / n_groups, g1 = (g + 1) * n / n_groups, ng = g1 - g0;
 		timer_begin(c, 1);
-		// many members: one LANE per member (inflate_lanes.cu); a handful: one WARP per member (inflate.cu), whose
-		// byte-parallel materialise finishes a single member sooner
-		// Highly compressed members (long runs: hundreds of output bytes per symbol) are copy-bound, and a warp copies one
-		// long match faster than a lane does: they stay on the warp kernel.
-		const char *lm = getenv("NXGPU_INFLATE_LANES_MIN");                      // developer / test switch: -1 never, 0 always
-		const int lanes_min = lm ? atoi(lm) : 4 * 7 * kNumSMs;
-		uint64_t sum_in = 0, sum_cap = 0;
-		for (size_t i = g0; i < g1; i++) { sum_in += jh[i].src_len; sum_cap += jh[i].dst_cap; }
-		const bool long_runs = !lm && sum_cap > 24 * sum_in;
-		if (lanes_min >= 0 && ng >= (size_t)lanes_min && !long_runs)
-			NXGPU_CUDA_OK(launch_inflate_lanes(dj + g0, dout + g0, (uint32_t)ng, static_cast<uint32_t *>(c->d_misc.p), c->stream));
-		else
-			NXGPU_CUDA_OK(launch_inflate(dj + g0, dout + g0, (uint32_t)ng, static_cast<uint32_t *>(c->d_misc.p), c->stream));
+		NXGPU_CUDA_OK(launch_inflate(dj + g0, dout + g0, (uint32_t)ng, static_cast<uint32_t *>(c->d_misc.p), c->stream));
 		timer_end(c, 1);
 		// crc32 / adler32 of every output, lengths taken from the device results
 		uint32_t *d_rs = d_rs_all + g0 + g;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Developer probe: batched inflate of distinct 64 KiB gzip members of the seed-4 stream (BASELINE.json configs[2]),
-lane-per-member kernel against the warp-per-member kernel.  usage: inflate_members_probe.py [members=16384] [seed=4] [log2=33]"""
+device resident.  usage: inflate_members_probe.py [members=16384] [seed=4] [log2=33]"""
 import ctypes as C, gzip, importlib.util, os, sys, time, zlib
 from concurrent.futures import ThreadPoolExecutor
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -26,8 +26,7 @@ o = 0
 for i, b in enumerate(blobs):
     items[i] = pg.InflateItem(dcomp.ptr + o, len(b), dout.ptr + i * M, M, pg.WRAP_GZIP, 0); o += len(b)
 res = (pg.InflateResult * nm)()
-for name, lm in (("warp-per-member", "-1"), ("lane-per-member", "0")):
-    os.environ["NXGPU_INFLATE_LANES_MIN"] = lm
+for name in ("warp-per-member",):
     best = 1e9
     for it in range(4):
         eng.kernel_time_reset()
