@@ -283,6 +283,19 @@ void nxgpu_team_close(nxgpu_team *team);
 int nxgpu_gunzip_concat(nxgpu_ctx *ctx, const void *src, uint64_t src_len, void *dst, uint64_t dst_cap,
 			uint64_t *out_len, uint32_t *n_members, int mem);
 
+/* --- gz* reader over the batched inflate (replaces the read side of lib/nx_gzlib.c:220-325, whose
+ * __gzread pulls 10 bytes per read() and stops after the first member).  zlib's calling convention: gzread returns the
+ * bytes delivered, 0 at the end of the file, -1 on error; every member of a multi-member file is inflated (one batch on
+ * the device) and its CRC-32 / ISIZE verified.  ctx may be NULL (a context on the default device is opened and closed
+ * with the file).  Only mode "r" is bound; writing stays with the reference's gzwrite over nxu_run_job. */
+typedef struct nxgpu_gzfile nxgpu_gzfile;
+nxgpu_gzfile *nxgpu_gzopen(nxgpu_ctx *ctx, const char *path, const char *mode);
+nxgpu_gzfile *nxgpu_gzdopen(nxgpu_ctx *ctx, int fd, const char *mode);
+int nxgpu_gzread(nxgpu_gzfile *file, void *buf, unsigned len);
+int nxgpu_gzeof(nxgpu_gzfile *file);
+uint32_t nxgpu_gzmembers(nxgpu_gzfile *file);
+int nxgpu_gzclose(nxgpu_gzfile *file);
+
 /* --- makedata-style synthetic text (reference samples/makedata.c:35-70):
  * byte-for-byte the stream `makedata -s seed -b log2size < seedfile` writes
  * (host-side generator; inputs for bench and tests).  Returns bytes written. */

@@ -81,6 +81,7 @@ EXPORTS = [
     "nxgpu_inflate_batch", "nxgpu_inflate_stream", "nxgpu_makedata", "nxgpu_makedata_range", "nxgpu_job_stats",
     "nxgpu_dhtgen", "nxgpu_dhtgen_batch", "nxgpu_gunzip_concat",
     "nxgpu_team_open", "nxgpu_team_deflate", "nxgpu_team_dst", "nxgpu_team_close",
+    "nxgpu_gzopen", "nxgpu_gzdopen", "nxgpu_gzread", "nxgpu_gzeof", "nxgpu_gzmembers", "nxgpu_gzclose",
 ]
 
 _lib = None
@@ -131,6 +132,12 @@ def load_library() -> C.CDLL:
         "nxgpu_team_deflate": (i32, [vp, vp, u64, i32, i32, u32, i32, P(TeamResult)]),
         "nxgpu_team_dst": (vp, [vp]),
         "nxgpu_team_close": (None, [vp]),
+        "nxgpu_gzopen": (vp, [vp, C.c_char_p, C.c_char_p]),
+        "nxgpu_gzdopen": (vp, [vp, i32, C.c_char_p]),
+        "nxgpu_gzread": (i32, [vp, vp, C.c_uint]),
+        "nxgpu_gzeof": (i32, [vp]),
+        "nxgpu_gzmembers": (u32, [vp]),
+        "nxgpu_gzclose": (i32, [vp]),
         "nxgpu_job_stats": (None, [i32, P(u64), P(u64), P(u64)]),
         "nxgpu_dhtgen": (i32, [vp, P(u32), i32, P(u32), i32, C.c_char_p, P(i32), P(i32), i32]),
         "nxgpu_dhtgen_batch": (i32, [vp, P(u32), sz, vp, P(u32), i32]),

@@ -2,13 +2,16 @@
 // POWER vpmsum CRC of lib/crc32_power.c:71 and the scalar loops of lib/nx_adler32.c:81, with
 // the GF(2) / modular combines of lib/nx_crc.c:374 and lib/nx_adler32.c:154 done on the device.
 //
-// Pass 1 (checksum_ranges_kernel): the input is cut into ranges; one CTA streams a range through
-// shared memory in 32 KiB tiles (cp.async, 16-byte vectors, double buffered).  Thread t owns the
-// 64-byte strip t of every tile, so its running CRC register simply skips the other 511 strips
-// with one "append 32704 zero bytes" operator (4 table look-ups) per tile; slice-by-4 tables sit
-// in shared memory.  Strips are padded to 80 bytes in shared memory so the LDS.128 reads of a
-// quarter-warp hit 8 distinct bank groups.  Adler-32 rides along with two dp4a per word.  A
-// shuffle/shared-memory tree folds the 512 registers with fixed shift operators.
+// Pass 1 (checksum_ranges_kernel): the input is cut into ranges; one CTA (1024 threads, one per SM) streams a range
+// in 16 KiB tiles with fully coalesced 16-byte loads straight into registers: thread t owns the 16-byte piece t of
+// every tile.  CRC-32 is linear over GF(2), so each of the thread's four 32-bit word columns is its own accumulator:
+// acc <- Shift_16KiB(acc) ^ word — four independent chains per thread, ONE fixed shift operator (4 x 256-entry table,
+// 4 look-ups per word = 1 per byte, the same count as slice-by-4) and no shared-memory staging of the data at all.
+// The shift table has a private copy per lane (entry (k, v) of lane L at word (k*256 + v)*32 + L: always bank L), so
+// the data-dependent look-ups never conflict.  Adler-32 rides along with two dp4a per word (byte sum and the
+// position-weighted sum of the piece; tile and piece offsets are folded in once per range).  At the end of a range
+// the 4096 word columns are folded with fixed shift operators (3 Horner steps per thread, then a 10-level tree over
+// the threads: shuffles inside a warp, shared memory across warps).
 // Pass 2 (checksum_combine_kernel): one warp per job folds its ranges: every range is shifted by
 // the bytes that follow it (x^(8n) mod P by repeated squaring) and XOR-ed; seeds are applied last.
 #include <cuda_runtime.h>
@@ -23,16 +26,15 @@ namespace {
 
 constexpr uint32_t kPoly = 0xEDB88320u;
 constexpr uint32_t kBase = 65521u;
-constexpr int kCkThreads = 512;
-constexpr int kStrip = 64;
-constexpr int kStripPad = 80;
-constexpr int kTile = kCkThreads * kStrip;          // 32 KiB
-constexpr int kLevels = 9;                          // log2(512)
+constexpr int kCkThreads = 1024;
+constexpr int kPiece = 16;                          // bytes per thread per tile: one 16-byte vector load
+constexpr int kTile = kCkThreads * kPiece;          // 16 KiB
+constexpr int kLevels = 10;                         // log2(1024)
 
 struct CkTables {
-	uint32_t slice[4][256];       // slice-by-4
-	uint32_t gap[4][256];         // append (kTile - kStrip) zero bytes
-	uint32_t lvl[kLevels][4][256];// append kStrip * 2^k zero bytes
+	uint32_t word[4][256];        // append 4 zero bytes (one slice-by-4 step without data)
+	uint32_t gap[4][256];         // append kTile zero bytes
+	uint32_t lvl[kLevels][4][256];// append kPiece * 2^k zero bytes
 };
 struct CkConst {
 	uint32_t x2n[32];             // x^(2^n) mod P
@@ -73,12 +75,10 @@ __device__ inline uint32_t x2nmodp_dev(uint64_t n, unsigned k)
 }
 
 struct __align__(16) CkSmem {
-	uint8_t tile[2][kCkThreads * kStripPad];   // 2 x 40 KiB
-	// slice-by-4 tables, one private copy per lane: entry (k, v) of lane L sits at word ((k*256 + v) * 32 + L),
+	// the tile-shift table, one private copy per lane: entry (k, v) of lane L sits at word ((k*256 + v) * 32 + L),
 	// i.e. always in bank L, so the four data-dependent look-ups per word never conflict (a single shared
-	// copy cost ~3.5 wavefronts per look-up and bounded the kernel at a third of the HBM peak)
-	uint32_t slice32[4 * 256 * 32];            // 128 KiB
-	uint32_t gap[4][256];
+	// copy costs ~3.5 wavefronts per look-up)
+	uint32_t gap32[4 * 256 * 32];              // 128 KiB
 	uint32_t red[kCkThreads / 32][4];
 };
 
@@ -86,38 +86,34 @@ __device__ __forceinline__ uint32_t apply4(const uint32_t (*t)[256], uint32_t c)
 {
 	return t[0][c & 255] ^ t[1][(c >> 8) & 255] ^ t[2][(c >> 16) & 255] ^ t[3][c >> 24];
 }
-// crc register after one more little-endian word; sl = the lane's own table copy (slice32 + lane)
-__device__ __forceinline__ uint32_t crc_word(const uint32_t *sl, uint32_t c, uint32_t w)
+// shift a register by one tile; g = the lane's own table copy (gap32 + lane)
+__device__ __forceinline__ uint32_t shift_tile(const uint32_t *g, uint32_t c)
 {
-	c ^= w;
-	return sl[(3 * 256 + (c & 255)) << 5] ^ sl[(2 * 256 + ((c >> 8) & 255)) << 5] ^ sl[(1 * 256 + ((c >> 16) & 255)) << 5] ^ sl[(c >> 24) << 5];
+	return g[(c & 255) << 5] ^ g[(256 + ((c >> 8) & 255)) << 5] ^ g[(512 + ((c >> 16) & 255)) << 5] ^ g[(768 + (c >> 24)) << 5];
 }
 
 struct Range { const uint8_t *src; uint64_t len; uint64_t after; uint32_t job; uint32_t pad_; };
 struct Partial { uint32_t crc, s1, s2, pad_; };
 
-__device__ void stage_tile(CkSmem &S, int buf, const uint8_t *abase, uint64_t tile_off, uint64_t valid_lo, uint64_t valid_hi)
+// the thread's 16 bytes of the tile at tile_off; bytes outside [valid_lo, valid_hi) read as zero
+__device__ __forceinline__ uint4 load_piece(const uint8_t *abase, uint64_t tile_off, uint64_t valid_lo, uint64_t valid_hi)
 {
-	// thread t stages its own 64-byte strip (4 x 16 B); out-of-range bytes become zero
-	uint8_t *dst = S.tile[buf] + threadIdx.x * kStripPad;
-	const uint64_t o = tile_off + (uint64_t)threadIdx.x * kStrip;
-#pragma unroll
-	for (int k = 0; k < 4; k++) {
-		const uint64_t p = o + 16 * k;
-		if (p >= valid_lo && p + 16 <= valid_hi) {
-			uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst + 16 * k);
-			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(abase + p));
-		} else {
-			uint32_t w[4] = { 0, 0, 0, 0 };
-			for (int b = 0; b < 16; b++) {
-				const uint64_t q = p + b;
-				if (q >= valid_lo && q < valid_hi)
-					w[b >> 2] |= (uint32_t)abase[q] << (8 * (b & 3));
-			}
-			*reinterpret_cast<uint4 *>(dst + 16 * k) = make_uint4(w[0], w[1], w[2], w[3]);
+	const uint64_t p = tile_off + (uint64_t)threadIdx.x * kPiece;
+	if (p >= valid_lo && p + kPiece <= valid_hi) {
+		uint4 v;
+		// streaming data, read once: do not keep it in L1
+		asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(abase + p));
+		return v;
+	}
+	uint32_t w[4] = { 0, 0, 0, 0 };
+	if (p < valid_hi && p + kPiece > valid_lo) {
+		for (int b = 0; b < kPiece; b++) {
+			const uint64_t q = p + b;
+			if (q >= valid_lo && q < valid_hi)
+				w[b >> 2] |= (uint32_t)abase[q] << (8 * (b & 3));
 		}
 	}
-	asm volatile("cp.async.commit_group;\n" ::);
+	return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 template <bool kCrc, bool kAdler>
@@ -127,13 +123,11 @@ checksum_ranges_kernel(const Range *__restrict__ ranges, uint32_t n_ranges, Part
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	CkSmem &S = *reinterpret_cast<CkSmem *>(smem_raw);
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-	for (int i = t; i < 1024; i += kCkThreads)
-		(&S.gap[0][0])[i] = (&g_tables.gap[0][0])[i];
 	if (kCrc)
 		for (int i = t; i < 4 * 256 * 32; i += kCkThreads)
-			S.slice32[i] = (&g_tables.slice[0][0])[i >> 5];
+			S.gap32[i] = (&g_tables.gap[0][0])[i >> 5];
 	__syncthreads();
-	const uint32_t *sl = S.slice32 + lane;
+	const uint32_t *g = S.gap32 + lane;
 
 	for (uint32_t r = blockIdx.x; r < n_ranges; r += gridDim.x) {
 		const Range R = ranges[r];
@@ -141,46 +135,43 @@ checksum_ranges_kernel(const Range *__restrict__ ranges, uint32_t n_ranges, Part
 		const uint8_t *abase = reinterpret_cast<const uint8_t *>(a & ~(uintptr_t)15);
 		const uint64_t lead = a & 15, vhi = lead + R.len;
 		const uint64_t ntiles = (vhi + kTile - 1) / kTile;
-		uint32_t crc = 0;
-		uint32_t cumA = 0, sumB = 0, P = 0;      // Adler partial sums of this thread, mod 65521
-		if (ntiles)
-			stage_tile(S, 0, abase, 0, lead, vhi);
+		uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;         // one CRC accumulator per 32-bit word column of the piece
+		uint32_t cumA = 0;                               // Adler: byte sum so far (< 2^32 for ranges below 16 GiB)
+		unsigned long long sumB = 0, P = 0;              // position-weighted sums inside the pieces; sum over tiles of the byte sum in front
+		uint4 nxt = ntiles ? load_piece(abase, 0, lead, vhi) : make_uint4(0, 0, 0, 0);
+		uint4 nxt2 = ntiles > 1 ? load_piece(abase, kTile, lead, vhi) : make_uint4(0, 0, 0, 0);
 		for (uint64_t k = 0; k < ntiles; k++) {
-			if (k + 1 < ntiles) {
-				stage_tile(S, (int)((k + 1) & 1), abase, (k + 1) * kTile, lead, vhi);
-				asm volatile("cp.async.wait_group 1;\n" ::);
-			} else {
-				asm volatile("cp.async.wait_group 0;\n" ::);
-			}
-			// each thread reads only what it staged itself: no CTA barrier needed
-			const uint4 *src = reinterpret_cast<const uint4 *>(S.tile[k & 1] + t * kStripPad);
-			if (kCrc && k)
-				crc = apply4(S.gap, crc);
-			uint32_t a_ = 0, b_ = 0;
-#pragma unroll
-			for (int q = 0; q < 4; q++) {
-				const uint4 v = src[q];
-				const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-				for (int j = 0; j < 4; j++) {
-					if (kCrc)
-						crc = crc_word(sl, crc, w[j]);
-					if (kAdler) {
-						b_ += 4 * a_;
-						b_ = __dp4a(w[j], 0x01020304u, b_);
-						a_ = __dp4a(w[j], 0x01010101u, a_);
-					}
-				}
+			const uint4 v = nxt;
+			nxt = nxt2;
+			if (k + 2 < ntiles)
+				nxt2 = load_piece(abase, (k + 2) * kTile, lead, vhi);       // two tiles ahead: ~32 KiB in flight per SM
+			if (kCrc) {
+				c0 = shift_tile(g, c0) ^ v.x;
+				c1 = shift_tile(g, c1) ^ v.y;
+				c2 = shift_tile(g, c2) ^ v.z;
+				c3 = shift_tile(g, c3) ^ v.w;
 			}
 			if (kAdler) {
-				// a_ <= 16320, b_ <= 64*255*... < 2^21: reduce once per strip
-				P = (P + cumA) % kBase;
-				cumA = (cumA + a_) % kBase;
-				sumB = (sumB + b_) % kBase;
+				uint32_t a_ = __dp4a(v.x, 0x01010101u, 0u);
+				a_ = __dp4a(v.y, 0x01010101u, a_);
+				a_ = __dp4a(v.z, 0x01010101u, a_);
+				a_ = __dp4a(v.w, 0x01010101u, a_);
+				// byte i of the piece counts 16 - i times
+				uint32_t b_ = __dp4a(v.x, 0x0d0e0f10u, 0u);
+				b_ = __dp4a(v.y, 0x090a0b0cu, b_);
+				b_ = __dp4a(v.z, 0x05060708u, b_);
+				b_ = __dp4a(v.w, 0x01020304u, b_);
+				P += cumA;
+				cumA += a_;
+				sumB += b_;
 			}
 		}
-		// ---- fold the 512 strip registers: neighbour pairs, shift doubles each level ----
+		// ---- fold: the thread's four columns (Horner, one 4-byte shift each), then the 1024 pieces as a tree ----
+		uint32_t crc = 0;
 		if (kCrc) {
+			crc = apply4(g_tables.word, c0) ^ c1;
+			crc = apply4(g_tables.word, crc) ^ c2;
+			crc = apply4(g_tables.word, crc) ^ c3;
 #pragma unroll
 			for (int lv = 0; lv < 5; lv++) {
 				const uint32_t other = __shfl_down_sync(0xffffffffu, crc, 1 << lv);
@@ -190,10 +181,11 @@ checksum_ranges_kernel(const Range *__restrict__ ranges, uint32_t n_ranges, Part
 		}
 		uint32_t s1 = 0, s2 = 0;
 		if (kAdler) {
-			// S2_t = sumB + c_t * cumA + kTile * P,  c_t = bytes after this strip inside a tile
-			const uint32_t ct = (uint32_t)(kCkThreads - 1 - t) * kStrip;
-			s1 = cumA;
-			s2 = (uint32_t)((sumB + (uint64_t)ct * cumA + (uint64_t)(kTile % kBase) * P) % kBase);
+			// S2_t = sumB + c_t * cumA + kTile * P,  c_t = bytes behind this piece inside a tile
+			const uint32_t ct = (uint32_t)(kCkThreads - 1 - t) * kPiece;
+			const uint32_t A = cumA % kBase;
+			s1 = A;
+			s2 = (uint32_t)((sumB % kBase + (uint64_t)ct * A + (uint64_t)(kTile % kBase) * (P % kBase)) % kBase);
 			for (int o = 16; o; o >>= 1) {
 				s1 += __shfl_xor_sync(0xffffffffu, s1, o);
 				s2 += __shfl_xor_sync(0xffffffffu, s2, o);
@@ -206,9 +198,9 @@ checksum_ranges_kernel(const Range *__restrict__ ranges, uint32_t n_ranges, Part
 		}
 		__syncthreads();
 		if (warp == 0) {
-			uint32_t c = lane < kCkThreads / 32 ? S.red[lane][0] : 0;
-			uint32_t x1 = lane < kCkThreads / 32 ? S.red[lane][1] : 0;
-			uint32_t x2 = lane < kCkThreads / 32 ? S.red[lane][2] : 0;
+			uint32_t c = S.red[lane][0];
+			uint32_t x1 = S.red[lane][1];
+			uint32_t x2 = S.red[lane][2];
 			if (kCrc) {
 #pragma unroll
 				for (int lv = 5; lv < kLevels; lv++) {
@@ -222,10 +214,11 @@ checksum_ranges_kernel(const Range *__restrict__ ranges, uint32_t n_ranges, Part
 				x2 += __shfl_xor_sync(0xffffffffu, x2, o);
 			}
 			if (lane == 0) {
-				// undo the zero padding behind the data (z bytes) and account for the lead-in
+				// a word entered its accumulator unshifted: one more 4-byte step makes it the register "after the word";
+				// then undo the zero padding behind the data (z bytes)
 				const uint64_t z = ntiles * kTile - vhi;
 				Partial p;
-				p.crc = kCrc ? multmodp(multmodp(c_ck.inv_hi[z >> 8], c_ck.inv_lo[z & 255]), c) : 0;
+				p.crc = kCrc ? multmodp(multmodp(c_ck.inv_hi[z >> 8], c_ck.inv_lo[z & 255]), apply4(g_tables.word, c)) : 0;
 				x1 %= kBase; x2 %= kBase;
 				// S2 was taken over the padded message: true b = S2 - z * S1
 				const uint32_t zz = (uint32_t)(z % kBase);
@@ -350,21 +343,14 @@ static cudaError_t upload_tables()
 {
 	static CkTables T;            // the caller holds g_tables_once's lock
 	static CkConst C;
-	for (uint32_t n = 0; n < 256; n++) {
-		uint32_t c = n;
-		for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ kPoly : c >> 1;
-		T.slice[0][n] = c;
-	}
-	for (int k = 1; k < 4; k++)
-		for (int n = 0; n < 256; n++)
-			T.slice[k][n] = (T.slice[k - 1][n] >> 8) ^ T.slice[0][T.slice[k - 1][n] & 255];
 	uint32_t p = 1u << 30;
 	C.x2n[0] = p;
 	for (int n = 1; n < 32; n++)
 		C.x2n[n] = p = multmodp(p, p);
-	make_shift_table(host_x8n(kTile - kStrip, C.x2n), T.gap);
+	make_shift_table(host_x8n(4, C.x2n), T.word);
+	make_shift_table(host_x8n(kTile, C.x2n), T.gap);
 	for (int lv = 0; lv < kLevels; lv++)
-		make_shift_table(host_x8n((uint64_t)kStrip << lv, C.x2n), T.lvl[lv]);
+		make_shift_table(host_x8n((uint64_t)kPiece << lv, C.x2n), T.lvl[lv]);
 	const uint64_t ord = 0xFFFFFFFFull;          // order of x modulo the (primitive) CRC-32 polynomial
 	for (int i = 0; i < 128; i++)
 		C.inv_hi[i] = host_xpow_bits((ord - (8ull * 256 * i) % ord) % ord, C.x2n);
@@ -400,7 +386,7 @@ cudaError_t launch_checksum_ranges(const void *d_ranges, uint32_t n_ranges, void
 {
 	if (n_ranges == 0)
 		return cudaSuccess;
-	uint32_t grid = n_ranges < (uint32_t)kNumSMs ? n_ranges : (uint32_t)kNumSMs;      // one CTA per SM (212 KiB of shared memory)
+	uint32_t grid = n_ranges < (uint32_t)kNumSMs ? n_ranges : (uint32_t)kNumSMs;      // one CTA per SM (128 KiB of shared memory, 1024 threads)
 	const Range *r = static_cast<const Range *>(d_ranges);
 	Partial *p = static_cast<Partial *>(d_parts);
 	if (which == 1)

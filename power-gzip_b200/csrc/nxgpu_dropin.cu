@@ -204,14 +204,53 @@ void nxgpu_job_stats(int dev, uint64_t *batches, uint64_t *jobs, uint64_t *max_b
 	if (max_batch) *max_batch = q.max_batch;
 }
 
+// Small-call policy (the reference has one at this very boundary: lib/nx_crc.c:247-255 keeps a table loop below 32 bytes
+// because starting the vector unit costs more than it saves, and lib/nx_zlib.h:88-89 sends streams below 1 KiB to
+// software).  A GPU call costs ~50 us of launch + synchronisation, the time a host core needs for ~64 KiB: below
+// NXGPU_CRC_MIN_BYTES (default 65536) the 16-byte aligned middle is folded by a slice-by-8 table loop on the calling
+// thread, exactly like the head and tail bytes the reference's crc32_ppc() already folds with its byte table
+// (lib/crc32_ppc.c:22-28,40-50).  Anything larger goes to the device; requests of concurrent threads coalesce.
+static uint32_t g_crc_tab[8][256];
+static std::once_flag g_crc_tab_once;
+static void crc_tab_init()
+{
+	for (uint32_t n = 0; n < 256; n++) {
+		uint32_t c = n;
+		for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
+		g_crc_tab[0][n] = c;
+	}
+	for (int k = 1; k < 8; k++)
+		for (int n = 0; n < 256; n++)
+			g_crc_tab[k][n] = (g_crc_tab[k - 1][n] >> 8) ^ g_crc_tab[0][g_crc_tab[k - 1][n] & 255];
+}
+static unsigned int crc_small(unsigned int crc, const uint8_t *p, unsigned long len)
+{
+	std::call_once(g_crc_tab_once, crc_tab_init);
+	while (len >= 8) {
+		uint32_t a, b;
+		memcpy(&a, p, 4); memcpy(&b, p + 4, 4);
+		a ^= crc;
+		crc = g_crc_tab[7][a & 255] ^ g_crc_tab[6][(a >> 8) & 255] ^ g_crc_tab[5][(a >> 16) & 255] ^ g_crc_tab[4][a >> 24] ^
+		      g_crc_tab[3][b & 255] ^ g_crc_tab[2][(b >> 8) & 255] ^ g_crc_tab[1][(b >> 16) & 255] ^ g_crc_tab[0][b >> 24];
+		p += 8; len -= 8;
+	}
+	while (len--) crc = g_crc_tab[0][(crc ^ *p++) & 255] ^ (crc >> 8);
+	return crc;
+}
+
 unsigned int __crc32_vpmsum(unsigned int crc, const void *p, unsigned long len)
 {
+	static const unsigned long min_bytes = getenv("NXGPU_CRC_MIN_BYTES") ? strtoul(getenv("NXGPU_CRC_MIN_BYTES"), nullptr, 0) : 65536;
+	if (len < min_bytes)
+		return crc_small(crc, static_cast<const uint8_t *>(p), len);
 	Request r;
 	r.kind = Request::CRC;
 	r.crc = crc; r.p = p; r.len = len;
 	if (submit(0, r) != 0) {
-		fprintf(stderr, "libnxgpu: __crc32_vpmsum: no usable GPU (%s)\n", nxgpu_last_error());
-		abort();                  // no CPU fallback: fail loudly
+		// The reference's signature has no error channel (lib/crc32_ppc.c:30) and a wrong CRC would be silent data
+		// corruption in the caller: a large buffer without a usable sm_100 device ends the process, loudly.
+		fprintf(stderr, "libnxgpu: __crc32_vpmsum(%lu bytes): no usable sm_100 GPU (%s); refusing to return a checksum\n", len, nxgpu_last_error());
+		abort();
 	}
 	return r.crc;
 }

@@ -51,3 +51,47 @@ def test_product_does_not_touch_the_oracle():
     so = os.path.join(ROOT, "power-gzip_b200", "libnxgpu.so")
     needed = subprocess.run(["readelf", "-d", so], capture_output=True, text=True).stdout
     assert "oracle" not in needed and "libz" not in needed
+
+
+def test_drop_in_library_keeps_the_reference_abi():
+    """The reference guards its ABI with test/test_abi (abidiff against test/libnxz.abi; abidiff is not in this image).
+    Same intent with readelf: the drop-in library (reference host code over libnxgpu.so, linked with the reference's own
+    version script lib/Versions) must define every function symbol of libnxz.abi under the same version node, and nothing
+    of the engine's internals may leak into its dynamic symbol table."""
+    import json
+    import pytest
+    so = os.path.join(ROOT, "power-gzip_b200", "libnxz_gpu.so")
+    if not os.path.exists(so):
+        pytest.skip("power-gzip_b200/libnxz_gpu.so not built (needs /root/reference at build time)")
+    want = {(n, v) for n, v in json.load(open(os.path.join(ROOT, "tests", "golden", "libnxz_abi_symbols.json")))["functions"]}
+    out = subprocess.run(["readelf", "--dyn-syms", "-W", so], capture_output=True, text=True).stdout
+    have = set()
+    for line in out.splitlines():
+        f = line.split()
+        if len(f) >= 8 and f[3] == "FUNC" and f[6] != "UND" and f[4] in ("GLOBAL", "WEAK"):
+            name, _, ver = f[7].partition("@@")
+            have.add((name, ver))
+    missing = want - have
+    assert not missing, sorted(missing)[:10]
+    extra = {n for n, _ in have - want}
+    # the six boundary symbols are imported (UND), never re-exported; nothing else may appear
+    assert not extra, sorted(extra)[:10]
+    needed = subprocess.run(["readelf", "-d", so], capture_output=True, text=True).stdout
+    assert "libnxgpu.so" in needed and "libnxz.so.1" in needed
+
+
+def test_crc32_vpmsum_small_calls_stay_on_the_calling_thread(pg):
+    """Below NXGPU_CRC_MIN_BYTES (64 KiB) the boundary's CRC is a table loop on the caller, as the reference keeps one below
+    its own break-even (lib/nx_crc.c:247-255): no device is needed, so this runs on the build container too."""
+    import ctypes as C
+    import random
+    import zlib
+    lib = pg.load_library()
+    rnd = random.Random(4)
+    for n in (0, 16, 32, 48, 4096, 65520):
+        data = rnd.randbytes(n)
+        for seed in (0, 0xffffffff, 0x12345678):
+            buf = C.create_string_buffer(data, max(n, 1))
+            got = lib.__crc32_vpmsum(seed, C.addressof(buf), n)
+            # raw update: no pre/post inversion (lib/crc32_ppc.c:33-67 inverts around the call)
+            assert got == (zlib.crc32(data, seed ^ 0xffffffff) ^ 0xffffffff), (n, hex(seed))

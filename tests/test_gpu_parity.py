@@ -680,3 +680,40 @@ def test_inflate_malformed_streams_like_zlib(engine, pg, alice):
             assert r.rc != 0, (i, "zlib rejects this stream, the engine accepted it", s[:12].hex(), r.out_len)
             n_rej += 1
     assert 50 < n_rej < len(cases)
+
+
+@pytest.mark.gpu
+def test_gzread_of_a_multi_member_file(engine, pg, alice, tmp_path):
+    """gzopen / gzread / gzeof / gzclose over the batched inflate: a file of many concatenated members (`cat a.gz b.gz`, what
+    the reference's own gzread cannot read past the first member of, lib/nx_gzlib.c:220-263) comes back whole through
+    65 521-byte reads; an empty file reads as empty; a corrupted member is an error, not short data."""
+    lib = engine.lib
+    parts = [alice, b"", pg.makedata(1, 20, alice)[:700001], b"x", alice[:3]] + [alice[i * 1000:(i + 3) * 1000] for i in range(40)]
+    path = tmp_path / "multi.gz"
+    path.write_bytes(b"".join(gzip.compress(p, 6) for p in parts))
+    want = b"".join(parts)
+    f = lib.nxgpu_gzopen(engine.ctx, str(path).encode(), b"rb")
+    assert f, pg.last_error()
+    got = bytearray()
+    buf = C.create_string_buffer(65521)
+    while True:
+        n = lib.nxgpu_gzread(f, buf, 65521)
+        assert n >= 0, pg.last_error()
+        if n == 0:
+            break
+        got += buf.raw[:n]
+    assert lib.nxgpu_gzeof(f) == 1 and lib.nxgpu_gzmembers(f) == len(parts)
+    assert lib.nxgpu_gzclose(f) == 0
+    assert bytes(got) == want
+    # own context, file descriptor flavour, empty file
+    empty = tmp_path / "empty.gz"
+    empty.write_bytes(b"")
+    f = lib.nxgpu_gzdopen(None, os.open(str(empty), os.O_RDONLY), b"r")
+    assert f and lib.nxgpu_gzread(f, buf, 100) == 0 and lib.nxgpu_gzclose(f) == 0
+    bad = bytearray(path.read_bytes())
+    bad[len(gzip.compress(alice, 6)) + 40] ^= 0x10          # inside the third member
+    (tmp_path / "bad.gz").write_bytes(bytes(bad))
+    f = lib.nxgpu_gzopen(engine.ctx, str(tmp_path / "bad.gz").encode(), b"r")
+    assert f and lib.nxgpu_gzread(f, buf, 100) == -1
+    assert lib.nxgpu_gzclose(f) != 0
+    assert not lib.nxgpu_gzopen(engine.ctx, str(path).encode(), b"w")      # only the read side is bound
