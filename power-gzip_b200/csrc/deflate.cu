@@ -49,7 +49,8 @@ struct __align__(16) Smem {
 	uint16_t prev[65536];             // 128 KiB: distance to the previous position with the same hash
 	uint16_t head[kHashSize];         // 32 KiB: low 16 bits of the most recent position per hash
 	uint64_t mbar[kSlots];            // TMA completion barriers of the staging blocks
-	uint64_t done_bar[kDoneSlots];    // producer arrives once block b's chains are built; parsers sleep on it
+	uint64_t done_bar[kDoneSlots];    // chain builder arrives once block b's chains are built; parsers sleep on it
+	uint64_t hash_bar[kDoneSlots];    // split producer: warp 0 arrives once block b's hashes sit in prev[]; warp 1 turns them into links
 	volatile uint32_t parse_pos[32];  // per parser warp: first position of the sub-block in flight
 	uint32_t next_sub;                // next sub-block to hand out
 	uint32_t ll_freq[288];
@@ -146,10 +147,23 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity)
 			ns *= 2;
 	}
 }
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+// L2 policy for data that streams through once (the input, the finished stream): evict first, so that the per-CTA
+// scratch (tokens, per-position results: written and re-read within one chunk, 148 x ~0.3 MB) stays resident in the
+// 126 MB L2 instead of being written back to DRAM behind every chunk (round 1: 2.1 x the algorithmic DRAM traffic)
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
 {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-		     ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+	return pol;
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint64_t pol)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n"
+		     ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_v4_evict_first(uint4 *p, uint4 v, uint64_t pol)
+{
+	asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;\n" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
 
 // ---- warp 0: stage the input into the ring with TMA and thread the hash chains through it ----
@@ -196,13 +210,93 @@ __device__ void build_chains(Smem &S, uint32_t lo, uint32_t hi)
 	}
 }
 
-__device__ void producer(Smem &S, const uint8_t *gbase, uint32_t P0, uint32_t PE)
+// The chain build as a two-warp pipeline (level 1 is bound by it: 3.7 cycles per position on one warp): warp 0 hashes
+// the staged positions and parks the 14-bit hash in the position's own prev[] slot, which nobody reads before the link
+// is written; warp 1 (another scheduler) reads it back and does the head exchange + link.  Same links as build_chains.
+__device__ void hash_range(Smem &S, uint32_t lo, uint32_t hi)
+{
+	const uint32_t lane = lane_id();
+	const uint8_t *ring8 = reinterpret_cast<const uint8_t *>(S.ring32);
+	constexpr int U = 4;
+	for (uint32_t p0 = lo; p0 < hi; p0 += 32 * U) {
+		uint32_t h[U];
+#pragma unroll
+		for (int u = 0; u < U; u++)
+			h[u] = hash5(ring8, p0 + 32 * u + lane);
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const uint32_t pos = p0 + 32 * u + lane;
+			if (pos < hi)
+				S.prev[pos & kRingMask] = (uint16_t)h[u];
+		}
+	}
+}
+__device__ void insert_range(Smem &S, uint32_t lo, uint32_t hi)
+{
+	const uint32_t lane = lane_id();
+	constexpr int U = 4;
+	for (uint32_t p0 = lo; p0 < hi; p0 += 32 * U) {
+		uint32_t h[U], old[U];
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const uint32_t pos = p0 + 32 * u + lane;
+			h[u] = pos < hi ? S.prev[pos & kRingMask] : 0;
+		}
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const uint32_t pos = p0 + 32 * u + lane;
+			old[u] = 0;
+			if (pos < hi) {
+				old[u] = S.head[h[u]];
+				S.head[h[u]] = (uint16_t)pos;
+			}
+			__syncwarp();
+		}
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const uint32_t pos = p0 + 32 * u + lane;
+			const uint32_t d = (pos - old[u]) & 0xFFFFu;
+			if (pos < hi)
+				S.prev[pos & kRingMask] = (uint16_t)(d <= (uint32_t)kWindow ? d : 0);
+		}
+	}
+}
+
+// warp 1 of the split producer: block by block behind the hashing warp
+__device__ void inserter(Smem &S, uint32_t P0, uint32_t PE)
+{
+	const uint32_t PEa = (PE + 15) & ~15u;
+	const uint32_t hash_hi = PE >= 4 ? PE - 4 : 0;
+	const uint32_t nblk = (PEa + kBlk - 1) / kBlk;
+	uint32_t BF = P0;
+	for (uint32_t b = 0; b < nblk; b++) {
+		const uint32_t parity = (b / kDoneSlots) & 1;
+		while (!mbar_try_wait(&S.hash_bar[b % kDoneSlots], parity))
+			__nanosleep(64);
+		__threadfence_block();
+		const uint32_t blk_hi = min((b + 1) * kBlk, PEa);
+		const uint32_t hi = (b + 1 == nblk) ? hash_hi : min(blk_hi - 4, hash_hi);
+		long long t1 = clock64();
+		if (hi > BF) {
+			insert_range(S, BF, hi);
+			BF = hi;
+		}
+		DBG_ADD(0, clock64() - t1);
+		__threadfence_block();
+		__syncwarp();
+		if (lane_id() == 0)
+			mbar_arrive(&S.done_bar[b % kDoneSlots]);
+	}
+}
+
+__device__ void producer(Smem &S, const uint8_t *gbase, uint32_t P0, uint32_t PE, bool split)
 {
 	const uint32_t lane = lane_id();
 	const uint32_t PEa = (PE + 15) & ~15u;
 	const uint32_t hash_hi = PE >= 4 ? PE - 4 : 0;           // positions with 5 bytes available
 	const uint32_t nblk = (PEa + kBlk - 1) / kBlk;
 	uint32_t issued = 0, BF = P0;
+	const uint64_t pol = l2_evict_first_policy();
 	for (uint32_t b = 0; b < nblk; b++) {
 		// keep up to two blocks in flight beyond b; only the block we need next may block on ring space
 		while (issued < nblk && issued <= b + 2) {
@@ -225,7 +319,7 @@ __device__ void producer(Smem &S, const uint8_t *gbase, uint32_t P0, uint32_t PE
 				const uint32_t bytes = min(kBlk, PEa - lo);
 				uint64_t *bar = &S.mbar[issued % kSlots];
 				mbar_expect_tx(bar, bytes);
-				tma_load_1d(reinterpret_cast<uint8_t *>(S.ring32) + (lo & kRingMask), gbase + lo, bytes, bar);
+				tma_load_1d(reinterpret_cast<uint8_t *>(S.ring32) + (lo & kRingMask), gbase + lo, bytes, bar, pol);
 			}
 			issued++;
 		}
@@ -246,15 +340,20 @@ __device__ void producer(Smem &S, const uint8_t *gbase, uint32_t P0, uint32_t PE
 		const uint32_t hi = (b + 1 == nblk) ? hash_hi : min(blk_hi - 4, hash_hi);
 		long long t1 = clock64();
 		if (hi > BF) {
-			build_chains(S, BF, hi);
+			if (split)
+				hash_range(S, BF, hi);
+			else
+				build_chains(S, BF, hi);
 			BF = hi;
 		}
-		DBG_ADD(0, clock64() - t1);
-		// block b done: chains exist for every position below (b+1)*kBlk - 4 (everything, for the last block)
+		if (!split)
+			DBG_ADD(0, clock64() - t1);
+		// block b done: chains exist for every position below (b+1)*kBlk - 4 (everything, for the last block) —
+		// or, split, their hashes are parked for warp 1
 		__threadfence_block();
 		__syncwarp();
 		if (lane == 0)
-			mbar_arrive(&S.done_bar[b % kDoneSlots]);
+			mbar_arrive(split ? &S.hash_bar[b % kDoneSlots] : &S.done_bar[b % kDoneSlots]);
 	}
 }
 
@@ -575,7 +674,15 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 			M &= (1u << nlive) - 1;
 		while (M) {
 			const uint32_t cnt = __popc(M), room = 32 - qn, tk_n = min(cnt, room);
-			const uint32_t from = __fns(M, 0, (int)(lane - qn + 1)) & 31;        // the window lane whose position this queue slot takes
+			// the window lane whose position this queue slot takes = the (lane - qn)-th set bit of M: binary search on the
+			// prefix population counts (__fns is ~60 straight-line instructions, and it ran twice per round)
+			const uint32_t want = lane - qn;
+			uint32_t from = 0;
+#pragma unroll
+			for (int st = 16; st; st >>= 1)
+				if ((uint32_t)__popc(M & (0xffffffffu >> (32 - st - from))) <= want)
+					from += st;
+			from &= 31;
 			const uint32_t ftok = __shfl_sync(0xffffffffu, mytok, from);
 			const uint32_t fcur = __shfl_sync(0xffffffffu, mycur, from);
 			if (lane >= qn && lane < qn + tk_n) {
@@ -587,7 +694,7 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 			if (tk_n == cnt)
 				M = 0;
 			else
-				M &= ~((1u << __fns(M, 0, (int)(tk_n + 1))) - 1);
+				M = __ballot_sync(0xffffffffu, ((M >> lane) & 1) && (uint32_t)__popc(M & lt) >= tk_n);    // keep the set bits behind the first tk_n
 			if (qn == 32) {
 				deep(32, min(w0 + 32, npos));
 				qn = 0;
@@ -1089,11 +1196,12 @@ __device__ void stream_out(Smem &S, const StreamOut &so, const DeflateJob &J, ui
 	const uint32_t sh = (head & 3) * 8;
 	const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src) + (head >> 2);
 	uint4 *d128 = reinterpret_cast<uint4 *>(d + head);
+	const uint64_t pol = l2_evict_first_policy();
 	for (uint32_t v = threadIdx.x; v < nvec; v += kThreads) {
 		const uint32_t *p = s32 + 4 * v;
 		const uint32_t a = p[0], b = p[1], c = p[2], e = p[3], f = sh ? p[4] : 0;
-		d128[v] = sh ? make_uint4(__funnelshift_r(a, b, sh), __funnelshift_r(b, c, sh), __funnelshift_r(c, e, sh), __funnelshift_r(e, f, sh))
-			     : make_uint4(a, b, c, e);
+		st_v4_evict_first(d128 + v, sh ? make_uint4(__funnelshift_r(a, b, sh), __funnelshift_r(b, c, sh), __funnelshift_r(c, e, sh), __funnelshift_r(e, f, sh))
+					       : make_uint4(a, b, c, e), pol);
 	}
 	const uint32_t done = head + nvec * 16;
 	if (threadIdx.x < len - done)
@@ -1147,15 +1255,17 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 			S.ll_freq[i] = 0;
 		if (threadIdx.x < 32) {
 			S.d_freq[threadIdx.x] = 0;
-			S.parse_pos[threadIdx.x] = (((parser_mask >> threadIdx.x) & 1) && n_sub) ? PS : kNone;
+			S.parse_pos[threadIdx.x] = (((parser_mask >> threadIdx.x) & 1) && threadIdx.x && n_sub) ? PS : kNone;
 		}
 		if (threadIdx.x == 0) {
 			S.n_tok = 0;
 			S.next_sub = 0;
 			for (int i = 0; i < kSlots; i++)
 				mbar_init(&S.mbar[i], 1);
-			for (int i = 0; i < kDoneSlots; i++)
+			for (int i = 0; i < kDoneSlots; i++) {
 				mbar_init(&S.done_bar[i], 1);
+				mbar_init(&S.hash_bar[i], 1);
+			}
 			asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 		}
 		// the ring was last written by ordinary stores (bit-packer staging); TMA writes come next
@@ -1163,8 +1273,11 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 		__syncthreads();
 
 		// ---- LZ77: warp 0 stages + builds chains, the parser warps take sub-blocks in order ----
+		const bool split = (parser_mask & 1) != 0;        // bit 0 (warp 0 is never a parser): chain build split over warps 0 and 1
 		if (warp == 0) {
-			producer(S, gbase, P0, PE);
+			producer(S, gbase, P0, PE, split);
+		} else if (warp == 1 && split) {
+			inserter(S, P0, PE);
 		} else if ((parser_mask >> warp) & 1) {
 			uint32_t nwin = 0;
 			long long busy = 0, waited = 0;
@@ -1209,14 +1322,16 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 			__syncwarp();
 			if (lane_id() == 0)
 				S.parse_pos[warp] = kNone;
-			if (warp == 1) { DBG_ADD(3, busy); DBG_ADD(4, waited); DBG_ADD(7, nwin); }
+			if (warp == 2) { DBG_ADD(3, busy); DBG_ADD(4, waited); DBG_ADD(7, nwin); }
 		}
 		__syncthreads();
 		if (threadIdx.x == 0) {
 			for (int i = 0; i < kSlots; i++)
 				asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&S.mbar[i])) : "memory");
-			for (int i = 0; i < kDoneSlots; i++)
+			for (int i = 0; i < kDoneSlots; i++) {
 				asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&S.done_bar[i])) : "memory");
+				asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&S.hash_bar[i])) : "memory");
+			}
 		}
 
 		// ---- stitch: per sub-block, tokens to drop in front and the cut-back last token ----
@@ -1562,11 +1677,16 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 		cudaMemsetAsync(d_dbg, 0, (size_t)grid * 64, s);
 		cudaMemcpyToSymbolAsync(g_dbg, &d_dbg, sizeof(d_dbg), 0, cudaMemcpyHostToDevice, s);
 	}
-	uint32_t parser_mask = 0xFFFFFFFEu;                       // warp 0 is the producer
+	// warp 0 stages the input and hashes it, warp 1 links the chains, warps 2-31 parse (NXGPU_PRODUCER_SPLIT=0: warp 0 does both
+	// halves of the build and warp 1 parses — the A/B switch behind profiles/)
+	static const bool split = !(getenv("NXGPU_PRODUCER_SPLIT") && atoi(getenv("NXGPU_PRODUCER_SPLIT")) == 0);
+	uint32_t parser_mask = split ? 0xFFFFFFFCu : 0xFFFFFFFEu;
 	if (const char *pm = getenv("NXGPU_PARSER_MASK"))
-		parser_mask = (uint32_t)strtoul(pm, nullptr, 0) & 0xFFFFFFFEu;
+		parser_mask = (uint32_t)strtoul(pm, nullptr, 0) & (split ? 0xFFFFFFFCu : 0xFFFFFFFEu);
 	if (parser_mask == 0)
-		parser_mask = 2;
+		parser_mask = split ? 4 : 2;
+	if (split)
+		parser_mask |= 1;                                 // bit 0 = split (warp 0 never parses)
 	cudaError_t me = cudaMemsetAsync(job_counter, 0, sizeof(uint32_t), s);
 	if (me != cudaSuccess)
 		return me;
@@ -1582,7 +1702,7 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 		const double st = t[4] ? (double)t[4] : 1.0;
 		(void)st;
 		const double nj = n_jobs;
-		fprintf(stderr, "[nxgpu cycles/job] level %d (depth %d lazy %d nice %d d1 %d): producer build %.0f wait-data %.0f wait-space %.0f | parser(w1) busy %.0f wait %.0f windows %.0f | huff+pack %.0f total %.0f\n",
+		fprintf(stderr, "[nxgpu cycles/job] level %d (depth %d lazy %d nice %d d1 %d): chain link/build %.0f wait-data %.0f wait-space %.0f | parser(w2) busy %.0f wait %.0f windows %.0f | huff+pack %.0f total %.0f\n",
 			level, lp.depth, lp.lazy, lp.nice, lp.d1, t[0] / nj, t[1] / nj, t[2] / nj, t[3] / nj, t[4] / nj, t[7] / nj, t[5] / nj, t[6] / nj);
 		d_dbg = nullptr;
 		cudaMemcpyToSymbol(g_dbg, &d_dbg, sizeof(d_dbg));

@@ -79,7 +79,17 @@ void serve(nxgpu_ctx *ctx, std::vector<Request *> &batch)
 		if (r->kind == Request::JOB) { crbs.push_back(r->crb); jobs.push_back(r); }
 	if (!crbs.empty()) {
 		std::vector<int> rcs(crbs.size(), 0);
+		static const bool trace = getenv("NXGPU_TRACE") != nullptr;
+		struct timespec t0, t1;
+		if (trace) clock_gettime(CLOCK_MONOTONIC, &t0);
 		nxgpu::run_jobs_batch(ctx, crbs.data(), rcs.data(), crbs.size());
+		if (trace) {
+			clock_gettime(CLOCK_MONOTONIC, &t1);
+			uint64_t src = 0;
+			for (uint8_t *c : crbs) src += (uint32_t)c[NXGPU_CRB_SRC_DDE + 4] << 24 | (uint32_t)c[NXGPU_CRB_SRC_DDE + 5] << 16 | (uint32_t)c[NXGPU_CRB_SRC_DDE + 6] << 8 | c[NXGPU_CRB_SRC_DDE + 7];
+			fprintf(stderr, "nxgpu batch: %zu descriptors, %llu source bytes, fc0 %02x cc0 %u, %.0f us\n", crbs.size(), (unsigned long long)src, crbs[0][3],
+				crbs[0][NXGPU_CRB_CSB + 2], ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / 1e3);
+		}
 		for (size_t i = 0; i < jobs.size(); i++)
 			jobs[i]->rc = rcs[i];
 	}
