@@ -140,11 +140,19 @@ checksum_ranges_kernel(const Range *__restrict__ ranges, uint32_t n_ranges, Part
 		unsigned long long sumB = 0, P = 0;              // position-weighted sums inside the pieces; sum over tiles of the byte sum in front
 		uint4 nxt = ntiles ? load_piece(abase, 0, lead, vhi) : make_uint4(0, 0, 0, 0);
 		uint4 nxt2 = ntiles > 1 ? load_piece(abase, kTile, lead, vhi) : make_uint4(0, 0, 0, 0);
-		for (uint64_t k = 0; k < ntiles; k++) {
+		// tiles 1 .. ntiles-2 lie wholly inside the range: their loads need no bounds checks
+		const uint8_t *pp = abase + (uint64_t)t * kPiece + 2 * (uint64_t)kTile;
+		const uint32_t nt = (uint32_t)ntiles;
+		for (uint32_t k = 0; k < nt; k++) {
 			const uint4 v = nxt;
 			nxt = nxt2;
-			if (k + 2 < ntiles)
-				nxt2 = load_piece(abase, (k + 2) * kTile, lead, vhi);       // two tiles ahead: ~32 KiB in flight per SM
+			if (k + 3 < nt) {
+				// two tiles ahead: ~32 KiB in flight per SM; streaming data, read once: do not keep it in L1
+				asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(nxt2.x), "=r"(nxt2.y), "=r"(nxt2.z), "=r"(nxt2.w) : "l"(pp));
+			} else if (k + 2 < nt) {
+				nxt2 = load_piece(abase, (uint64_t)(k + 2) * kTile, lead, vhi);
+			}
+			pp += kTile;
 			if (kCrc) {
 				c0 = shift_tile(g, c0) ^ v.x;
 				c1 = shift_tile(g, c1) ^ v.y;
