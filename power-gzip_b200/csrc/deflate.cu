@@ -537,7 +537,7 @@ __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, ui
 // chain again; only strictly longer matches replace it, so the 4-byte filter rejects the candidates that
 // produced it without a full compare and the result is the same as walking from scratch)
 __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, uint32_t pos, uint32_t maxl, uint32_t maxdist,
-					   int depth, uint32_t nice, uint32_t vbatch, uint32_t &bl, uint32_t &bd, uint32_t seed = 0,
+					   int depth, uint32_t nice, uint32_t &bl, uint32_t &bd, uint32_t seed = 0,
 					   uint32_t *cursor = nullptr, uint32_t resume = 0xffffffffu)
 {
 	// cursor: where this walk stopped in the chain (distance walked << 16 | next link), so that a later, deeper
@@ -564,43 +564,28 @@ __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, 
 		acc = resume >> 16;
 		d = resume & 0xffffu;
 	}
-	// Hops and full comparisons are decoupled: a candidate that passes the 4-byte filter is parked (pend) and its lane
-	// stops hopping; the comparison (~45 instructions whatever the lane count) runs once `vbatch` lanes are parked or no
-	// lane can hop any more, instead of once per hop for the 6 lanes (ncu, round 1) that happened to pass together.
-	// Every lane still sees its candidates in the same order with the same filter, so the result is unchanged.
-	uint32_t pend = 0;
-	int left = depth;
-	for (;;) {
-		if (d != 0 && pend == 0 && left > 0) {
-			left--;
+	for (int hop = 0; hop < depth; hop++) {
+		if (!__any_sync(0xffffffffu, d != 0))
+			break;
+		if (d) {
 			acc += d;
 			if (acc > maxdist) {
 				d = 0;
 			} else {
 				const uint32_t q = pos - acc;
 				d = S.prev[q & kRingMask];
-				if (load4(ring8, q + bl - 3) == endw)
-					pend = acc;
-			}
-		}
-		const uint32_t pm = __ballot_sync(0xffffffffu, pend != 0);
-		const uint32_t hm = __ballot_sync(0xffffffffu, d != 0 && pend == 0 && left > 0);
-		if (pm && ((uint32_t)__popc(pm) >= vbatch || hm == 0)) {
-			if (pend) {
-				const uint32_t len = match_length(ring8, pos, pos - pend, maxl, P0, P1, P2, P3);
-				if (len > bl) {
-					bl = len; bd = pend;
-					if (len >= nice || len >= maxl)
-						d = 0;
-					else
-						endw = load4(ring8, pos + bl - 3);
+				if (load4(ring8, q + bl - 3) == endw) {
+					const uint32_t len = match_length(ring8, pos, q, maxl, P0, P1, P2, P3);
+					if (len > bl) {
+						bl = len; bd = acc;
+						if (len >= nice || len >= maxl)
+							d = 0;
+						else
+							endw = load4(ring8, pos + bl - 3);
+					}
 				}
-				pend = 0;
 			}
-			continue;
 		}
-		if (hm == 0)
-			break;
 	}
 	if (cursor)
 		*cursor = acc << 16 | d;
@@ -628,7 +613,7 @@ __device__ __forceinline__ void window_parse(uint32_t lane, uint32_t nlive, uint
 }
 
 __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_hi, uint32_t valid_lo, uint32_t PE,
-					 int d1, int depth, int nice, int lazy, uint32_t vbatch, uint32_t *tk, uint32_t *pres,
+					 int d1, int depth, int nice, int lazy, uint32_t *tk, uint32_t *pres,
 					 uint32_t &nwin, uint32_t &end_pos)
 {
 	const uint32_t lane = lane_id();
@@ -653,7 +638,7 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 		const uint32_t pos = act ? qpos : sub_lo;
 		const uint32_t maxl = act ? min((uint32_t)kMaxMatch, PE - pos) : 0;
 		uint32_t bl, bd;
-		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), max(1, depth - d1), (uint32_t)nice, vbatch, bl, bd, act ? qtok : 0, nullptr, act ? qcur : 0);   // the first d1 hops were walked by the shallow pass
+		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), max(1, depth - d1), (uint32_t)nice, bl, bd, act ? qtok : 0, nullptr, act ? qcur : 0);   // the first d1 hops were walked by the shallow pass
 		if (act && bl >= (uint32_t)kMinMatch)
 			__stcg(&pres[pos - sub_lo], tok_match(bl, bd));
 	};
@@ -667,7 +652,7 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 		const uint32_t maxl = live ? min((uint32_t)kMaxMatch, PE - pos) : 0;
 		uint32_t bl, bd;
 		uint32_t mycur;
-		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), d1, (uint32_t)nice, vbatch, bl, bd, 0, &mycur);
+		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), d1, (uint32_t)nice, bl, bd, 0, &mycur);
 		const uint32_t len = bl >= (uint32_t)kMinMatch ? bl : 0;
 		const uint32_t mytok = len ? tok_match(len, bd) : 0;
 		if (live)
@@ -1324,7 +1309,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 				const long long t1 = clock64();
 				uint32_t end_pos;
 				const uint32_t cnt = d1
-					? parse_subblock_2pass(S, sub_lo, sub_hi, P0, PE, d1 & 0xff, depth, nice, lazy, (uint32_t)d1 >> 8, tokpos + (size_t)sb * kSub,
+					? parse_subblock_2pass(S, sub_lo, sub_hi, P0, PE, d1, depth, nice, lazy, tokpos + (size_t)sb * kSub,
 							       pres + (size_t)warp * (kSub + 32), nwin, end_pos)
 					: parse_subblock(S, sub_lo, sub_hi, P0, PE, depth, nice, lazy, tokpos + (size_t)sb * kSub, nwin, end_pos);
 				if (lane_id() == 0) {
@@ -1705,11 +1690,8 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 	cudaError_t me = cudaMemsetAsync(job_counter, 0, sizeof(uint32_t), s);
 	if (me != cudaSuccess)
 		return me;
-	// how many parked filter hits trigger a batched comparison in the chain walk (1 = compare at once, as round 1 did)
-	static const int vbatch = getenv("NXGPU_VERIFY_BATCH") ? atoi(getenv("NXGPU_VERIFY_BATCH")) : 12;
-	const int d1v = lp.d1 | (vbatch < 1 ? 1 : vbatch > 32 ? 32 : vbatch) << 8;       // rides in the high bits of d1
 	deflate_kernel<<<grid, kThreads, sizeof(Smem), s>>>(jobs, outs, n_jobs, lp.depth, lp.lazy, lp.nice, tok_scratch, tok_stride, parser_mask,
-							    job_counter, ready, jobs_per_flag ? jobs_per_flag : 1, lp.d1 ? d1v : 0, so ? *so : StreamOut());
+							    job_counter, ready, jobs_per_flag ? jobs_per_flag : 1, lp.d1, so ? *so : StreamOut());
 	cudaError_t e = cudaGetLastError();
 	if (dbg) {
 		std::vector<unsigned long long> h((size_t)grid * 8);

@@ -289,7 +289,14 @@ __device__ int parse_dyn_header(BitReader &br, uint8_t *lens, int &hlit, int &hd
 	return rc;
 }
 
-__device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
+// kWin: the last 32 KiB of output are mirrored in a shared-memory ring (win), and every match source is read from
+// there instead of from global memory.  A warp that is alone with its stream (a lone uncompress() through
+// nxu_run_job, a handful of large members) otherwise pays an L2 round trip per materialise step and per
+// short-distance match: 54 MB/s.  With thousands of members in flight the other warps hide that latency and the
+// 32 KiB per warp would cost occupancy, so the batch kernel keeps reading the window from L1/L2.
+constexpr uint32_t kWinBytes = 32768;
+template <bool kWin>
+__device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, uint8_t *win)
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const bool job = J.wrap == kWrapJob;     // NX decompress-job semantics: stop at the source end and report where
@@ -304,6 +311,14 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 	br.setup(J.src, J.src_len, T.in);   // every lane knows the geometry; the read position lives in lane 0
 	int rc = 0;                      // uniform after each broadcast
 	uint32_t out = 0;
+	// window ring: output position p (counted from the first history byte) lives at win[p % 32 KiB]
+	const uint32_t wofs = J.hist_len;
+	if (kWin) {
+		const uint32_t h = J.hist_len < kWinBytes ? J.hist_len : kWinBytes;
+		for (uint32_t i = lane; i < h; i += 32)
+			win[(wofs - h + i) & (kWinBytes - 1)] = J.dst[(int32_t)i - (int32_t)h];
+		__syncwarp();
+	}
 	// dry run (kWrapDry): walk the Huffman stream and count, write nothing — finds where a member ends and how
 	// long its output is (nxgpu_gunzip_concat discovers the members of a concatenated file this way)
 	const bool dry = (J.wrap & kWrapDry) != 0;
@@ -444,8 +459,11 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 				n = J.src_len > stored_at ? J.src_len - stored_at : 0;   // copy what is there, resume later
 			}
 			if (n > J.dst_cap - out) { rc = job ? 13 : NXGPU_E_BUF; break; }
-			for (uint32_t i = lane; i < n && !dry; i += 32)
-				J.dst[out + i] = J.src[stored_at + i];
+			for (uint32_t i = lane; i < n && !dry; i += 32) {
+				const uint8_t v = J.src[stored_at + i];
+				J.dst[out + i] = v;
+				if (kWin) win[(wofs + out + i) & (kWinBytes - 1)] = v;
+			}
 			out += n;
 			if (n < stored_len) {
 				o_sfbt = 0x8 | (final_block ? 1u : 0u);
@@ -658,10 +676,18 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 				uint32_t xa = ta, xb = tb;
 				const bool ca = ba < total && tok_is_match(ta) && tok_dist(ta) >= ia;
 				const bool cb = bb < total && tok_is_match(tb) && tok_dist(tb) >= ib;
-				if (ca) xa = dq[(int32_t)ba - (int32_t)tok_dist(ta)];
-				if (cb) xb = dq[(int32_t)bb - (int32_t)tok_dist(tb)];
-				if (ba < total && (ca || !tok_is_match(ta))) dq[ba] = (uint8_t)xa;
-				if (bb < total && (cb || !tok_is_match(tb))) dq[bb] = (uint8_t)xb;
+				if (kWin) {
+					const uint32_t wa = wofs + out + ba, wb = wofs + out + bb;
+					if (ca) xa = win[(wa - tok_dist(ta)) & (kWinBytes - 1)];
+					if (cb) xb = win[(wb - tok_dist(tb)) & (kWinBytes - 1)];
+					if (ba < total && (ca || !tok_is_match(ta))) { dq[ba] = (uint8_t)xa; win[wa & (kWinBytes - 1)] = (uint8_t)xa; }
+					if (bb < total && (cb || !tok_is_match(tb))) { dq[bb] = (uint8_t)xb; win[wb & (kWinBytes - 1)] = (uint8_t)xb; }
+				} else {
+					if (ca) xa = dq[(int32_t)ba - (int32_t)tok_dist(ta)];
+					if (cb) xb = dq[(int32_t)bb - (int32_t)tok_dist(tb)];
+					if (ba < total && (ca || !tok_is_match(ta))) dq[ba] = (uint8_t)xa;
+					if (bb < total && (cb || !tok_is_match(tb))) dq[bb] = (uint8_t)xb;
+				}
 			}
 			__syncwarp();
 			while (mm) {
@@ -671,7 +697,27 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T)
 				const uint32_t mo = __shfl_sync(0xffffffffu, my_out, src_lane);
 				const uint32_t len = tok_len(mt), dist = tok_dist(mt);
 				uint8_t *d = J.dst + mo;
-				if (dist >= len || dist >= 32) {
+				if (kWin) {
+					volatile uint8_t *vw = win;
+					const uint32_t wp = wofs + mo;
+					if (dist >= len || dist >= 32) {
+						for (uint32_t k = 0; k < len; k += 32) {
+							if (k + lane < len) {
+								const uint8_t v = vw[(wp + k + lane - dist) & (kWinBytes - 1)];
+								d[k + lane] = v;
+								vw[(wp + k + lane) & (kWinBytes - 1)] = v;
+							}
+							if (dist < len)
+								__syncwarp();
+						}
+					} else {
+						for (uint32_t k = lane; k < len; k += 32) {
+							const uint8_t v = vw[(wp - dist + (k % dist)) & (kWinBytes - 1)];
+							d[k] = v;
+							vw[(wp + k) & (kWinBytes - 1)] = v;
+						}
+					}
+				} else if (dist >= len || dist >= 32) {
 					// each 32-byte pass reads bytes that earlier passes (or earlier symbols) wrote
 					for (uint32_t k = 0; k < len; k += 32) {
 						if (k + lane < len)
@@ -797,7 +843,31 @@ inflate_kernel(const InflateJob *__restrict__ jobs, InflateOut *__restrict__ out
 		if (j >= n_jobs)
 			break;
 		const InflateJob J = jobs[j];
-		inflate_one(J, outs[j], T);
+		inflate_one<false>(J, outs[j], T, nullptr);
+		__syncwarp();
+	}
+}
+
+// a few large streams: one warp per CTA with its 32 KiB window in shared memory (see inflate_one<kWin>)
+__global__ void __launch_bounds__(32)
+inflate_solo_kernel(const InflateJob *__restrict__ jobs, InflateOut *__restrict__ outs, uint32_t n_jobs, uint32_t *next_job)
+{
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	WarpTables &T = *reinterpret_cast<WarpTables *>(smem_raw);
+	uint8_t *win = smem_raw + ((sizeof(WarpTables) + 15) & ~(size_t)15);
+	const uint32_t lane = threadIdx.x & 31;
+	for (;;) {
+		uint32_t j = 0;
+		if (lane == 0)
+			j = atomicAdd(next_job, 1u);
+		j = __shfl_sync(0xffffffffu, j, 0);
+		if (j >= n_jobs)
+			break;
+		const InflateJob J = jobs[j];
+		if ((J.wrap & kWrapDry) != 0)
+			inflate_one<false>(J, outs[j], T, nullptr);
+		else
+			inflate_one<true>(J, outs[j], T, win);
 		__syncwarp();
 	}
 }
@@ -852,8 +922,29 @@ static cudaError_t launch_inflate_t(const InflateJob *jobs, InflateOut *outs, ui
 	return cudaGetLastError();
 }
 
+// Up to this many streams per launch run on the solo kernel (5 CTAs of one warp fit an SM with 40 KiB each): beyond that
+// the batch kernel's 28 warps per SM hide the window's L2 latency by themselves.
+static cudaError_t launch_inflate_solo(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s)
+{
+	static PerDeviceOnce once;
+	const size_t smem = ((sizeof(WarpTables) + 15) & ~(size_t)15) + kWinBytes;
+	cudaError_t e = once.run([smem] { return cudaFuncSetAttribute(inflate_solo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+	if (e != cudaSuccess)
+		return e;
+	e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
+	if (e != cudaSuccess)
+		return e;
+	const uint32_t grid = n_jobs < (uint32_t)(kNumSMs * 5) ? n_jobs : (uint32_t)(kNumSMs * 5);
+	inflate_solo_kernel<<<grid ? grid : 1, 32, smem, s>>>(jobs, outs, n_jobs, counter);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_inflate(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s)
 {
+	const char *sm = getenv("NXGPU_INFLATE_SOLO_MAX");          // developer / test switch: 0 = never
+	const uint32_t solo_max = sm ? (uint32_t)atoi(sm) : (uint32_t)(kNumSMs * 5);
+	if (n_jobs <= solo_max)
+		return launch_inflate_solo(jobs, outs, n_jobs, counter, s);
 	static const int occ = getenv("NXGPU_INFLATE_OCC") ? atoi(getenv("NXGPU_INFLATE_OCC")) : 7;   // developer switch
 	if (occ <= 4)
 		return launch_inflate_t<4>(jobs, outs, n_jobs, counter, s);

@@ -80,7 +80,12 @@ def test_cpu_engine_matches_the_manual_derived_vectors(oracle, vectors):
 
 
 @pytest.mark.gpu
-def test_gpu_engine_matches_the_manual_derived_vectors(pg, vectors):
+@pytest.mark.parametrize("kernel", ["solo", "batch"])
+def test_gpu_engine_matches_the_manual_derived_vectors(pg, vectors, kernel, monkeypatch):
+    # a single descriptor runs on the one-warp-per-stream kernel (window in shared memory); NXGPU_INFLATE_SOLO_MAX=0 sends the
+    # same descriptors through the batch kernel (window read from L1/L2)
+    if kernel == "batch":
+        monkeypatch.setenv("NXGPU_INFLATE_SOLO_MAX", "0")
     lib = pg.load_library()
 
     class Dev(C.Structure):

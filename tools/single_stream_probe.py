@@ -28,7 +28,7 @@ for level in (1, 6):
 # one compress descriptor (nxu_run_job, host buffers, wall clock): cut into 64 KiB pieces above 128 KiB
 import ctypes as C
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from test_dropin import Job
+from nxjob import Job
 lib = pg.load_library()
 
 
