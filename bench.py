@@ -648,6 +648,9 @@ def extras_single_gpu(args, pg, eng, lib, torch, src, hsrc, n, extra, hbm_peak, 
                                capture_output=True, text=True, timeout=300, env=env)
             ie = json.loads(p.stdout.strip().splitlines()[-1])
             extra["zstream_init_end"] = {k: round(v, 2) for k, v in ie.items() if k.endswith(("_us", "_ms"))}
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "nx_dropin_driver.py"), gpu_nxz, "initend", "10"],
+                               capture_output=True, text=True, timeout=300, env=dict(env, NXGPU_PREWARM="1"))
+            extra["zstream_init_end"]["first_use_ms_with_NXGPU_PREWARM"] = round(json.loads(p.stdout.strip().splitlines()[-1])["first_use_ms"], 2)
         except Exception as e:                      # noqa: BLE001
             extra["zstream_init_end"] = {"error": repr(e)[:200]}
 

@@ -231,9 +231,14 @@ __device__ void hash_range(Smem &S, uint32_t lo, uint32_t hi)
 		}
 	}
 }
-__device__ void insert_range(Smem &S, uint32_t lo, uint32_t hi)
+// exact = true (levels 5 and up): positions of ONE instruction that share a bucket are chained among themselves
+// (match.any finds them; each links to the nearest lower lane, the highest becomes the head), as a serial insert would.
+// Without it they all link to the older head, which hides the nearest candidates of short-period data (runs of a 1-7
+// byte pattern came out 2.4 x zlib's size) for well under 1 % on text.
+__device__ void insert_range(Smem &S, uint32_t lo, uint32_t hi, bool exact)
 {
 	const uint32_t lane = lane_id();
+	const uint32_t lt = (1u << lane) - 1;
 	constexpr int U = 4;
 	for (uint32_t p0 = lo; p0 < hi; p0 += 32 * U) {
 		uint32_t h[U], old[U];
@@ -246,7 +251,15 @@ __device__ void insert_range(Smem &S, uint32_t lo, uint32_t hi)
 		for (int u = 0; u < U; u++) {
 			const uint32_t pos = p0 + 32 * u + lane;
 			old[u] = 0;
-			if (pos < hi) {
+			if (exact) {
+				const uint32_t grp = __match_any_sync(0xffffffffu, pos < hi ? h[u] : (0x10000u | lane));
+				const uint32_t lower = grp & lt;
+				if (pos < hi) {
+					old[u] = lower ? pos - (lane - (31u - (uint32_t)__clz(lower))) : S.head[h[u]];
+					if ((grp >> lane) == 1u)                 // highest lane of the group
+						S.head[h[u]] = (uint16_t)pos;
+				}
+			} else if (pos < hi) {
 				old[u] = S.head[h[u]];
 				S.head[h[u]] = (uint16_t)pos;
 			}
@@ -263,7 +276,7 @@ __device__ void insert_range(Smem &S, uint32_t lo, uint32_t hi)
 }
 
 // warp 1 of the split producer: block by block behind the hashing warp
-__device__ void inserter(Smem &S, uint32_t P0, uint32_t PE)
+__device__ void inserter(Smem &S, uint32_t P0, uint32_t PE, bool exact)
 {
 	const uint32_t PEa = (PE + 15) & ~15u;
 	const uint32_t hash_hi = PE >= 4 ? PE - 4 : 0;
@@ -278,7 +291,7 @@ __device__ void inserter(Smem &S, uint32_t P0, uint32_t PE)
 		const uint32_t hi = (b + 1 == nblk) ? hash_hi : min(blk_hi - 4, hash_hi);
 		long long t1 = clock64();
 		if (hi > BF) {
-			insert_range(S, BF, hi);
+			insert_range(S, BF, hi, exact);
 			BF = hi;
 		}
 		DBG_ADD(0, clock64() - t1);
@@ -538,7 +551,7 @@ __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, ui
 // produced it without a full compare and the result is the same as walking from scratch)
 __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, uint32_t pos, uint32_t maxl, uint32_t maxdist,
 					   int depth, uint32_t nice, uint32_t &bl, uint32_t &bd, uint32_t seed = 0,
-					   uint32_t *cursor = nullptr, uint32_t resume = 0xffffffffu)
+					   uint32_t *cursor = nullptr, uint32_t resume = 0xffffffffu, uint32_t rep = 0)
 {
 	// cursor: where this walk stopped in the chain (distance walked << 16 | next link), so that a later, deeper
 	// walk of the same position (resume) continues there instead of repeating the first hops
@@ -553,6 +566,22 @@ __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, 
 	uint32_t acc = 0;
 	uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;
 	uint32_t endw = __funnelshift_r(P0, P1, 8);                  // the 4 bytes ending at offset bl = 4
+	// The repeat distance (that of the most recent match): records and tables repeat at a fixed stride in runs of 3-4
+	// bytes that the 5-byte chains cannot see.  One probe; a 3- or 4-byte hit is kept as the fallback when the chain
+	// finds nothing (3 bytes only up to 4096 back, zlib's TOO_FAR rule).
+	uint32_t rl = 0;
+	if (rep && rep <= maxdist && maxl >= 3 && ((load4(ring8, pos - rep) ^ P0) & 0xffffffu) == 0) {
+		rl = match_length(ring8, pos, pos - rep, maxl, P0, P1, P2, P3);
+		if (rl == 3 && rep > 4096)
+			rl = 0;
+		if (rl >= (uint32_t)kMinMatch) {
+			bl = rl; bd = rep;
+			if (bl >= nice || bl >= maxl)
+				d = 0;
+			else
+				endw = load4(ring8, pos + bl - 3);
+		}
+	}
 	if (tok_is_match(seed) && tok_len(seed) <= maxl) {
 		bl = tok_len(seed); bd = tok_dist(seed);
 		if (bl >= nice || bl >= maxl)
@@ -589,6 +618,9 @@ __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, 
 	}
 	if (cursor)
 		*cursor = acc << 16 | d;
+	if (bd == 0 && rl >= 3) {
+		bl = rl; bd = rep;
+	}
 }
 
 // greedy / lazy choice per position of one window, then pointer jumping: every lane ends up with
@@ -623,6 +655,7 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 	uint32_t qpos = 0, qtok = 0, qcur = 0, qn = 0;             // pass-2 queue: one position (its shallow result, its chain cursor) per lane
 	uint32_t headA = 0;                                        // pass-1 parse: next token start (relative to sub_lo)
 	uint32_t carry = 0;                                        // mark for lane 0 of the next window
+	uint32_t rep = 0;                                          // repeat distance probed by the shallow pass (warp-uniform)
 
 	// Chain depth of the deep pass follows the data: the cost of a sub-block is (queued positions) x
 	// depth, and long-match data (few token starts per byte, many equally good candidates) is where
@@ -639,7 +672,7 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 		const uint32_t maxl = act ? min((uint32_t)kMaxMatch, PE - pos) : 0;
 		uint32_t bl, bd;
 		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), max(1, depth - d1), (uint32_t)nice, bl, bd, act ? qtok : 0, nullptr, act ? qcur : 0);   // the first d1 hops were walked by the shallow pass
-		if (act && bl >= (uint32_t)kMinMatch)
+		if (act && bd)
 			__stcg(&pres[pos - sub_lo], tok_match(bl, bd));
 	};
 
@@ -652,8 +685,14 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 		const uint32_t maxl = live ? min((uint32_t)kMaxMatch, PE - pos) : 0;
 		uint32_t bl, bd;
 		uint32_t mycur;
-		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), d1, (uint32_t)nice, bl, bd, 0, &mycur);
-		const uint32_t len = bl >= (uint32_t)kMinMatch ? bl : 0;
+		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), d1, (uint32_t)nice, bl, bd, 0, &mycur, 0xffffffffu, rep);
+		const uint32_t len = bd ? bl : 0;
+		{
+			// repeat distance for the next window: that of the last position of this one that found a match
+			const uint32_t hasm = __ballot_sync(0xffffffffu, live && bd != 0);
+			if (hasm)
+				rep = __shfl_sync(0xffffffffu, bd, 31 - __clz(hasm));
+		}
 		const uint32_t mytok = len ? tok_match(len, bd) : 0;
 		if (live)
 			__stcg(&pres[w0 + lane], len ? mytok : (uint32_t)ring8[pos & kRingMask]);
@@ -1277,7 +1316,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 		if (warp == 0) {
 			producer(S, gbase, P0, PE, split);
 		} else if (warp == 1 && split) {
-			inserter(S, P0, PE);
+			inserter(S, P0, PE, d1 != 0);
 		} else if ((parser_mask >> warp) & 1) {
 			uint32_t nwin = 0;
 			long long busy = 0, waited = 0;

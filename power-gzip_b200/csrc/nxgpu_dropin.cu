@@ -9,6 +9,7 @@
 #include <time.h>
 #include <unistd.h>
 #include <mutex>
+#include <pthread.h>
 #include "common.cuh"
 #include "../../include/nxgpu.h"
 
@@ -140,6 +141,29 @@ int submit(int dev, Request &r)
 	}
 }
 } // namespace
+
+// First use: creating the CUDA context, loading the kernels and pinning the staging buffers costs
+// 0.25-2 s once per process; every later deflateInit/inflateInit pair costs microseconds.  A process that knows it will
+// compress can hide that behind its own start-up: NXGPU_PREWARM=1 opens the device from a background thread while the
+// library is being loaded (nx_function_begin then finds the context ready).
+__attribute__((constructor)) static void nxgpu_prewarm()
+{
+	const char *e = getenv("NXGPU_PREWARM");
+	if (!e || atoi(e) == 0)
+		return;
+	pthread_t th;
+	auto fn = [](void *) -> void * {
+		std::lock_guard<std::mutex> lk(g_mu);
+		nxgpu_ctx *c = ctx_for(0);
+		if (c) {
+			// the buffers a first small job needs
+			c->h_stage.reserve(4u << 20); c->d_in.reserve(4u << 20); c->d_out.reserve(4u << 20);
+		}
+		return nullptr;
+	};
+	if (pthread_create(&th, nullptr, fn, nullptr) == 0)
+		pthread_detach(th);
+}
 
 extern "C" {
 
