@@ -232,7 +232,8 @@ __device__ void hash_range(Smem &S, uint32_t lo, uint32_t hi)
 	}
 }
 // exact = true (levels 5 and up): positions of ONE instruction that share a bucket are chained among themselves
-// (match.any finds them; each links to the nearest lower lane, the highest becomes the head), as a serial insert would.
+// (each links to the nearest lower lane, the highest becomes the head), as a serial insert would.  (match.any would
+// find the groups in one instruction but runs at a fraction of the issue rate: level 6 fell from 23 to 11.5 GB/s.)
 // Without it they all link to the older head, which hides the nearest candidates of short-period data (runs of a 1-7
 // byte pattern came out 2.4 x zlib's size) for well under 1 % on text.
 __device__ void insert_range(Smem &S, uint32_t lo, uint32_t hi, bool exact)
@@ -251,19 +252,30 @@ __device__ void insert_range(Smem &S, uint32_t lo, uint32_t hi, bool exact)
 		for (int u = 0; u < U; u++) {
 			const uint32_t pos = p0 + 32 * u + lane;
 			old[u] = 0;
-			if (exact) {
-				const uint32_t grp = __match_any_sync(0xffffffffu, pos < hi ? h[u] : (0x10000u | lane));
-				const uint32_t lower = grp & lt;
-				if (pos < hi) {
-					old[u] = lower ? pos - (lane - (31u - (uint32_t)__clz(lower))) : S.head[h[u]];
-					if ((grp >> lane) == 1u)                 // highest lane of the group
-						S.head[h[u]] = (uint16_t)pos;
-				}
-			} else if (pos < hi) {
+			if (pos < hi) {
 				old[u] = S.head[h[u]];
 				S.head[h[u]] = (uint16_t)pos;
 			}
 			__syncwarp();
+			if (exact) {
+				// who shares a bucket inside this instruction?  The racy store left ONE of them as head: everybody else
+				// reads back a foreign position.  Rare on text (no extra work beyond this read), the rule in periodic data.
+				const bool act = pos < hi;
+				uint32_t cm = __ballot_sync(0xffffffffu, act && S.head[h[u]] != (uint16_t)pos);
+				while (cm) {
+					const uint32_t hs = __shfl_sync(0xffffffffu, h[u], __ffs(cm) - 1);
+					const uint32_t grp = __ballot_sync(0xffffffffu, act && h[u] == hs);
+					if (act && h[u] == hs) {
+						const uint32_t lower = grp & lt;
+						if (lower)
+							old[u] = pos - (lane - (31u - (uint32_t)__clz(lower)));      // the nearest lower lane of the group
+						if ((grp >> lane) == 1u)
+							S.head[hs] = (uint16_t)pos;                                   // the highest lane is the head
+					}
+					cm &= ~grp;
+				}
+				__syncwarp();
+			}
 		}
 #pragma unroll
 		for (int u = 0; u < U; u++) {
@@ -645,7 +657,7 @@ __device__ __forceinline__ void window_parse(uint32_t lane, uint32_t nlive, uint
 }
 
 __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_hi, uint32_t valid_lo, uint32_t PE,
-					 int d1, int depth, int nice, int lazy, uint32_t *tk, uint32_t *pres,
+					 int d1, int depth, int nice, int lazy, bool use_rep, uint32_t *tk, uint32_t *pres,
 					 uint32_t &nwin, uint32_t &end_pos)
 {
 	const uint32_t lane = lane_id();
@@ -690,7 +702,7 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 		{
 			// repeat distance for the next window: that of the last position of this one that found a match
 			const uint32_t hasm = __ballot_sync(0xffffffffu, live && bd != 0);
-			if (hasm)
+			if (hasm && use_rep)
 				rep = __shfl_sync(0xffffffffu, bd, 31 - __clz(hasm));
 		}
 		const uint32_t mytok = len ? tok_match(len, bd) : 0;
@@ -1316,7 +1328,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 		if (warp == 0) {
 			producer(S, gbase, P0, PE, split);
 		} else if (warp == 1 && split) {
-			inserter(S, P0, PE, d1 != 0);
+			inserter(S, P0, PE, (d1 & 0x100) != 0);
 		} else if ((parser_mask >> warp) & 1) {
 			uint32_t nwin = 0;
 			long long busy = 0, waited = 0;
@@ -1348,7 +1360,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 				const long long t1 = clock64();
 				uint32_t end_pos;
 				const uint32_t cnt = d1
-					? parse_subblock_2pass(S, sub_lo, sub_hi, P0, PE, d1, depth, nice, lazy, tokpos + (size_t)sb * kSub,
+					? parse_subblock_2pass(S, sub_lo, sub_hi, P0, PE, d1 & 0xff, depth, nice, lazy, (d1 & 0x200) != 0, tokpos + (size_t)sb * kSub,
 							       pres + (size_t)warp * (kSub + 32), nwin, end_pos)
 					: parse_subblock(S, sub_lo, sub_hi, P0, PE, depth, nice, lazy, tokpos + (size_t)sb * kSub, nwin, end_pos);
 				if (lane_id() == 0) {
@@ -1729,8 +1741,12 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 	cudaError_t me = cudaMemsetAsync(job_counter, 0, sizeof(uint32_t), s);
 	if (me != cudaSuccess)
 		return me;
+	// levels 5 and up: exact chains (bit 8) and the repeat-distance probe (bit 9) ride in the high bits of d1 (developer switches)
+	static const bool exact = !(getenv("NXGPU_EXACT_CHAINS") && atoi(getenv("NXGPU_EXACT_CHAINS")) == 0);
+	static const bool use_rep = !(getenv("NXGPU_REP_PROBE") && atoi(getenv("NXGPU_REP_PROBE")) == 0);
+	const int d1f = lp.d1 ? (lp.d1 | (exact && split ? 0x100 : 0) | (use_rep ? 0x200 : 0)) : 0;
 	deflate_kernel<<<grid, kThreads, sizeof(Smem), s>>>(jobs, outs, n_jobs, lp.depth, lp.lazy, lp.nice, tok_scratch, tok_stride, parser_mask,
-							    job_counter, ready, jobs_per_flag ? jobs_per_flag : 1, lp.d1, so ? *so : StreamOut());
+							    job_counter, ready, jobs_per_flag ? jobs_per_flag : 1, d1f, so ? *so : StreamOut());
 	cudaError_t e = cudaGetLastError();
 	if (dbg) {
 		std::vector<unsigned long long> h((size_t)grid * 8);
