@@ -465,6 +465,26 @@ __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, ui
 		uint32_t bl = kMinMatch - 1, bd = 0, acc = 0;
 		uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;
 		uint32_t endw = __funnelshift_r(P0, P1, 8);              // the 4 bytes ending at offset bl = 4
+		if (maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
+			// runs of a 1-4 byte pattern: the chains cannot see their nearest candidates (see walk_chain)
+			const uint32_t o = pos & kRingMask, a = o & ~3u, sh = (o & 3) * 8;
+			const uint32_t before = __funnelshift_r(ld32(ring8, (a - 4) & kRingMask), ld32(ring8, a), sh);
+			uint32_t rd = 0;
+			if (before == P0) rd = 4;
+			if (__funnelshift_r(before, P0, 8) == P0) rd = 3;
+			if (__funnelshift_r(before, P0, 16) == P0) rd = 2;
+			if (__funnelshift_r(before, P0, 24) == P0) rd = 1;
+			if (rd) {
+				const uint32_t rl = match_length(ring8, pos, pos - rd, maxl, P0, P1, P2, P3);
+				if (rl >= (uint32_t)kMinMatch) {
+					bl = rl; bd = rd;
+					if (bl >= (uint32_t)nice || bl >= maxl)
+						d = 0;
+					else
+						endw = load4(ring8, pos + bl - 3);
+				}
+			}
+		}
 		uint32_t head = 0;
 		bool finished = false;
 		for (int hop = 1; !finished; hop++) {
@@ -563,7 +583,7 @@ __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, ui
 // produced it without a full compare and the result is the same as walking from scratch)
 __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, uint32_t pos, uint32_t maxl, uint32_t maxdist,
 					   int depth, uint32_t nice, uint32_t &bl, uint32_t &bd, uint32_t seed = 0,
-					   uint32_t *cursor = nullptr, uint32_t resume = 0xffffffffu, uint32_t rep = 0)
+					   uint32_t *cursor = nullptr, uint32_t resume = 0xffffffffu, bool probe_runs = false)
 {
 	// cursor: where this walk stopped in the chain (distance walked << 16 | next link), so that a later, deeper
 	// walk of the same position (resume) continues there instead of repeating the first hops
@@ -578,20 +598,27 @@ __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, 
 	uint32_t acc = 0;
 	uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;
 	uint32_t endw = __funnelshift_r(P0, P1, 8);                  // the 4 bytes ending at offset bl = 4
-	// The repeat distance (that of the most recent match): records and tables repeat at a fixed stride in runs of 3-4
-	// bytes that the 5-byte chains cannot see.  One probe; a 3- or 4-byte hit is kept as the fallback when the chain
-	// finds nothing (3 bytes only up to 4096 back, zlib's TOO_FAR rule).
-	uint32_t rl = 0;
-	if (rep && rep <= maxdist && maxl >= 3 && ((load4(ring8, pos - rep) ^ P0) & 0xffffffu) == 0) {
-		rl = match_length(ring8, pos, pos - rep, maxl, P0, P1, P2, P3);
-		if (rl == 3 && rep > 4096)
-			rl = 0;
-		if (rl >= (uint32_t)kMinMatch) {
-			bl = rl; bd = rep;
-			if (bl >= nice || bl >= maxl)
-				d = 0;
-			else
-				endw = load4(ring8, pos + bl - 3);
+	// Runs (a 1-4 byte pattern repeated): the nearest candidates of such a position sit inside the same 32-position
+	// insert instruction, where the racy chain build links everybody to the OLDER head — so the chains miss them and
+	// short runs came out as literals (2.4 x zlib's size on runs of 20-120 repeats).  The shallow pass (consecutive
+	// positions) looks at distances 1-4 directly: the 4 bytes in front of the position are one more word away.
+	if (probe_runs && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
+		const uint32_t o = pos & kRingMask, a = o & ~3u, sh = (o & 3) * 8;
+		const uint32_t before = __funnelshift_r(ld32(ring8, (a - 4) & kRingMask), ld32(ring8, a), sh);   // bytes [pos-4, pos)
+		uint32_t rd = 0;
+		if (before == P0) rd = 4;
+		if (__funnelshift_r(before, P0, 8) == P0) rd = 3;
+		if (__funnelshift_r(before, P0, 16) == P0) rd = 2;
+		if (__funnelshift_r(before, P0, 24) == P0) rd = 1;
+		if (rd) {
+			const uint32_t rl = match_length(ring8, pos, pos - rd, maxl, P0, P1, P2, P3);
+			if (rl >= (uint32_t)kMinMatch) {
+				bl = rl; bd = rd;
+				if (bl >= nice || bl >= maxl)
+					d = 0;
+				else
+					endw = load4(ring8, pos + bl - 3);
+			}
 		}
 	}
 	if (tok_is_match(seed) && tok_len(seed) <= maxl) {
@@ -630,9 +657,6 @@ __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, 
 	}
 	if (cursor)
 		*cursor = acc << 16 | d;
-	if (bd == 0 && rl >= 3) {
-		bl = rl; bd = rep;
-	}
 }
 
 // greedy / lazy choice per position of one window, then pointer jumping: every lane ends up with
@@ -657,7 +681,7 @@ __device__ __forceinline__ void window_parse(uint32_t lane, uint32_t nlive, uint
 }
 
 __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_hi, uint32_t valid_lo, uint32_t PE,
-					 int d1, int depth, int nice, int lazy, bool use_rep, uint32_t *tk, uint32_t *pres,
+					 int d1, int depth, int nice, int lazy, bool use_rep /* run probe */, uint32_t *tk, uint32_t *pres,
 					 uint32_t &nwin, uint32_t &end_pos)
 {
 	const uint32_t lane = lane_id();
@@ -667,7 +691,6 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 	uint32_t qpos = 0, qtok = 0, qcur = 0, qn = 0;             // pass-2 queue: one position (its shallow result, its chain cursor) per lane
 	uint32_t headA = 0;                                        // pass-1 parse: next token start (relative to sub_lo)
 	uint32_t carry = 0;                                        // mark for lane 0 of the next window
-	uint32_t rep = 0;                                          // repeat distance probed by the shallow pass (warp-uniform)
 
 	// Chain depth of the deep pass follows the data: the cost of a sub-block is (queued positions) x
 	// depth, and long-match data (few token starts per byte, many equally good candidates) is where
@@ -697,14 +720,8 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 		const uint32_t maxl = live ? min((uint32_t)kMaxMatch, PE - pos) : 0;
 		uint32_t bl, bd;
 		uint32_t mycur;
-		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), d1, (uint32_t)nice, bl, bd, 0, &mycur, 0xffffffffu, rep);
+		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), d1, (uint32_t)nice, bl, bd, 0, &mycur, 0xffffffffu, use_rep);
 		const uint32_t len = bd ? bl : 0;
-		{
-			// repeat distance for the next window: that of the last position of this one that found a match
-			const uint32_t hasm = __ballot_sync(0xffffffffu, live && bd != 0);
-			if (hasm && use_rep)
-				rep = __shfl_sync(0xffffffffu, bd, 31 - __clz(hasm));
-		}
 		const uint32_t mytok = len ? tok_match(len, bd) : 0;
 		if (live)
 			__stcg(&pres[w0 + lane], len ? mytok : (uint32_t)ring8[pos & kRingMask]);
@@ -1741,9 +1758,10 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 	cudaError_t me = cudaMemsetAsync(job_counter, 0, sizeof(uint32_t), s);
 	if (me != cudaSuccess)
 		return me;
-	// levels 5 and up: exact chains (bit 8) and the repeat-distance probe (bit 9) ride in the high bits of d1 (developer switches)
-	static const bool exact = !(getenv("NXGPU_EXACT_CHAINS") && atoi(getenv("NXGPU_EXACT_CHAINS")) == 0);
-	static const bool use_rep = !(getenv("NXGPU_REP_PROBE") && atoi(getenv("NXGPU_REP_PROBE")) == 0);
+	// levels 5 and up: exact chains (bit 8; off: -28 % speed for +0.1 % ratio on the workload) and the run probe (bit 9) ride in the
+	// high bits of d1 (developer switches)
+	static const bool exact = getenv("NXGPU_EXACT_CHAINS") && atoi(getenv("NXGPU_EXACT_CHAINS")) != 0;
+	static const bool use_rep = !(getenv("NXGPU_RUN_PROBE") && atoi(getenv("NXGPU_RUN_PROBE")) == 0);
 	const int d1f = lp.d1 ? (lp.d1 | (exact && split ? 0x100 : 0) | (use_rep ? 0x200 : 0)) : 0;
 	deflate_kernel<<<grid, kThreads, sizeof(Smem), s>>>(jobs, outs, n_jobs, lp.depth, lp.lazy, lp.nice, tok_scratch, tok_stride, parser_mask,
 							    job_counter, ready, jobs_per_flag ? jobs_per_flag : 1, d1f, so ? *so : StreamOut());
