@@ -466,10 +466,18 @@ __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, ui
 		uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;
 		uint32_t endw = __funnelshift_r(P0, P1, 8);              // the 4 bytes ending at offset bl = 4
 		if (maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
-			// runs of a 1-4 byte pattern: the chains cannot see their nearest candidates (see walk_chain)
+			// runs of a 1-8 byte pattern: the chains cannot see their nearest candidates (see walk_chain)
 			const uint32_t o = pos & kRingMask, a = o & ~3u, sh = (o & 3) * 8;
-			const uint32_t before = __funnelshift_r(ld32(ring8, (a - 4) & kRingMask), ld32(ring8, a), sh);
+			const uint32_t wm1 = ld32(ring8, (a - 4) & kRingMask);
+			const uint32_t before = __funnelshift_r(wm1, ld32(ring8, a), sh);
+			const uint32_t before8 = __funnelshift_r(ld32(ring8, (a - 8) & kRingMask), wm1, sh);
 			uint32_t rd = 0;
+			if (maxdist >= 8) {
+				if (before8 == P0) rd = 8;
+				if (__funnelshift_r(before8, before, 8) == P0) rd = 7;
+				if (__funnelshift_r(before8, before, 16) == P0) rd = 6;
+				if (__funnelshift_r(before8, before, 24) == P0) rd = 5;
+			}
 			if (before == P0) rd = 4;
 			if (__funnelshift_r(before, P0, 8) == P0) rd = 3;
 			if (__funnelshift_r(before, P0, 16) == P0) rd = 2;
@@ -598,14 +606,22 @@ __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, 
 	uint32_t acc = 0;
 	uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;
 	uint32_t endw = __funnelshift_r(P0, P1, 8);                  // the 4 bytes ending at offset bl = 4
-	// Runs (a 1-4 byte pattern repeated): the nearest candidates of such a position sit inside the same 32-position
+	// Runs (a 1-8 byte pattern repeated): the nearest candidates of such a position sit inside the same 32-position
 	// insert instruction, where the racy chain build links everybody to the OLDER head — so the chains miss them and
 	// short runs came out as literals (2.4 x zlib's size on runs of 20-120 repeats).  The shallow pass (consecutive
-	// positions) looks at distances 1-4 directly: the 4 bytes in front of the position are one more word away.
+	// positions) looks at distances 1-8 directly: the 8 bytes in front of the position are two more words away.
 	if (probe_runs && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
 		const uint32_t o = pos & kRingMask, a = o & ~3u, sh = (o & 3) * 8;
-		const uint32_t before = __funnelshift_r(ld32(ring8, (a - 4) & kRingMask), ld32(ring8, a), sh);   // bytes [pos-4, pos)
+		const uint32_t wm1 = ld32(ring8, (a - 4) & kRingMask);
+		const uint32_t before = __funnelshift_r(wm1, ld32(ring8, a), sh);                                  // bytes [pos-4, pos)
+		const uint32_t before8 = __funnelshift_r(ld32(ring8, (a - 8) & kRingMask), wm1, sh);              // bytes [pos-8, pos-4)
 		uint32_t rd = 0;
+		if (maxdist >= 8) {
+			if (before8 == P0) rd = 8;
+			if (__funnelshift_r(before8, before, 8) == P0) rd = 7;
+			if (__funnelshift_r(before8, before, 16) == P0) rd = 6;
+			if (__funnelshift_r(before8, before, 24) == P0) rd = 5;
+		}
 		if (before == P0) rd = 4;
 		if (__funnelshift_r(before, P0, 8) == P0) rd = 3;
 		if (__funnelshift_r(before, P0, 16) == P0) rd = 2;
