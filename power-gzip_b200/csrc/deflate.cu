@@ -53,6 +53,7 @@ struct __align__(16) Smem {
 	uint64_t hash_bar[kDoneSlots];    // split producer: warp 0 arrives once block b's hashes sit in prev[]; warp 1 turns them into links
 	volatile uint32_t parse_pos[32];  // per parser warp: first position of the sub-block in flight
 	uint32_t next_sub;                // next sub-block to hand out
+	uint32_t runflag[4];              // bit b: staging block b holds short-distance chain links (runs): the parsers probe distances 1-8 there
 	uint32_t ll_freq[288];
 	uint32_t d_freq[32];
 	uint32_t n_tok;
@@ -206,6 +207,8 @@ __device__ void build_chains(Smem &S, uint32_t lo, uint32_t hi)
 			const uint32_t d = (pos - old[u]) & 0xFFFFu;
 			if (pos < hi)
 				S.prev[pos & kRingMask] = (uint16_t)(d <= (uint32_t)kWindow ? d : 0);
+			if (__any_sync(0xffffffffu, pos < hi && d - 1 < 40) && lane == 0)       // see insert_range
+				S.runflag[((pos / kBlk) >> 5) & 3] |= 1u << ((pos / kBlk) & 31);
 		}
 	}
 }
@@ -277,12 +280,22 @@ __device__ void insert_range(Smem &S, uint32_t lo, uint32_t hi, bool exact)
 				__syncwarp();
 			}
 		}
+		bool near = false;
 #pragma unroll
 		for (int u = 0; u < U; u++) {
 			const uint32_t pos = p0 + 32 * u + lane;
 			const uint32_t d = (pos - old[u]) & 0xFFFFu;
-			if (pos < hi)
+			if (pos < hi) {
 				S.prev[pos & kRingMask] = (uint16_t)(d <= (uint32_t)kWindow ? d : 0);
+				near |= d - 1 < 40;
+			}
+		}
+		// a link of a few bytes means a short-period run; the racy build above hides such a run's nearest candidates,
+		// so its staging block is flagged and the parsers look at distances 1-8 directly there
+		if (__any_sync(0xffffffffu, near) && lane == 0) {
+			const uint32_t b0 = p0 / kBlk, b1 = min(hi - 1, p0 + 32 * U - 1) / kBlk;
+			S.runflag[(b0 >> 5) & 3] |= 1u << (b0 & 31);
+			S.runflag[(b1 >> 5) & 3] |= 1u << (b1 & 31);
 		}
 	}
 }
@@ -434,7 +447,7 @@ __device__ __forceinline__ uint32_t match_length(const uint8_t *ring8, uint32_t 
 // the last match may run past its end (end_pos), and the stitch pass trims it to a token boundary
 // of the next sub-block.
 __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, uint32_t valid_lo, uint32_t PE,
-				   int depth, int nice, int lazy, uint32_t *tk, uint32_t &nwin, uint32_t &end_pos)
+				   int depth, int nice, int lazy, bool probe_runs, uint32_t *tk, uint32_t &nwin, uint32_t &end_pos)
 {
 	const uint32_t lane = lane_id();
 	const uint32_t lt = (1u << lane) - 1;
@@ -465,7 +478,7 @@ __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, ui
 		uint32_t bl = kMinMatch - 1, bd = 0, acc = 0;
 		uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;
 		uint32_t endw = __funnelshift_r(P0, P1, 8);              // the 4 bytes ending at offset bl = 4
-		if (maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
+		if (probe_runs && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
 			// runs of a 1-8 byte pattern: the chains cannot see their nearest candidates (see walk_chain)
 			const uint32_t o = pos & kRingMask, a = o & ~3u, sh = (o & 3) * 8;
 			const uint32_t wm1 = ld32(ring8, (a - 4) & kRingMask);
@@ -1344,6 +1357,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 		if (threadIdx.x == 0) {
 			S.n_tok = 0;
 			S.next_sub = 0;
+			S.runflag[0] = S.runflag[1] = S.runflag[2] = S.runflag[3] = 0;
 			for (int i = 0; i < kSlots; i++)
 				mbar_init(&S.mbar[i], 1);
 			for (int i = 0; i < kDoneSlots; i++) {
@@ -1358,6 +1372,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 
 		// ---- LZ77: warp 0 stages + builds chains, the parser warps take sub-blocks in order ----
 		const bool split = (parser_mask & 1) != 0;        // bit 0 (warp 0 is never a parser): chain build split over warps 0 and 1
+		const bool run_probe = (d1 & 0x200) != 0;
 		if (warp == 0) {
 			producer(S, gbase, P0, PE, split);
 		} else if (warp == 1 && split) {
@@ -1392,10 +1407,17 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 				__threadfence_block();
 				const long long t1 = clock64();
 				uint32_t end_pos;
-				const uint32_t cnt = d1
-					? parse_subblock_2pass(S, sub_lo, sub_hi, P0, PE, d1 & 0xff, depth, nice, lazy, (d1 & 0x200) != 0, tokpos + (size_t)sb * kSub,
+				// runs in (or just in front of) this sub-block?  (flags of the staging blocks it touches; a chunk has at most 72)
+				bool probe = false;
+				if (run_probe) {
+					const uint32_t fb0 = (sub_lo >= 64 ? sub_lo - 64 : 0) / kBlk, fb1 = (sub_hi - 1) / kBlk;
+					const volatile uint32_t *rf = S.runflag;
+					probe = ((rf[(fb0 >> 5) & 3] >> (fb0 & 31)) & 1) | ((rf[(fb1 >> 5) & 3] >> (fb1 & 31)) & 1);
+				}
+				const uint32_t cnt = d1 & 0xff
+					? parse_subblock_2pass(S, sub_lo, sub_hi, P0, PE, d1 & 0xff, depth, nice, lazy, probe, tokpos + (size_t)sb * kSub,
 							       pres + (size_t)warp * (kSub + 32), nwin, end_pos)
-					: parse_subblock(S, sub_lo, sub_hi, P0, PE, depth, nice, lazy, tokpos + (size_t)sb * kSub, nwin, end_pos);
+					: parse_subblock(S, sub_lo, sub_hi, P0, PE, depth, nice, lazy, probe, tokpos + (size_t)sb * kSub, nwin, end_pos);
 				if (lane_id() == 0) {
 					meta[sb * kMeta + M_CNT] = cnt;
 					meta[sb * kMeta + M_END] = end_pos;
@@ -1774,11 +1796,11 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 	cudaError_t me = cudaMemsetAsync(job_counter, 0, sizeof(uint32_t), s);
 	if (me != cudaSuccess)
 		return me;
-	// levels 5 and up: exact chains (bit 8; off: -28 % speed for +0.1 % ratio on the workload) and the run probe (bit 9) ride in the
-	// high bits of d1 (developer switches)
+	// exact chains (bit 8, levels 5+; off by default: -28 % speed for +0.1 % ratio on the workload) and the run probe (bit 9) ride in
+	// the high bits of d1 (developer switches)
 	static const bool exact = getenv("NXGPU_EXACT_CHAINS") && atoi(getenv("NXGPU_EXACT_CHAINS")) != 0;
 	static const bool use_rep = !(getenv("NXGPU_RUN_PROBE") && atoi(getenv("NXGPU_RUN_PROBE")) == 0);
-	const int d1f = lp.d1 ? (lp.d1 | (exact && split ? 0x100 : 0) | (use_rep ? 0x200 : 0)) : 0;
+	const int d1f = lp.d1 | (lp.d1 && exact && split ? 0x100 : 0) | (use_rep ? 0x200 : 0);
 	deflate_kernel<<<grid, kThreads, sizeof(Smem), s>>>(jobs, outs, n_jobs, lp.depth, lp.lazy, lp.nice, tok_scratch, tok_stride, parser_mask,
 							    job_counter, ready, jobs_per_flag ? jobs_per_flag : 1, d1f, so ? *so : StreamOut());
 	cudaError_t e = cudaGetLastError();
