@@ -53,7 +53,6 @@ struct __align__(16) Smem {
 	uint64_t hash_bar[kDoneSlots];    // split producer: warp 0 arrives once block b's hashes sit in prev[]; warp 1 turns them into links
 	volatile uint32_t parse_pos[32];  // per parser warp: first position of the sub-block in flight
 	uint32_t next_sub;                // next sub-block to hand out
-	uint32_t runflag[4];              // bit b: staging block b holds short-distance chain links (runs): the parsers probe distances 1-8 there
 	uint32_t ll_freq[288];
 	uint32_t d_freq[32];
 	uint32_t n_tok;
@@ -207,8 +206,6 @@ __device__ void build_chains(Smem &S, uint32_t lo, uint32_t hi)
 			const uint32_t d = (pos - old[u]) & 0xFFFFu;
 			if (pos < hi)
 				S.prev[pos & kRingMask] = (uint16_t)(d <= (uint32_t)kWindow ? d : 0);
-			if (__any_sync(0xffffffffu, pos < hi && d - 1 < 40) && lane == 0)       // see insert_range
-				S.runflag[((pos / kBlk) >> 5) & 3] |= 1u << ((pos / kBlk) & 31);
 		}
 	}
 }
@@ -280,22 +277,12 @@ __device__ void insert_range(Smem &S, uint32_t lo, uint32_t hi, bool exact)
 				__syncwarp();
 			}
 		}
-		bool near = false;
 #pragma unroll
 		for (int u = 0; u < U; u++) {
 			const uint32_t pos = p0 + 32 * u + lane;
 			const uint32_t d = (pos - old[u]) & 0xFFFFu;
-			if (pos < hi) {
+			if (pos < hi)
 				S.prev[pos & kRingMask] = (uint16_t)(d <= (uint32_t)kWindow ? d : 0);
-				near |= d - 1 < 40;
-			}
-		}
-		// a link of a few bytes means a short-period run; the racy build above hides such a run's nearest candidates,
-		// so its staging block is flagged and the parsers look at distances 1-8 directly there
-		if (__any_sync(0xffffffffu, near) && lane == 0) {
-			const uint32_t b0 = p0 / kBlk, b1 = min(hi - 1, p0 + 32 * U - 1) / kBlk;
-			S.runflag[(b0 >> 5) & 3] |= 1u << (b0 & 31);
-			S.runflag[(b1 >> 5) & 3] |= 1u << (b1 & 31);
 		}
 	}
 }
@@ -478,7 +465,7 @@ __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, ui
 		uint32_t bl = kMinMatch - 1, bd = 0, acc = 0;
 		uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;
 		uint32_t endw = __funnelshift_r(P0, P1, 8);              // the 4 bytes ending at offset bl = 4
-		if (probe_runs && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
+		if (probe_runs && __any_sync(0xffffffffu, d - 1 < 64) && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
 			// runs of a 1-8 byte pattern: the chains cannot see their nearest candidates (see walk_chain)
 			const uint32_t o = pos & kRingMask, a = o & ~3u, sh = (o & 3) * 8;
 			const uint32_t wm1 = ld32(ring8, (a - 4) & kRingMask);
@@ -622,8 +609,10 @@ __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, 
 	// Runs (a 1-8 byte pattern repeated): the nearest candidates of such a position sit inside the same 32-position
 	// insert instruction, where the racy chain build links everybody to the OLDER head — so the chains miss them and
 	// short runs came out as literals (2.4 x zlib's size on runs of 20-120 repeats).  The shallow pass (consecutive
-	// positions) looks at distances 1-8 directly: the 8 bytes in front of the position are two more words away.
-	if (probe_runs && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
+	// positions) looks at distances 1-8 directly: the 8 bytes in front of the position are two more words away.  Only
+	// windows in which some position's first link is short (what a run looks like in the racy chains: a small multiple
+	// of the period) pay for the probe — one vote elsewhere.
+	if (probe_runs && __any_sync(0xffffffffu, d - 1 < 64) && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
 		const uint32_t o = pos & kRingMask, a = o & ~3u, sh = (o & 3) * 8;
 		const uint32_t wm1 = ld32(ring8, (a - 4) & kRingMask);
 		const uint32_t before = __funnelshift_r(wm1, ld32(ring8, a), sh);                                  // bytes [pos-4, pos)
@@ -1357,7 +1346,6 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 		if (threadIdx.x == 0) {
 			S.n_tok = 0;
 			S.next_sub = 0;
-			S.runflag[0] = S.runflag[1] = S.runflag[2] = S.runflag[3] = 0;
 			for (int i = 0; i < kSlots; i++)
 				mbar_init(&S.mbar[i], 1);
 			for (int i = 0; i < kDoneSlots; i++) {
@@ -1407,13 +1395,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 				__threadfence_block();
 				const long long t1 = clock64();
 				uint32_t end_pos;
-				// runs in (or just in front of) this sub-block?  (flags of the staging blocks it touches; a chunk has at most 72)
-				bool probe = false;
-				if (run_probe) {
-					const uint32_t fb0 = (sub_lo >= 64 ? sub_lo - 64 : 0) / kBlk, fb1 = (sub_hi - 1) / kBlk;
-					const volatile uint32_t *rf = S.runflag;
-					probe = ((rf[(fb0 >> 5) & 3] >> (fb0 & 31)) & 1) | ((rf[(fb1 >> 5) & 3] >> (fb1 & 31)) & 1);
-				}
+				const bool probe = run_probe;
 				const uint32_t cnt = d1 & 0xff
 					? parse_subblock_2pass(S, sub_lo, sub_hi, P0, PE, d1 & 0xff, depth, nice, lazy, probe, tokpos + (size_t)sb * kSub,
 							       pres + (size_t)warp * (kSub + 32), nwin, end_pos)
