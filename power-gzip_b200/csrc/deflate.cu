@@ -231,15 +231,9 @@ __device__ void hash_range(Smem &S, uint32_t lo, uint32_t hi)
 		}
 	}
 }
-// exact = true (levels 5 and up): positions of ONE instruction that share a bucket are chained among themselves
-// (each links to the nearest lower lane, the highest becomes the head), as a serial insert would.  (match.any would
-// find the groups in one instruction but runs at a fraction of the issue rate: level 6 fell from 23 to 11.5 GB/s.)
-// Without it they all link to the older head, which hides the nearest candidates of short-period data (runs of a 1-7
-// byte pattern came out 2.4 x zlib's size) for well under 1 % on text.
-__device__ void insert_range(Smem &S, uint32_t lo, uint32_t hi, bool exact)
+__device__ void insert_range(Smem &S, uint32_t lo, uint32_t hi)
 {
 	const uint32_t lane = lane_id();
-	const uint32_t lt = (1u << lane) - 1;
 	constexpr int U = 4;
 	for (uint32_t p0 = lo; p0 < hi; p0 += 32 * U) {
 		uint32_t h[U], old[U];
@@ -257,25 +251,6 @@ __device__ void insert_range(Smem &S, uint32_t lo, uint32_t hi, bool exact)
 				S.head[h[u]] = (uint16_t)pos;
 			}
 			__syncwarp();
-			if (exact) {
-				// who shares a bucket inside this instruction?  The racy store left ONE of them as head: everybody else
-				// reads back a foreign position.  Rare on text (no extra work beyond this read), the rule in periodic data.
-				const bool act = pos < hi;
-				uint32_t cm = __ballot_sync(0xffffffffu, act && S.head[h[u]] != (uint16_t)pos);
-				while (cm) {
-					const uint32_t hs = __shfl_sync(0xffffffffu, h[u], __ffs(cm) - 1);
-					const uint32_t grp = __ballot_sync(0xffffffffu, act && h[u] == hs);
-					if (act && h[u] == hs) {
-						const uint32_t lower = grp & lt;
-						if (lower)
-							old[u] = pos - (lane - (31u - (uint32_t)__clz(lower)));      // the nearest lower lane of the group
-						if ((grp >> lane) == 1u)
-							S.head[hs] = (uint16_t)pos;                                   // the highest lane is the head
-					}
-					cm &= ~grp;
-				}
-				__syncwarp();
-			}
 		}
 #pragma unroll
 		for (int u = 0; u < U; u++) {
@@ -288,7 +263,7 @@ __device__ void insert_range(Smem &S, uint32_t lo, uint32_t hi, bool exact)
 }
 
 // warp 1 of the split producer: block by block behind the hashing warp
-__device__ void inserter(Smem &S, uint32_t P0, uint32_t PE, bool exact)
+__device__ void inserter(Smem &S, uint32_t P0, uint32_t PE)
 {
 	const uint32_t PEa = (PE + 15) & ~15u;
 	const uint32_t hash_hi = PE >= 4 ? PE - 4 : 0;
@@ -303,7 +278,7 @@ __device__ void inserter(Smem &S, uint32_t P0, uint32_t PE, bool exact)
 		const uint32_t hi = (b + 1 == nblk) ? hash_hi : min(blk_hi - 4, hash_hi);
 		long long t1 = clock64();
 		if (hi > BF) {
-			insert_range(S, BF, hi, exact);
+			insert_range(S, BF, hi);
 			BF = hi;
 		}
 		DBG_ADD(0, clock64() - t1);
@@ -465,7 +440,7 @@ __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, ui
 		uint32_t bl = kMinMatch - 1, bd = 0, acc = 0;
 		uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;
 		uint32_t endw = __funnelshift_r(P0, P1, 8);              // the 4 bytes ending at offset bl = 4
-		if (probe_runs && __any_sync(0xffffffffu, d - 1 < 64) && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
+		if (probe_runs && __popc(__ballot_sync(0xffffffffu, d - 1 < 64)) >= 6 && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
 			// runs of a 1-8 byte pattern: the chains cannot see their nearest candidates (see walk_chain)
 			const uint32_t o = pos & kRingMask, a = o & ~3u, sh = (o & 3) * 8;
 			const uint32_t wm1 = ld32(ring8, (a - 4) & kRingMask);
@@ -610,9 +585,11 @@ __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, 
 	// insert instruction, where the racy chain build links everybody to the OLDER head — so the chains miss them and
 	// short runs came out as literals (2.4 x zlib's size on runs of 20-120 repeats).  The shallow pass (consecutive
 	// positions) looks at distances 1-8 directly: the 8 bytes in front of the position are two more words away.  Only
-	// windows in which some position's first link is short (what a run looks like in the racy chains: a small multiple
-	// of the period) pay for the probe — one vote elsewhere.
-	if (probe_runs && __any_sync(0xffffffffu, d - 1 < 64) && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
+	// windows in which six or more positions have a short first link (what a run looks like in the racy chains: a small
+	// multiple of the period; ordinary text shows one or two) pay for the probe — one vote elsewhere.  Tried instead and
+	// measured: exact chaining inside the insert instruction with match.any (level 6: 23 -> 11.5 GB/s) or with a read-back
+	// of the racy store (-28 %), a repeat-distance probe with 3/4-byte matches (-6 % for +0.3 % ratio).
+	if (probe_runs && __popc(__ballot_sync(0xffffffffu, d - 1 < 64)) >= 6 && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
 		const uint32_t o = pos & kRingMask, a = o & ~3u, sh = (o & 3) * 8;
 		const uint32_t wm1 = ld32(ring8, (a - 4) & kRingMask);
 		const uint32_t before = __funnelshift_r(wm1, ld32(ring8, a), sh);                                  // bytes [pos-4, pos)
@@ -1364,7 +1341,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 		if (warp == 0) {
 			producer(S, gbase, P0, PE, split);
 		} else if (warp == 1 && split) {
-			inserter(S, P0, PE, (d1 & 0x100) != 0);
+			inserter(S, P0, PE);
 		} else if ((parser_mask >> warp) & 1) {
 			uint32_t nwin = 0;
 			long long busy = 0, waited = 0;
@@ -1778,11 +1755,9 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 	cudaError_t me = cudaMemsetAsync(job_counter, 0, sizeof(uint32_t), s);
 	if (me != cudaSuccess)
 		return me;
-	// exact chains (bit 8, levels 5+; off by default: -28 % speed for +0.1 % ratio on the workload) and the run probe (bit 9) ride in
-	// the high bits of d1 (developer switches)
-	static const bool exact = getenv("NXGPU_EXACT_CHAINS") && atoi(getenv("NXGPU_EXACT_CHAINS")) != 0;
+	// the run probe (bit 9) rides in the high bits of d1 (NXGPU_RUN_PROBE=0: developer switch)
 	static const bool use_rep = !(getenv("NXGPU_RUN_PROBE") && atoi(getenv("NXGPU_RUN_PROBE")) == 0);
-	const int d1f = lp.d1 | (lp.d1 && exact && split ? 0x100 : 0) | (use_rep ? 0x200 : 0);
+	const int d1f = lp.d1 | (use_rep ? 0x200 : 0);
 	deflate_kernel<<<grid, kThreads, sizeof(Smem), s>>>(jobs, outs, n_jobs, lp.depth, lp.lazy, lp.nice, tok_scratch, tok_stride, parser_mask,
 							    job_counter, ready, jobs_per_flag ? jobs_per_flag : 1, d1f, so ? *so : StreamOut());
 	cudaError_t e = cudaGetLastError();

@@ -724,3 +724,26 @@ def test_gzread_of_a_multi_member_file(engine, pg, alice, tmp_path):
     assert f and lib.nxgpu_gzread(f, buf, 100) == -1
     assert lib.nxgpu_gzclose(f) != 0
     assert not lib.nxgpu_gzopen(engine.ctx, str(path).encode(), b"w")      # only the read side is bound
+
+
+# inputs on which the 5-byte minimum match of the LZ77 stage is known to cost more than the 5 % gate allows, with the bound
+# that is asserted instead (DESIGN.md §4.1 "Ratio"): zlib takes the 3- and 4-byte matches that fixed-stride records and a
+# four-letter alphabet are made of
+_RATIO_KNOWN_GAPS = {("binary-records", 6): 1.30, ("binary-records", 1): 1.25, ("four-symbols", 6): 1.08, ("short-periods", 6): 1.06}
+
+
+@pytest.mark.gpu
+def test_deflate_ratio_gate_wide(engine, pg):
+    """Level 6 within 5 % of zlib -6 and level 1 within 5 % of zlib -1 (output size) on every ratio input: the makedata and
+    alice29 fixtures plus data where short matches matter — source code, the 33-symbol alphabet text of the reference's tests,
+    a small vocabulary, short-period runs, binary records, a four-symbol alphabet.  The known gaps carry their own bound."""
+    from ratio_inputs import ratio_inputs
+    rows = []
+    for name, data in ratio_inputs(pg):
+        for lvl in (1, 6):
+            blob = engine.compress(data, level=lvl, wrap=pg.WRAP_ZLIB)
+            assert zlib.decompress(blob) == data
+            rel = len(blob) / len(zlib.compress(data, lvl))
+            rows.append((name, lvl, round(rel, 3)))
+            bound = _RATIO_KNOWN_GAPS.get((name, lvl), 1.05)
+            assert rel <= bound, (name, lvl, rel, bound, rows)
