@@ -440,7 +440,7 @@ __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, ui
 		uint32_t bl = kMinMatch - 1, bd = 0, acc = 0;
 		uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;
 		uint32_t endw = __funnelshift_r(P0, P1, 8);              // the 4 bytes ending at offset bl = 4
-		if (probe_runs && __popc(__ballot_sync(0xffffffffu, d - 1 < 64)) >= 6 && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
+		if (probe_runs && __any_sync(0xffffffffu, d - 1 < 16) && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
 			// runs of a 1-8 byte pattern: the chains cannot see their nearest candidates (see walk_chain)
 			const uint32_t o = pos & kRingMask, a = o & ~3u, sh = (o & 3) * 8;
 			const uint32_t wm1 = ld32(ring8, (a - 4) & kRingMask);
@@ -585,11 +585,12 @@ __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, 
 	// insert instruction, where the racy chain build links everybody to the OLDER head — so the chains miss them and
 	// short runs came out as literals (2.4 x zlib's size on runs of 20-120 repeats).  The shallow pass (consecutive
 	// positions) looks at distances 1-8 directly: the 8 bytes in front of the position are two more words away.  Only
-	// windows in which six or more positions have a short first link (what a run looks like in the racy chains: a small
-	// multiple of the period; ordinary text shows one or two) pay for the probe — one vote elsewhere.  Tried instead and
+	// windows in which some position's first link is below 16 (what a run looks like in the racy chains — a small multiple
+	// of the period, counted from the previous insert instruction — and rare in ordinary text) pay for the probe: one vote
+	// elsewhere.  (A vote that wants six short links misses the window in which a run STARTS, and with it most of the gain.)  Tried instead and
 	// measured: exact chaining inside the insert instruction with match.any (level 6: 23 -> 11.5 GB/s) or with a read-back
 	// of the racy store (-28 %), a repeat-distance probe with 3/4-byte matches (-6 % for +0.3 % ratio).
-	if (probe_runs && __popc(__ballot_sync(0xffffffffu, d - 1 < 64)) >= 6 && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
+	if (probe_runs && __any_sync(0xffffffffu, d - 1 < 16) && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
 		const uint32_t o = pos & kRingMask, a = o & ~3u, sh = (o & 3) * 8;
 		const uint32_t wm1 = ld32(ring8, (a - 4) & kRingMask);
 		const uint32_t before = __funnelshift_r(wm1, ld32(ring8, a), sh);                                  // bytes [pos-4, pos)
