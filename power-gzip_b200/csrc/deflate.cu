@@ -409,7 +409,7 @@ __device__ __forceinline__ uint32_t match_length(const uint8_t *ring8, uint32_t 
 // the last match may run past its end (end_pos), and the stitch pass trims it to a token boundary
 // of the next sub-block.
 __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, uint32_t valid_lo, uint32_t PE,
-				   int depth, int nice, int lazy, bool probe_runs, uint32_t *tk, uint32_t &nwin, uint32_t &end_pos)
+				   int depth, int nice, int lazy, uint32_t *tk, uint32_t &nwin, uint32_t &end_pos)
 {
 	const uint32_t lane = lane_id();
 	const uint32_t lt = (1u << lane) - 1;
@@ -440,34 +440,6 @@ __device__ uint32_t parse_subblock(Smem &S, uint32_t sub_lo, uint32_t sub_hi, ui
 		uint32_t bl = kMinMatch - 1, bd = 0, acc = 0;
 		uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;
 		uint32_t endw = __funnelshift_r(P0, P1, 8);              // the 4 bytes ending at offset bl = 4
-		if (probe_runs && __any_sync(0xffffffffu, d - 1 < 16) && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
-			// runs of a 1-8 byte pattern: the chains cannot see their nearest candidates (see walk_chain)
-			const uint32_t o = pos & kRingMask, a = o & ~3u, sh = (o & 3) * 8;
-			const uint32_t wm1 = ld32(ring8, (a - 4) & kRingMask);
-			const uint32_t before = __funnelshift_r(wm1, ld32(ring8, a), sh);
-			const uint32_t before8 = __funnelshift_r(ld32(ring8, (a - 8) & kRingMask), wm1, sh);
-			uint32_t rd = 0;
-			if (maxdist >= 8) {
-				if (before8 == P0) rd = 8;
-				if (__funnelshift_r(before8, before, 8) == P0) rd = 7;
-				if (__funnelshift_r(before8, before, 16) == P0) rd = 6;
-				if (__funnelshift_r(before8, before, 24) == P0) rd = 5;
-			}
-			if (before == P0) rd = 4;
-			if (__funnelshift_r(before, P0, 8) == P0) rd = 3;
-			if (__funnelshift_r(before, P0, 16) == P0) rd = 2;
-			if (__funnelshift_r(before, P0, 24) == P0) rd = 1;
-			if (rd) {
-				const uint32_t rl = match_length(ring8, pos, pos - rd, maxl, P0, P1, P2, P3);
-				if (rl >= (uint32_t)kMinMatch) {
-					bl = rl; bd = rd;
-					if (bl >= (uint32_t)nice || bl >= maxl)
-						d = 0;
-					else
-						endw = load4(ring8, pos + bl - 3);
-				}
-			}
-		}
 		uint32_t head = 0;
 		bool finished = false;
 		for (int hop = 1; !finished; hop++) {
@@ -581,16 +553,27 @@ __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, 
 	uint32_t acc = 0;
 	uint32_t d = (maxl >= (uint32_t)kMinMatch) ? S.prev[pos & kRingMask] : 0;
 	uint32_t endw = __funnelshift_r(P0, P1, 8);                  // the 4 bytes ending at offset bl = 4
+	if (tok_is_match(seed) && tok_len(seed) <= maxl) {
+		bl = tok_len(seed); bd = tok_dist(seed);
+		if (bl >= nice || bl >= maxl)
+			d = 0;
+		else
+			endw = load4(ring8, pos + bl - 3);
+	}
+	if (resume != 0xffffffffu && d) {
+		acc = resume >> 16;
+		d = resume & 0xffffu;
+	}
 	// Runs (a 1-8 byte pattern repeated): the nearest candidates of such a position sit inside the same 32-position
-	// insert instruction, where the racy chain build links everybody to the OLDER head — so the chains miss them and
-	// short runs came out as literals (2.4 x zlib's size on runs of 20-120 repeats).  The shallow pass (consecutive
-	// positions) looks at distances 1-8 directly: the 8 bytes in front of the position are two more words away.  Only
-	// windows in which some position's first link is below 16 (what a run looks like in the racy chains — a small multiple
-	// of the period, counted from the previous insert instruction — and rare in ordinary text) pay for the probe: one vote
-	// elsewhere.  (A vote that wants six short links misses the window in which a run STARTS, and with it most of the gain.)  Tried instead and
-	// measured: exact chaining inside the insert instruction with match.any (level 6: 23 -> 11.5 GB/s) or with a read-back
-	// of the racy store (-28 %), a repeat-distance probe with 3/4-byte matches (-6 % for +0.3 % ratio).
-	if (probe_runs && __any_sync(0xffffffffu, d - 1 < 16) && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
+	// insert instruction, where the racy chain build links everybody to the OLDER head — so the chains miss the first
+	// 32-64 bytes of every run and short runs (20-120 repeats) came out 2.4 x zlib's size.  Those positions come out of
+	// the shallow pass as literals, i.e. as token starts, so the DEEP pass sees every one of them: it looks at distances
+	// 1-8 directly (the 8 bytes in front of the position are two more words away).  28 instructions per 32 queued
+	// positions, about 0.5 % of a sub-block.  Tried instead and measured: the same probe in the shallow pass behind a
+	// warp vote on the first links (-4 % with a vote that catches run starts, no gain with a stricter one), exact
+	// chaining inside the insert instruction with match.any (level 6: 23 -> 11.5 GB/s) or with a read-back of the racy
+	// store (-28 %), a repeat-distance probe with 3/4-byte matches (-6 % for +0.3 % ratio).
+	if (probe_runs && maxl >= (uint32_t)kMinMatch && maxdist >= 4) {
 		const uint32_t o = pos & kRingMask, a = o & ~3u, sh = (o & 3) * 8;
 		const uint32_t wm1 = ld32(ring8, (a - 4) & kRingMask);
 		const uint32_t before = __funnelshift_r(wm1, ld32(ring8, a), sh);                                  // bytes [pos-4, pos)
@@ -608,7 +591,7 @@ __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, 
 		if (__funnelshift_r(before, P0, 24) == P0) rd = 1;
 		if (rd) {
 			const uint32_t rl = match_length(ring8, pos, pos - rd, maxl, P0, P1, P2, P3);
-			if (rl >= (uint32_t)kMinMatch) {
+			if (rl > bl) {
 				bl = rl; bd = rd;
 				if (bl >= nice || bl >= maxl)
 					d = 0;
@@ -616,17 +599,6 @@ __device__ __forceinline__ void walk_chain(const Smem &S, const uint8_t *ring8, 
 					endw = load4(ring8, pos + bl - 3);
 			}
 		}
-	}
-	if (tok_is_match(seed) && tok_len(seed) <= maxl) {
-		bl = tok_len(seed); bd = tok_dist(seed);
-		if (bl >= nice || bl >= maxl)
-			d = 0;
-		else
-			endw = load4(ring8, pos + bl - 3);
-	}
-	if (resume != 0xffffffffu && d) {
-		acc = resume >> 16;
-		d = resume & 0xffffu;
 	}
 	for (int hop = 0; hop < depth; hop++) {
 		if (!__any_sync(0xffffffffu, d != 0))
@@ -702,7 +674,7 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 		const uint32_t pos = act ? qpos : sub_lo;
 		const uint32_t maxl = act ? min((uint32_t)kMaxMatch, PE - pos) : 0;
 		uint32_t bl, bd;
-		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), max(1, depth - d1), (uint32_t)nice, bl, bd, act ? qtok : 0, nullptr, act ? qcur : 0);   // the first d1 hops were walked by the shallow pass
+		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), max(1, depth - d1), (uint32_t)nice, bl, bd, act ? qtok : 0, nullptr, act ? qcur : 0, use_rep);   // the first d1 hops were walked by the shallow pass
 		if (act && bd)
 			__stcg(&pres[pos - sub_lo], tok_match(bl, bd));
 	};
@@ -716,7 +688,7 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 		const uint32_t maxl = live ? min((uint32_t)kMaxMatch, PE - pos) : 0;
 		uint32_t bl, bd;
 		uint32_t mycur;
-		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), d1, (uint32_t)nice, bl, bd, 0, &mycur, 0xffffffffu, use_rep);
+		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), d1, (uint32_t)nice, bl, bd, 0, &mycur);
 		const uint32_t len = bd ? bl : 0;
 		const uint32_t mytok = len ? tok_match(len, bd) : 0;
 		if (live)
@@ -1377,7 +1349,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 				const uint32_t cnt = d1 & 0xff
 					? parse_subblock_2pass(S, sub_lo, sub_hi, P0, PE, d1 & 0xff, depth, nice, lazy, probe, tokpos + (size_t)sb * kSub,
 							       pres + (size_t)warp * (kSub + 32), nwin, end_pos)
-					: parse_subblock(S, sub_lo, sub_hi, P0, PE, depth, nice, lazy, probe, tokpos + (size_t)sb * kSub, nwin, end_pos);
+					: parse_subblock(S, sub_lo, sub_hi, P0, PE, depth, nice, lazy, tokpos + (size_t)sb * kSub, nwin, end_pos);
 				if (lane_id() == 0) {
 					meta[sb * kMeta + M_CNT] = cnt;
 					meta[sb * kMeta + M_END] = end_pos;
