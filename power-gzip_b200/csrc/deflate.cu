@@ -156,6 +156,15 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy()
 	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
 	return pol;
 }
+// Scratch that is dead (the tokens once they are packed, the private output slot once it is copied into the stream) would
+// still be written back to DRAM when the L2 evicts its dirty lines — 1.0 GB of the 2.3 GB a 1 GiB launch moved.
+// discard.global.L2 drops the lines instead.  base must be 128-byte aligned and the whole lines private to this CTA.
+__device__ __forceinline__ void l2_discard_lines(const void *base, uint32_t bytes)
+{
+	const char *p = static_cast<const char *>(base);
+	for (uint32_t o = threadIdx.x * 128u; o < bytes; o += kThreads * 128u)
+		asm volatile("discard.global.L2 [%0], 128;\n" ::"l"(p + o) : "memory");
+}
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint64_t pol)
 {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n"
@@ -1197,7 +1206,8 @@ __device__ uint32_t emit_stored(const DeflateJob &J, bool final_flag)
 __host__ __device__ inline uint32_t scratch_nsub(uint32_t tok_stride) { return tok_stride / kSub + 2; }
 constexpr int kMeta = 8;     // per sub-block: tokens, end position, tokens dropped in front, kept tokens, flat offset, tail count, tail tokens[2]
 enum { M_CNT = 0, M_END = 1, M_SKIP = 2, M_NEW = 3, M_OFF = 4, M_TAILN = 5, M_TAIL0 = 6, M_TAIL1 = 7 };
-__host__ __device__ inline size_t scratch_words(uint32_t tok_stride) { return 2 * (size_t)tok_stride + kMeta * (size_t)scratch_nsub(tok_stride) + 32 * (size_t)(kSub + 32); }
+// (a multiple of 32 words, so that every CTA's scratch starts on a 128-byte line: dead token lines are discarded from the L2)
+__host__ __device__ inline size_t scratch_words(uint32_t tok_stride) { return (2 * (size_t)tok_stride + kMeta * (size_t)scratch_nsub(tok_stride) + 32 * (size_t)(kSub + 32) + 31) & ~(size_t)31; }
 
 // ---- fused stitch (StreamOut): wait for the predecessor's end offset, publish ours, copy the slot there ----
 __device__ void stream_out(Smem &S, const StreamOut &so, const DeflateJob &J, uint32_t job, uint32_t n_jobs, uint32_t len)
@@ -1262,11 +1272,21 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 		// jobs are handed out in order; when the input is still being uploaded (host-pointer streams)
 		// ready[k] turns non-zero once the slice holding jobs [k*jobs_per_flag, (k+1)*jobs_per_flag) has landed
 		if (threadIdx.x == 0) {
-			const uint32_t j = atomicAdd(job_counter, 1u);
+			uint32_t j = atomicAdd(job_counter, 1u);
 			if (j < n_jobs && ready) {
-				while (ready[j / jobs_per_flag] == 0)
+				// bounded: if the upload of this slice never completes (a failed copy on the host side) the chunk is
+				// reported as failed after ~30 s instead of spinning for ever
+				uint32_t spins = 0;
+				while (ready[j / jobs_per_flag] == 0 && ++spins < 30000000u)
 					__nanosleep(1000);
 				__threadfence();
+				if (spins >= 30000000u) {
+					DeflateOut o = {};
+					o.rc = NXGPU_E_NODEV;
+					outs[j] = o;
+					if (so.dst) so.chain[j] = 1;          // an empty chunk at offset 0: nobody behind it waits for ever either
+					j = 0xffffffffu;                      // this CTA stops
+				}
 			}
 			S.misc[7] = j;
 		}
@@ -1607,6 +1627,14 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 					J.out[P.words_out * 4 + b] = (uint8_t)(v >> (8 * b));
 			}
 		}
+		// the tokens of this chunk are dead now (every thread is past the barriers of the packer)
+		l2_discard_lines(tok, (ntok * 4 + 127) & ~127u);
+		for (uint32_t sb = threadIdx.x; sb < n_sub; sb += kThreads) {
+			const uint32_t lines = (meta[sb * kMeta + M_CNT] * 4 + 127) >> 7;
+			const char *tp = reinterpret_cast<const char *>(tokpos + (size_t)sb * kSub);
+			for (uint32_t l = 0; l < lines; l++)
+				asm volatile("discard.global.L2 [%0], 128;\n" ::"l"(tp + 128 * l) : "memory");
+		}
 		if (warp == 2) { DBG_ADD(5, clock64() - thuf0); DBG_ADD(6, clock64() - tjob0); }
 		if (threadIdx.x == 0) {
 			DeflateOut o = {};
@@ -1621,6 +1649,9 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 		if (so.dst) {
 			stream_out(S, so, J, job, n_jobs, total_bytes);
 			__syncthreads();
+			// the slot has been copied into the stream: drop its lines too (slots are 128-byte aligned and padded)
+			if ((reinterpret_cast<uintptr_t>(J.out) & 127) == 0)
+				l2_discard_lines(J.out, (total_bytes + 127) & ~127u);
 		}
 	}
 }

@@ -398,7 +398,7 @@ extern "C++" int nxgpu::deflate_device(nxgpu_ctx *c, DeflateJob *jobs_h, size_t 
 		return (j.flags & NXGPU_F_NO_JOINER) ? 2 * j.src_len + 1024 : nxgpu_deflate_bound(j.src_len);
 	};
 	for (size_t i = 0; i < n; i++) {
-		slot_total += align_up(slot_cap(jobs_h[i]) + 16, 16);
+		slot_total += align_up(slot_cap(jobs_h[i]) + 16, 128);      // whole 128-byte lines per slot: the kernel discards them from the L2 once copied
 		if (jobs_h[i].src_len > max_len) max_len = jobs_h[i].src_len;
 	}
 	const int grid = (int)(n < (size_t)kNumSMs ? n : (size_t)kNumSMs);
@@ -411,7 +411,7 @@ extern "C++" int nxgpu::deflate_device(nxgpu_ctx *c, DeflateJob *jobs_h, size_t 
 	for (size_t i = 0; i < n; i++) {
 		jobs_h[i].out = static_cast<uint8_t *>(c->d_slots.p) + o;
 		jobs_h[i].out_cap = slot_cap(jobs_h[i]);
-		o += align_up(jobs_h[i].out_cap + 16, 16);
+		o += align_up(jobs_h[i].out_cap + 16, 128);
 	}
 	NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_jobs.p, jobs_h, n * sizeof(DeflateJob), cudaMemcpyHostToDevice, c->stream));
 	// one persistent launch; jobs are claimed in order.  For host-pointer streams the kernel is launched
