@@ -658,7 +658,7 @@ __device__ __forceinline__ void window_parse(uint32_t lane, uint32_t nlive, uint
 }
 
 __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_hi, uint32_t valid_lo, uint32_t PE,
-					 int d1, int depth, int nice, int lazy, bool use_rep /* run probe */, uint32_t *tk, uint32_t *pres,
+					 int d1, int depth, int nice, int lazy, bool use_rep /* run probe */, bool skip_covered, uint32_t *tk, uint32_t *pres,
 					 uint32_t &nwin, uint32_t &end_pos)
 {
 	const uint32_t lane = lane_id();
@@ -668,6 +668,7 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 	uint32_t qpos = 0, qtok = 0, qcur = 0, qn = 0;             // pass-2 queue: one position (its shallow result, its chain cursor) per lane
 	uint32_t headA = 0;                                        // pass-1 parse: next token start (relative to sub_lo)
 	uint32_t carry = 0;                                        // mark for lane 0 of the next window
+	uint32_t cov_d = 0;                                        // distance of the match that carries the shallow parse to headA (0: a literal)
 
 	// Chain depth of the deep pass follows the data: the cost of a sub-block is (queued positions) x
 	// depth, and long-match data (few token starts per byte, many equally good candidates) is where
@@ -690,8 +691,17 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 
 	// ---- pass 1 (+ pass 2 whenever 32 positions are queued) ----
 	for (uint32_t w0 = 0; w0 < npos; w0 += 32) {
-		nwin++;
 		const uint32_t pos = sub_lo + w0 + lane;
+		if (skip_covered && cov_d && carry == 0 && headA >= w0 + 32 && w0 + 32 <= npos) {
+			// The token the shallow parse is inside of covers this whole window: no token starts here, so nothing here is
+			// queued for the deep pass, and the only way the final parse can land in this window is a deep match at an
+			// earlier start that ends in it — and then the covering match's own tail (same distance, what is left of its
+			// length) is a valid match for that position.  The window is not searched at all.
+			const uint32_t rem = headA - (w0 + lane);
+			__stcg(&pres[w0 + lane], rem >= (uint32_t)kMinMatch ? tok_match(rem, cov_d) : (uint32_t)ring8[pos & kRingMask]);
+			continue;
+		}
+		nwin++;
 		const uint32_t nlive = min(32u, npos - w0);
 		const bool live = lane < nlive;
 		const uint32_t maxl = live ? min((uint32_t)kMaxMatch, PE - pos) : 0;
@@ -710,6 +720,12 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 			const uint32_t h = headA - w0;
 			const uint32_t R = __shfl_sync(0xffffffffu, Rl, h);
 			headA = w0 + __shfl_sync(0xffffffffu, J, h);
+			{
+				// the token that leaves the window: the last start of the reach set
+				const uint32_t last = 31 - __clz(R);
+				const uint32_t ltake = __ballot_sync(0xffffffffu, take);
+				cov_d = ((ltake >> last) & 1) ? __shfl_sync(0xffffffffu, bd, last) : 0;
+			}
 			// a start whose match is short enough for the lazy rule also needs the position behind it
 			const uint32_t nx = __ballot_sync(0xffffffffu, ((R >> lane) & 1) && lazy && len < (uint32_t)lazy);
 			M |= R | (nx << 1);
@@ -1367,7 +1383,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 				uint32_t end_pos;
 				const bool probe = run_probe;
 				const uint32_t cnt = d1 & 0xff
-					? parse_subblock_2pass(S, sub_lo, sub_hi, P0, PE, d1 & 0xff, depth, nice, lazy, probe, tokpos + (size_t)sb * kSub,
+					? parse_subblock_2pass(S, sub_lo, sub_hi, P0, PE, d1 & 0xff, depth, nice, lazy, probe, (d1 & 0x400) != 0, tokpos + (size_t)sb * kSub,
 							       pres + (size_t)warp * (kSub + 32), nwin, end_pos)
 					: parse_subblock(S, sub_lo, sub_hi, P0, PE, depth, nice, lazy, tokpos + (size_t)sb * kSub, nwin, end_pos);
 				if (lane_id() == 0) {
@@ -1761,7 +1777,9 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 		return me;
 	// the run probe (bit 9) rides in the high bits of d1 (NXGPU_RUN_PROBE=0: developer switch)
 	static const bool use_rep = !(getenv("NXGPU_RUN_PROBE") && atoi(getenv("NXGPU_RUN_PROBE")) == 0);
-	const int d1f = lp.d1 | (use_rep ? 0x200 : 0);
+	// bit 10: windows wholly covered by the current shallow token are not searched (NXGPU_SKIP_COVERED=0: developer switch)
+	static const bool skip_cov = !(getenv("NXGPU_SKIP_COVERED") && atoi(getenv("NXGPU_SKIP_COVERED")) == 0);
+	const int d1f = lp.d1 | (use_rep ? 0x200 : 0) | (skip_cov ? 0x400 : 0);
 	deflate_kernel<<<grid, kThreads, sizeof(Smem), s>>>(jobs, outs, n_jobs, lp.depth, lp.lazy, lp.nice, tok_scratch, tok_stride, parser_mask,
 							    job_counter, ready, jobs_per_flag ? jobs_per_flag : 1, d1f, so ? *so : StreamOut());
 	cudaError_t e = cudaGetLastError();
