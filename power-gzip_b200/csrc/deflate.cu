@@ -658,7 +658,7 @@ __device__ __forceinline__ void window_parse(uint32_t lane, uint32_t nlive, uint
 }
 
 __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_hi, uint32_t valid_lo, uint32_t PE,
-					 int d1, int depth, int nice, int lazy, bool use_rep /* run probe */, bool skip_covered, uint32_t *tk, uint32_t *pres,
+					 int d1, int depth, int nice, int lazy, bool use_rep /* run probe */, bool skip_covered, bool stride2, uint32_t *tk, uint32_t *pres,
 					 uint32_t &nwin, uint32_t &end_pos)
 {
 	const uint32_t lane = lane_id();
@@ -690,26 +690,22 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 	};
 
 	// ---- pass 1 (+ pass 2 whenever 32 positions are queued) ----
-	for (uint32_t w0 = 0; w0 < npos; w0 += 32) {
-		const uint32_t pos = sub_lo + w0 + lane;
-		if (skip_covered && cov_d && carry == 0 && headA >= w0 + 32 && w0 + 32 <= npos) {
-			// The token the shallow parse is inside of covers this whole window: no token starts here, so nothing here is
-			// queued for the deep pass, and the only way the final parse can land in this window is a deep match at an
-			// earlier start that ends in it — and then the covering match's own tail (same distance, what is left of its
-			// length) is a valid match for that position.  The window is not searched at all.
-			const uint32_t rem = headA - (w0 + lane);
-			__stcg(&pres[w0 + lane], rem >= (uint32_t)kMinMatch ? tok_match(rem, cov_d) : (uint32_t)ring8[pos & kRingMask]);
-			continue;
-		}
+	// The token the shallow parse is inside of may cover a whole window: no token starts there, so nothing there is
+	// queued for the deep pass, and the only way the final parse can land in it is a deep match at an earlier start that
+	// ends in it — and then the covering match's own tail (same distance, what is left of its length) is a valid match
+	// for that position.  Such a window is not searched at all.
+	auto covered = [&](uint32_t w0) { return skip_covered && cov_d && carry == 0 && headA >= w0 + 32 && w0 + 32 <= npos; };
+	auto inherit = [&](uint32_t w0) {
+		const uint32_t rem = headA - (w0 + lane);
+		__stcg(&pres[w0 + lane], rem >= (uint32_t)kMinMatch ? tok_match(rem, cov_d) : (uint32_t)ring8[(sub_lo + w0 + lane) & kRingMask]);
+	};
+	// one window of 32 positions whose shallow results are in (mytok, mycur), one position per lane
+	auto window = [&](uint32_t w0, uint32_t mytok, uint32_t mycur) {
 		nwin++;
+		const uint32_t pos = sub_lo + w0 + lane;
 		const uint32_t nlive = min(32u, npos - w0);
 		const bool live = lane < nlive;
-		const uint32_t maxl = live ? min((uint32_t)kMaxMatch, PE - pos) : 0;
-		uint32_t bl, bd;
-		uint32_t mycur;
-		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), d1, (uint32_t)nice, bl, bd, 0, &mycur);
-		const uint32_t len = bd ? bl : 0;
-		const uint32_t mytok = len ? tok_match(len, bd) : 0;
+		const uint32_t len = tok_is_match(mytok) ? tok_len(mytok) : 0;
 		if (live)
 			__stcg(&pres[w0 + lane], len ? mytok : (uint32_t)ring8[pos & kRingMask]);
 		uint32_t M = carry;
@@ -724,7 +720,7 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 				// the token that leaves the window: the last start of the reach set
 				const uint32_t last = 31 - __clz(R);
 				const uint32_t ltake = __ballot_sync(0xffffffffu, take);
-				cov_d = ((ltake >> last) & 1) ? __shfl_sync(0xffffffffu, bd, last) : 0;
+				cov_d = ((ltake >> last) & 1) ? tok_dist(__shfl_sync(0xffffffffu, mytok, last)) : 0;
 			}
 			// a start whose match is short enough for the lazy rule also needs the position behind it
 			const uint32_t nx = __ballot_sync(0xffffffffu, ((R >> lane) & 1) && lazy && len < (uint32_t)lazy);
@@ -759,6 +755,54 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 			if (qn == 32) {
 				deep(32, min(w0 + 32, npos));
 				qn = 0;
+			}
+		}
+	};
+	if (!stride2) {
+		for (uint32_t w0 = 0; w0 < npos; w0 += 32) {
+			if (covered(w0)) { inherit(w0); continue; }
+			const uint32_t pos = sub_lo + w0 + lane;
+			const uint32_t maxl = lane < min(32u, npos - w0) ? min((uint32_t)kMaxMatch, PE - pos) : 0;
+			uint32_t bl, bd, mycur;
+			walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), d1, (uint32_t)nice, bl, bd, 0, &mycur);
+			window(w0, bd ? tok_match(bl, bd) : 0, mycur);
+		}
+	} else {
+		// Stride 2: the shallow pass only searches the EVEN positions of 64 (one per lane); an odd position takes the better
+		// of its left neighbour's match minus its first byte and its right neighbour's match extended one byte backwards.
+		// A match that starts at an odd position is missed only when it is exactly 5 bytes long and does not extend to
+		// the left (tools/lzsim.c stride=2: alice29 -0.15 %, source code -0.06 %, makedata +0.2 .. +1.5 % ratio) — and the
+		// shallow search, a third of all instructions, halves.
+		for (uint32_t g0 = 0; g0 < npos; g0 += 64) {
+			if (covered(g0) && headA >= g0 + 64 && g0 + 64 <= npos) { inherit(g0); inherit(g0 + 32); continue; }
+			const uint32_t pe = sub_lo + g0 + 2 * lane, po = pe + 1;
+			const bool le = g0 + 2 * lane < npos, lo = g0 + 2 * lane + 1 < npos;
+			const uint32_t maxl = le ? min((uint32_t)kMaxMatch, PE - pe) : 0;
+			uint32_t bl, bd, cur_e;
+			walk_chain(S, ring8, pe, maxl, min((uint32_t)kWindow, pe - valid_lo), d1, (uint32_t)nice, bl, bd, 0, &cur_e);
+			const uint32_t tok_e = bd ? tok_match(bl, bd) : 0;
+			// the odd position behind it
+			uint32_t ol = 0, od = 0;
+			if (bd && bl > (uint32_t)kMinMatch) { ol = bl - 1; od = bd; }
+			{
+				const uint32_t nt = __shfl_down_sync(0xffffffffu, tok_e, 1);       // lane 31 has no right neighbour in this group
+				if (lane < 31 && lo && tok_is_match(nt)) {
+					const uint32_t nl = tok_len(nt), nd = tok_dist(nt);
+					if (nl + 1 > ol && nl < (uint32_t)kMaxMatch && po - valid_lo >= nd &&
+					    ring8[po & kRingMask] == ring8[(po - nd) & kRingMask]) { ol = nl + 1; od = nd; }
+				}
+			}
+			const uint32_t tok_o = (lo && od) ? tok_match(ol, od) : 0;
+#pragma unroll
+			for (int half = 0; half < 2; half++) {
+				const uint32_t w0 = g0 + 32 * half;
+				if (w0 >= npos)
+					break;
+				if (covered(w0)) { inherit(w0); continue; }
+				const uint32_t srcl = 16 * half + (lane >> 1);
+				const uint32_t te = __shfl_sync(0xffffffffu, tok_e, srcl), to = __shfl_sync(0xffffffffu, tok_o, srcl);
+				const uint32_t ce = __shfl_sync(0xffffffffu, cur_e, srcl);
+				window(w0, (lane & 1) ? to : te, (lane & 1) ? 0xffffffffu : ce);
 			}
 		}
 	}
@@ -1383,7 +1427,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 				uint32_t end_pos;
 				const bool probe = run_probe;
 				const uint32_t cnt = d1 & 0xff
-					? parse_subblock_2pass(S, sub_lo, sub_hi, P0, PE, d1 & 0xff, depth, nice, lazy, probe, (d1 & 0x400) != 0, tokpos + (size_t)sb * kSub,
+					? parse_subblock_2pass(S, sub_lo, sub_hi, P0, PE, d1 & 0xff, depth, nice, lazy, probe, (d1 & 0x400) != 0, (d1 & 0x800) != 0, tokpos + (size_t)sb * kSub,
 							       pres + (size_t)warp * (kSub + 32), nwin, end_pos)
 					: parse_subblock(S, sub_lo, sub_hi, P0, PE, depth, nice, lazy, tokpos + (size_t)sb * kSub, nwin, end_pos);
 				if (lane_id() == 0) {
@@ -1779,7 +1823,9 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 	static const bool use_rep = !(getenv("NXGPU_RUN_PROBE") && atoi(getenv("NXGPU_RUN_PROBE")) == 0);
 	// bit 10: windows wholly covered by the current shallow token are not searched (NXGPU_SKIP_COVERED=0: developer switch)
 	static const bool skip_cov = !(getenv("NXGPU_SKIP_COVERED") && atoi(getenv("NXGPU_SKIP_COVERED")) == 0);
-	const int d1f = lp.d1 | (use_rep ? 0x200 : 0) | (skip_cov ? 0x400 : 0);
+	// bit 11: the shallow pass searches every second position (NXGPU_STRIDE2=0: developer switch)
+	static const bool stride2 = !(getenv("NXGPU_STRIDE2") && atoi(getenv("NXGPU_STRIDE2")) == 0);
+	const int d1f = lp.d1 | (use_rep ? 0x200 : 0) | (skip_cov ? 0x400 : 0) | (stride2 ? 0x800 : 0);
 	deflate_kernel<<<grid, kThreads, sizeof(Smem), s>>>(jobs, outs, n_jobs, lp.depth, lp.lazy, lp.nice, tok_scratch, tok_stride, parser_mask,
 							    job_counter, ready, jobs_per_flag ? jobs_per_flag : 1, d1f, so ? *so : StreamOut());
 	cudaError_t e = cudaGetLastError();

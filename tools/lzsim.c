@@ -6,7 +6,7 @@
 #include <math.h>
 #define WIN 32768
 static uint8_t *buf; static size_t n;
-static int HB_A=12, NB_A=4, DEPTH_A=32, HB_B=12, NB_B=0, DEPTH_B=1, LAZY=32, NICE=258, SUB=0, CHUNK=262144, MINM=4, GOODCUT=0, RACY=0, CS=0, TWO=0;
+static int HB_A=12, NB_A=4, DEPTH_A=32, HB_B=12, NB_B=0, DEPTH_B=1, LAZY=32, NICE=258, SUB=0, CHUNK=262144, MINM=4, GOODCUT=0, RACY=0, CS=0, TWO=0, STRIDE=1;
 static inline uint64_t ld8(const uint8_t*p){uint64_t v; memcpy(&v,p,8); return v;}
 static inline uint32_t hashn(const uint8_t*p,int nb,int hb){ uint64_t v=ld8(p); if(nb<8) v&=((1ull<<(8*nb))-1); return (uint32_t)((v*0x9E3779B185EBCA87ull)>>(64-hb)); }
 static int mlen(const uint8_t*a,const uint8_t*b,int maxl){int l=0; while(l<maxl&&a[l]==b[l])l++; return l;}
@@ -26,7 +26,7 @@ int main(int argc,char**argv){
   const char*fn=argv[1]; size_t limit=0;
   for(int i=2;i<argc;i++){ char*a=argv[i]; int v=atoi(strchr(a,'=')?strchr(a,'=')+1:"0");
     if(!strncmp(a,"ha=",3))HB_A=v; else if(!strncmp(a,"na=",3))NB_A=v; else if(!strncmp(a,"da=",3))DEPTH_A=v; else if(!strncmp(a,"hb=",3))HB_B=v; else if(!strncmp(a,"nb=",3))NB_B=v; else if(!strncmp(a,"db=",3))DEPTH_B=v;
-    else if(!strncmp(a,"lazy=",5))LAZY=v; else if(!strncmp(a,"nice=",5))NICE=v; else if(!strncmp(a,"sub=",4))SUB=v; else if(!strncmp(a,"chunk=",6))CHUNK=v; else if(!strncmp(a,"min=",4))MINM=v; else if(!strncmp(a,"limit=",6))limit=(size_t)v<<20; else if(!strncmp(a,"good=",5))GOODCUT=v; else if(!strncmp(a,"racy=",5))RACY=v; else if(!strncmp(a,"cs=",3))CS=v; else if(!strncmp(a,"two=",4))TWO=v; }
+    else if(!strncmp(a,"lazy=",5))LAZY=v; else if(!strncmp(a,"nice=",5))NICE=v; else if(!strncmp(a,"sub=",4))SUB=v; else if(!strncmp(a,"chunk=",6))CHUNK=v; else if(!strncmp(a,"min=",4))MINM=v; else if(!strncmp(a,"limit=",6))limit=(size_t)v<<20; else if(!strncmp(a,"good=",5))GOODCUT=v; else if(!strncmp(a,"racy=",5))RACY=v; else if(!strncmp(a,"cs=",3))CS=v; else if(!strncmp(a,"two=",4))TWO=v; else if(!strncmp(a,"stride=",7))STRIDE=v; }
   FILE*f=fopen(fn,"rb"); fseek(f,0,SEEK_END); n=ftell(f); fseek(f,0,SEEK_SET); if(limit&&n>limit)n=limit; buf=malloc(n+16); if(fread(buf,1,n,f)!=n)return 1; memset(buf+n,0,16);
   int *headA=malloc(sizeof(int)<<HB_A), *headB=malloc(sizeof(int)<<(NB_B?HB_B:1)); int *prevA=malloc(sizeof(int)*(n+1)), *prevB=NB_B?malloc(sizeof(int)*(n+1)):0;
   int *blen=malloc(sizeof(int)*(CHUNK+1)), *bdist=malloc(sizeof(int)*(CHUNK+1));
@@ -44,7 +44,8 @@ int main(int argc,char**argv){
     int npass = TWO?2:1;
     for(int pass=0; pass<npass; pass++){
     int DEPTH_SAVE=DEPTH_A; if(TWO && pass==0) DEPTH_A=TWO;
-    for(size_t p=c0;p<c1;p++){ int maxl=258; if(TWO && pass==1 && !mark[p-c0]) continue; size_t lim=c1; if(SUB){ size_t sb=c0+((p-c0)/SUB+1)*SUB; if(sb<lim)lim=sb; } if(p+maxl>lim)maxl=lim-p;
+    for(size_t p=c0;p<c1;p++){ int maxl=258; if(TWO && pass==1 && !mark[p-c0]) continue;
+      if(TWO && pass==0 && STRIDE==2 && ((p-c0)&1)){ blen[p-c0]=-1; continue; }   /* stride 2: odd positions are derived from their neighbours below */ size_t lim=c1; if(SUB){ size_t sb=c0+((p-c0)/SUB+1)*SUB; if(sb<lim)lim=sb; } if(p+maxl>lim)maxl=lim-p;
       int bl=MINM-1,bd=0; nsearch++;
       int depth=DEPTH_A;
       if(CS){ int off=0, seen=0; int node=prevA[p]; for(int k=0;k<depth;k++){ if(node<0)break; int q=node-off; if(q<(int)h0||(int)p-q>WIN)break; hops++; int dist=p-q;
@@ -57,6 +58,9 @@ int main(int argc,char**argv){
       if(NB_B&&bl<NICE&&bl<maxl){ for(int q=prevB[p],k=0;q>=(int)h0&&k<DEPTH_B&&(int)p-q<=WIN;q=prevB[q],k++){ hops++; if(buf[q+bl]!=buf[p+bl]&&bl<maxl)continue; cmps++; int l=mlen(buf+p,buf+q,maxl); if(l>bl){bl=l;bd=p-q; if(l>=NICE||l>=maxl)break;} } }
       if(bl<MINM||bl>maxl){bl=0;} blen[p-c0]=bl; bdist[p-c0]=bd; }
     DEPTH_A=DEPTH_SAVE;
+    if(TWO && pass==0 && STRIDE==2){ for(size_t p=c0+1;p<c1;p+=2){ int bl=0,bd=0; int l0=blen[p-1-c0]; if(l0-1>=MINM){bl=l0-1;bd=bdist[p-1-c0];}
+        if(p+1<c1){ int l1=blen[p+1-c0], d1=bdist[p+1-c0]; if(l1>0 && (int)(p-c0)>=0 && p>=(size_t)d1+h0 && buf[p]==buf[p-d1] && l1+1>bl && l1+1<=258){bl=l1+1;bd=d1;} }
+        blen[p-c0]=bl; bdist[p-c0]=bd; } }
     if(TWO && pass==0){ memset(mark,0,CHUNK+2); size_t p=c0; while(p<c1){ int l=blen[p-c0]; mark[p-c0]=1; if(p+1<c1) mark[p+1-c0]=1; if(l&&LAZY&&l<LAZY&&p+1<c1&&blen[p+1-c0]>l) l=0; p+= l?l:1; } }
     }
     // parse greedy/lazy(1)
