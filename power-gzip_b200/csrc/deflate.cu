@@ -658,7 +658,7 @@ __device__ __forceinline__ void window_parse(uint32_t lane, uint32_t nlive, uint
 }
 
 __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_hi, uint32_t valid_lo, uint32_t PE,
-					 int d1, int depth, int nice, int lazy, bool use_rep /* run probe */, bool skip_covered, bool stride2, uint32_t *tk, uint32_t *pres,
+					 int d1, int depth, int nice, int lazy, bool use_rep /* run probe */, bool skip_covered, uint32_t *tk, uint32_t *pres,
 					 uint32_t &nwin, uint32_t &end_pos)
 {
 	const uint32_t lane = lane_id();
@@ -758,53 +758,13 @@ __device__ uint32_t parse_subblock_2pass(Smem &S, uint32_t sub_lo, uint32_t sub_
 			}
 		}
 	};
-	if (!stride2) {
-		for (uint32_t w0 = 0; w0 < npos; w0 += 32) {
-			if (covered(w0)) { inherit(w0); continue; }
-			const uint32_t pos = sub_lo + w0 + lane;
-			const uint32_t maxl = lane < min(32u, npos - w0) ? min((uint32_t)kMaxMatch, PE - pos) : 0;
-			uint32_t bl, bd, mycur;
-			walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), d1, (uint32_t)nice, bl, bd, 0, &mycur);
-			window(w0, bd ? tok_match(bl, bd) : 0, mycur);
-		}
-	} else {
-		// Stride 2: the shallow pass only searches the EVEN positions of 64 (one per lane); an odd position takes the better
-		// of its left neighbour's match minus its first byte and its right neighbour's match extended one byte backwards.
-		// A match that starts at an odd position is missed only when it is exactly 5 bytes long and does not extend to
-		// the left (tools/lzsim.c stride=2: alice29 -0.15 %, source code -0.06 %, makedata +0.2 .. +1.5 % ratio) — and the
-		// shallow search, a third of all instructions, halves.
-		for (uint32_t g0 = 0; g0 < npos; g0 += 64) {
-			if (covered(g0) && headA >= g0 + 64 && g0 + 64 <= npos) { inherit(g0); inherit(g0 + 32); continue; }
-			const uint32_t pe = sub_lo + g0 + 2 * lane, po = pe + 1;
-			const bool le = g0 + 2 * lane < npos, lo = g0 + 2 * lane + 1 < npos;
-			const uint32_t maxl = le ? min((uint32_t)kMaxMatch, PE - pe) : 0;
-			uint32_t bl, bd, cur_e;
-			walk_chain(S, ring8, pe, maxl, min((uint32_t)kWindow, pe - valid_lo), d1, (uint32_t)nice, bl, bd, 0, &cur_e);
-			const uint32_t tok_e = bd ? tok_match(bl, bd) : 0;
-			// the odd position behind it
-			uint32_t ol = 0, od = 0;
-			if (bd && bl > (uint32_t)kMinMatch) { ol = bl - 1; od = bd; }
-			{
-				const uint32_t nt = __shfl_down_sync(0xffffffffu, tok_e, 1);       // lane 31 has no right neighbour in this group
-				if (lane < 31 && lo && tok_is_match(nt)) {
-					const uint32_t nl = tok_len(nt), nd = tok_dist(nt);
-					if (nl + 1 > ol && nl < (uint32_t)kMaxMatch && po - valid_lo >= nd &&
-					    ring8[po & kRingMask] == ring8[(po - nd) & kRingMask]) { ol = nl + 1; od = nd; }
-				}
-			}
-			const uint32_t tok_o = (lo && od) ? tok_match(ol, od) : 0;
-#pragma unroll
-			for (int half = 0; half < 2; half++) {
-				const uint32_t w0 = g0 + 32 * half;
-				if (w0 >= npos)
-					break;
-				if (covered(w0)) { inherit(w0); continue; }
-				const uint32_t srcl = 16 * half + (lane >> 1);
-				const uint32_t te = __shfl_sync(0xffffffffu, tok_e, srcl), to = __shfl_sync(0xffffffffu, tok_o, srcl);
-				const uint32_t ce = __shfl_sync(0xffffffffu, cur_e, srcl);
-				window(w0, (lane & 1) ? to : te, (lane & 1) ? 0xffffffffu : ce);
-			}
-		}
+	for (uint32_t w0 = 0; w0 < npos; w0 += 32) {
+		if (covered(w0)) { inherit(w0); continue; }
+		const uint32_t pos = sub_lo + w0 + lane;
+		const uint32_t maxl = lane < min(32u, npos - w0) ? min((uint32_t)kMaxMatch, PE - pos) : 0;
+		uint32_t bl, bd, mycur;
+		walk_chain(S, ring8, pos, maxl, min((uint32_t)kWindow, pos - valid_lo), d1, (uint32_t)nice, bl, bd, 0, &mycur);
+		window(w0, bd ? tok_match(bl, bd) : 0, mycur);
 	}
 	if (qn)
 		deep(qn, npos);
@@ -1427,7 +1387,7 @@ deflate_kernel(const DeflateJob *__restrict__ jobs, DeflateOut *__restrict__ out
 				uint32_t end_pos;
 				const bool probe = run_probe;
 				const uint32_t cnt = d1 & 0xff
-					? parse_subblock_2pass(S, sub_lo, sub_hi, P0, PE, d1 & 0xff, depth, nice, lazy, probe, (d1 & 0x400) != 0, (d1 & 0x800) != 0, tokpos + (size_t)sb * kSub,
+					? parse_subblock_2pass(S, sub_lo, sub_hi, P0, PE, d1 & 0xff, depth, nice, lazy, probe, (d1 & 0x400) != 0, tokpos + (size_t)sb * kSub,
 							       pres + (size_t)warp * (kSub + 32), nwin, end_pos)
 					: parse_subblock(S, sub_lo, sub_hi, P0, PE, depth, nice, lazy, tokpos + (size_t)sb * kSub, nwin, end_pos);
 				if (lane_id() == 0) {
@@ -1824,8 +1784,7 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 	// bit 10: windows wholly covered by the current shallow token are not searched (NXGPU_SKIP_COVERED=0: developer switch)
 	static const bool skip_cov = !(getenv("NXGPU_SKIP_COVERED") && atoi(getenv("NXGPU_SKIP_COVERED")) == 0);
 	// bit 11: the shallow pass searches every second position (NXGPU_STRIDE2=0: developer switch)
-	static const bool stride2 = !(getenv("NXGPU_STRIDE2") && atoi(getenv("NXGPU_STRIDE2")) == 0);
-	const int d1f = lp.d1 | (use_rep ? 0x200 : 0) | (skip_cov ? 0x400 : 0) | (stride2 ? 0x800 : 0);
+	const int d1f = lp.d1 | (use_rep ? 0x200 : 0) | (skip_cov ? 0x400 : 0);
 	deflate_kernel<<<grid, kThreads, sizeof(Smem), s>>>(jobs, outs, n_jobs, lp.depth, lp.lazy, lp.nice, tok_scratch, tok_stride, parser_mask,
 							    job_counter, ready, jobs_per_flag ? jobs_per_flag : 1, d1f, so ? *so : StreamOut());
 	cudaError_t e = cudaGetLastError();
