@@ -71,6 +71,10 @@ struct DeflateOut {
 
 constexpr uint32_t kWrapDry = 0x100;     // InflateJob::wrap flag: decode and count only, write nothing (member discovery)
 constexpr uint32_t kWrapJob = 4;         // InflateJob::wrap: NX decompress job semantics (nxu_run_job), raw deflate
+constexpr uint32_t kWrapNoHeader = 0x200; // InflateJob::wrap flag: the container header is behind us, src/start_bit point at a block header
+constexpr uint32_t kWrapSkip = 0x400;    // InflateJob::wrap flag: not this launch's business (the parallel path runs it), write nothing
+constexpr uint32_t kInflateMapStop = 8;  // InflateOut::flags: stopped at a block boundary that InflateJob::stop_map marks
+constexpr int32_t kInflateRetry = -1000; // InflateOut::rc (internal): the parallel path disagreed with itself, run the job serially
 struct InflateJob {
 	const uint8_t *src;
 	uint32_t src_len;
@@ -87,6 +91,10 @@ struct InflateJob {
 	uint32_t rembytecnt;    // stored bytes still to copy (sfbt 100x)
 	uint32_t single_block;  // FC 0x12 / 0x16: suspend at the end of the first block that completes
 	uint32_t pad_;
+	// --- one stream decoded by many warps (inflate_par.cuh) ---
+	const uint32_t *stop_map; // optional: one bit per source bit; a BFINAL=0 block that ends on a set bit ends the job (flags |= kInflateMapStop)
+	uint64_t map_bit0;        // map index of bit 0 of src[0]
+	const uint8_t *hist_ptr;  // optional: the 32 KiB in front of dst live here (last hist_len bytes valid) instead of at dst[-hist_len..]
 };
 struct InflateOut {
 	int32_t rc;             // job mode: NX completion code (0/3 ok, 13 target full, 66/67/68 data)
@@ -100,7 +108,7 @@ struct InflateOut {
 	uint32_t subc;          // source bits read but not processed (16-bit field: Table 5-3 bounds it by 2285)
 	uint32_t rembytecnt;
 	uint32_t dhtlen;        // valid bits in out_dht
-	uint32_t reserved[2];
+	uint32_t end_bit_lo, end_bit_hi;   // kInflateMapStop: map index of the boundary
 };
 
 struct CksumJob {
@@ -174,6 +182,30 @@ cudaError_t launch_deflate(const DeflateJob *jobs, DeflateOut *outs, uint32_t n_
 cudaError_t launch_dhtgen(const uint32_t *counts, uint32_t n, uint8_t *dht_out, uint32_t *dht_bits, cudaStream_t s);
 cudaError_t launch_gzip_candidates(const uint8_t *src, uint64_t len, uint64_t *cand, uint32_t max_cand, uint32_t *count, cudaStream_t s);
 cudaError_t launch_inflate(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s);
+// one stream decoded by many warps (inflate_par.cuh): block-start candidates, speculative decode of every candidate with
+// markers for the unknown window, chain + window resolution, the real decode of every chained piece
+struct SpecOut { uint64_t end_bit; uint32_t out_len; uint32_t status; uint32_t max_back; uint32_t pad_; };
+struct ChainMeta { uint64_t bit; uint64_t exp_end; uint32_t unit; uint32_t out_off; uint32_t exp_len; uint32_t last; };
+struct ParPlan {
+	InflateJob job;              // the descriptor as the caller built it (device pointers)
+	uint32_t *map;               // one bit per source bit: a dynamic block header that decodes to complete codes starts here
+	const uint64_t *cands;       // the set bits, ascending
+	uint32_t n_cand;
+	uint32_t pad_;
+	uint16_t *rings;             // per candidate: the last 32 Ki symbols of its speculative output, markers for what lies in front of it
+	SpecOut *spec;               // per candidate
+	InflateJob *cjobs;           // the chain: descriptors of the pieces, in stream order
+	InflateOut *couts;
+	ChainMeta *meta;
+	uint8_t *hists;              // per chain piece: the 32 KiB in front of it
+	uint32_t *n_chain;
+	InflateOut *head_out;        // piece 0 (from the descriptor's own start state to the first candidate boundary)
+	InflateOut *final_out;       // where the caller expects the result
+	InflateJob *retry_job;       // written by the last kernel: the descriptor again if the pieces disagreed, else a skip
+};
+cudaError_t launch_blockfind(const uint8_t *src, uint32_t src_len, uint64_t first_bit, uint32_t *map, uint64_t *surv, uint32_t surv_cap,
+			     uint64_t *cand, uint32_t cand_cap, uint32_t *counts, cudaStream_t s);
+cudaError_t launch_inflate_par(const ParPlan &plan, uint32_t *counter, cudaStream_t s);
 // checksum.cu
 cudaError_t checksum_init_tables();
 size_t checksum_range_bytes();

@@ -81,8 +81,8 @@ struct nxgpu_ctx {
 	uint32_t jobs_per_flag = 0;
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
 	uint64_t launches = 0;
-	DevBuf d_jobs, d_outs, d_tok, d_slots, d_ranges, d_parts, d_rs, d_seeds, d_cks, d_in, d_out, d_offsets, d_misc, d_dst_ptrs, d_dht, d_lz, d_ctr, d_flags, d_ijobs, d_iouts, d_cat, d_catdesc, d_chain;
-	PinBuf h_jobs, h_outs, h_misc, h_stage, h_ones, h_cat;
+	DevBuf d_jobs, d_outs, d_tok, d_slots, d_ranges, d_parts, d_rs, d_seeds, d_cks, d_in, d_out, d_offsets, d_misc, d_dst_ptrs, d_dht, d_lz, d_ctr, d_flags, d_ijobs, d_iouts, d_cat, d_catdesc, d_chain, d_par1, d_par2;
+	PinBuf h_jobs, h_outs, h_misc, h_stage, h_ones, h_cat, h_par;
 	KernelTimer timers[3];           // 0 deflate, 1 inflate, 2 checksum
 	bool timing = true;
 };
@@ -97,6 +97,11 @@ struct StreamEnq { size_t n = 0; uint64_t *d_off = nullptr; uint32_t *d_cks = nu
 int deflate_stream_enqueue(nxgpu_ctx *c, const void *src, uint64_t src_len, void *dst, uint64_t dst_cap,
 			   int level, int wrap, uint32_t chunk, int mem, StreamEnq *e);
 int deflate_stream_collect(nxgpu_ctx *c, const StreamEnq &e, void *dst, uint64_t dst_cap, int mem, uint64_t *chunk_offsets, nxgpu_stream_result *res);
+// one stream decoded by many warps (inflate_par.cuh): inflate_par_select() marks the descriptors of a launch that take the
+// parallel path (kWrapSkip in jobs[], the originals in `picked`), inflate_parallel() runs one of them on c->stream
+// behind the launch, result in *d_final
+void inflate_par_select(InflateJob *jobs, size_t n, std::vector<std::pair<size_t, InflateJob>> &picked);
+int inflate_parallel(nxgpu_ctx *c, const InflateJob &job, InflateOut *d_final);
 void timer_begin(nxgpu_ctx *c, int fam);
 void timer_end(nxgpu_ctx *c, int fam);
 // nxgpu_job.cu: NX job descriptors, one at a time or coalesced

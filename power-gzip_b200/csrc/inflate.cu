@@ -315,14 +315,17 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, u
 	const uint32_t wofs = J.hist_len;
 	if (kWin) {
 		const uint32_t h = J.hist_len < kWinBytes ? J.hist_len : kWinBytes;
+		const uint8_t *hp = J.hist_ptr ? J.hist_ptr + kWinBytes : J.dst;      // one past the last history byte
 		for (uint32_t i = lane; i < h; i += 32)
-			win[(wofs - h + i) & (kWinBytes - 1)] = J.dst[(int32_t)i - (int32_t)h];
+			win[(wofs - h + i) & (kWinBytes - 1)] = hp[(int32_t)i - (int32_t)h];
 		__syncwarp();
 	}
 	// dry run (kWrapDry): walk the Huffman stream and count, write nothing — finds where a member ends and how
 	// long its output is (nxgpu_gunzip_concat discovers the members of a concatenated file this way)
 	const bool dry = (J.wrap & kWrapDry) != 0;
-	uint32_t start = 0, wrap = J.wrap & ~kWrapDry;
+	uint32_t start = 0, wrap = J.wrap & 0xff;
+	const bool no_header = (J.wrap & kWrapNoHeader) != 0;
+	bool map_stop = false;           // a block ended where J.stop_map says another warp takes over
 	uint32_t tr_crc = 0, tr_isize = 0, flags = 0;
 	// job mode: set when the source ran out (or the final EOB was seen); lane 0 holds the details
 	bool suspended = false;
@@ -345,7 +348,9 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, u
 			else if (n >= 2 && (s[0] & 0x0f) == 8 && (((uint32_t)s[0] << 8 | s[1]) % 31) == 0) wrap = NXGPU_WRAP_ZLIB;
 			else wrap = NXGPU_WRAP_RAW;
 		}
-		if (wrap == NXGPU_WRAP_GZIP) {
+		if (no_header) {
+			start = 0;
+		} else if (wrap == NXGPU_WRAP_GZIP) {
 			if (n < 18 || s[0] != 0x1f || s[1] != 0x8b || s[2] != 8) rc = NXGPU_E_DATA;
 			else {
 				const uint32_t flg = s[3];
@@ -363,7 +368,7 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, u
 		}
 		if (!rc) {
 			br.seek(start);
-			if (job && J.start_bit)
+			if ((job || no_header) && J.start_bit)
 				br.drop(J.start_bit & 7);
 		}
 	}
@@ -372,6 +377,17 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, u
 	bool final_block = false;
 	bool block_ended = false;
 	while (!rc && !final_block && !suspended) {
+		if (J.stop_map && block_ended) {
+			uint64_t at = 0;
+			if (lane == 0)
+				at = J.map_bit0 + br.bits_used();
+			at = __shfl_sync(0xffffffffu, at, 0);
+			if ((J.stop_map[at >> 5] >> (at & 31)) & 1) {
+				map_stop = true;
+				self_stop = true;
+				break;
+			}
+		}
 		if (job && block_ended) {
 			// A block with BFINAL=0 just ended.  Manual Table 5-3, SFBT 1110: the engine suspends here by
 			// itself for the single-block function codes (inc_nx/nxu.h:813,815), and also when the source
@@ -790,6 +806,11 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, u
 			O.subc = o_subc;
 			O.rembytecnt = o_rem;
 			O.dhtlen = in_dyn ? dht_len : 0;
+			if (map_stop) {
+				const uint64_t at = J.map_bit0 + br.bits_used();
+				O.flags |= kInflateMapStop;
+				O.end_bit_lo = (uint32_t)at; O.end_bit_hi = (uint32_t)(at >> 32);
+			}
 		}
 		return;
 	}
@@ -797,7 +818,11 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, u
 	// ---- trailer (lane 0) ----
 	uint32_t in_used = 0;
 	if (lane == 0) {
-		if (!rc) {
+		if (!rc && map_stop) {
+			const uint64_t at = J.map_bit0 + br.bits_used();
+			flags |= kInflateMapStop;
+			O.end_bit_lo = (uint32_t)at; O.end_bit_hi = (uint32_t)(at >> 32);
+		} else if (!rc) {
 			flags |= 1;
 			uint32_t p = (uint32_t)((br.bits_used() + 7) >> 3);
 			const uint8_t *s = J.src;
@@ -843,6 +868,8 @@ inflate_kernel(const InflateJob *__restrict__ jobs, InflateOut *__restrict__ out
 		if (j >= n_jobs)
 			break;
 		const InflateJob J = jobs[j];
+		if (J.wrap & kWrapSkip)
+			continue;
 		inflate_one<false>(J, outs[j], T, nullptr);
 		__syncwarp();
 	}
@@ -864,6 +891,8 @@ inflate_solo_kernel(const InflateJob *__restrict__ jobs, InflateOut *__restrict_
 		if (j >= n_jobs)
 			break;
 		const InflateJob J = jobs[j];
+		if (J.wrap & kWrapSkip)
+			continue;
 		if ((J.wrap & kWrapDry) != 0)
 			inflate_one<false>(J, outs[j], T, nullptr);
 		else
@@ -871,6 +900,8 @@ inflate_solo_kernel(const InflateJob *__restrict__ jobs, InflateOut *__restrict_
 		__syncwarp();
 	}
 }
+
+#include "inflate_par.cuh"
 
 // every offset where a gzip member COULD start: 1f 8b 08 and a flag byte without reserved bits (RFC 1952 §2.3);
 // the list is unordered, false positives (the pattern inside compressed or stored data) are weeded out by decoding
@@ -937,6 +968,59 @@ static cudaError_t launch_inflate_solo(const InflateJob *jobs, InflateOut *outs,
 	const uint32_t grid = n_jobs < (uint32_t)(kNumSMs * 5) ? n_jobs : (uint32_t)(kNumSMs * 5);
 	inflate_solo_kernel<<<grid ? grid : 1, 32, smem, s>>>(jobs, outs, n_jobs, counter);
 	return cudaGetLastError();
+}
+
+cudaError_t launch_blockfind(const uint8_t *src, uint32_t src_len, uint64_t first_bit, uint32_t *map, uint64_t *surv, uint32_t surv_cap,
+			     uint64_t *cand, uint32_t cand_cap, uint32_t *counts, cudaStream_t s)
+{
+	cudaError_t e = cudaMemsetAsync(map, 0, ((size_t)src_len / 4 + 4) * 4, s);
+	if (e != cudaSuccess)
+		return e;
+	e = cudaMemsetAsync(counts, 0, 2 * sizeof(uint32_t), s);
+	if (e != cudaSuccess)
+		return e;
+	const uint32_t n_words = src_len / 4 + 2;
+	uint32_t grid = (n_words + 255) / 256;
+	if (grid > (uint32_t)kNumSMs * 8)
+		grid = kNumSMs * 8;
+	blockfind_filter_kernel<<<grid, 256, 0, s>>>(src, src_len, first_bit, surv, surv_cap, counts);
+	uint32_t g2 = (surv_cap + 127) / 128;
+	if (g2 > (uint32_t)kNumSMs * 8)
+		g2 = kNumSMs * 8;
+	blockfind_verify_kernel<<<g2 ? g2 : 1, 128, 0, s>>>(src, src_len, surv, surv_cap, map, cand, cand_cap, counts);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_inflate_par(const ParPlan &plan, uint32_t *counter, cudaStream_t s)
+{
+	static PerDeviceOnce once;
+	const size_t tables = (sizeof(WarpTables) + 15) & ~(size_t)15;
+	const size_t smem_spec = tables + kRingSyms * 2, smem_chain = tables + kWinBytes;
+	cudaError_t e = once.run([=] {
+		cudaError_t r = cudaFuncSetAttribute(inflate_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_spec);
+		if (r != cudaSuccess)
+			return r;
+		return cudaFuncSetAttribute(inflate_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain);
+	});
+	if (e != cudaSuccess)
+		return e;
+	e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
+	if (e != cudaSuccess)
+		return e;
+	inflate_spec_kernel<<<plan.n_cand + 1, 32, smem_spec, s>>>(plan);
+	inflate_link_kernel<<<1, 32, 0, s>>>(plan);
+	if (plan.n_cand) {
+		const uint32_t gw = plan.n_cand < (uint32_t)kNumSMs * 2 ? plan.n_cand : (uint32_t)kNumSMs * 2;
+		inflate_windows_kernel<<<gw, 1024, 0, s>>>(plan);
+		const uint32_t gc = plan.n_cand < (uint32_t)kNumSMs * 5 ? plan.n_cand : (uint32_t)kNumSMs * 5;
+		inflate_chain_kernel<<<gc, 32, smem_chain, s>>>(plan, counter);
+	}
+	inflate_finish_kernel<<<1, 32, 0, s>>>(plan);
+	e = cudaGetLastError();
+	if (e != cudaSuccess)
+		return e;
+	// the descriptor again, serially, should the pieces have disagreed (retry_job is a skip otherwise)
+	return launch_inflate_solo(plan.retry_job, plan.final_out, 1, counter, s);
 }
 
 cudaError_t launch_inflate(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s)

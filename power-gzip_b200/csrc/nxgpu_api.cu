@@ -154,9 +154,9 @@ void nxgpu_close(nxgpu_ctx *c)
 	cudaSetDevice(c->dev);
 	cudaStreamSynchronize(c->stream);
 	DevBuf *db[] = { &c->d_jobs, &c->d_outs, &c->d_tok, &c->d_slots, &c->d_ranges, &c->d_parts, &c->d_rs, &c->d_seeds,
-			 &c->d_cks, &c->d_in, &c->d_out, &c->d_offsets, &c->d_misc, &c->d_dst_ptrs, &c->d_dht, &c->d_lz, &c->d_ctr, &c->d_flags, &c->d_ijobs, &c->d_iouts, &c->d_cat, &c->d_catdesc, &c->d_chain };
+			 &c->d_cks, &c->d_in, &c->d_out, &c->d_offsets, &c->d_misc, &c->d_dst_ptrs, &c->d_dht, &c->d_lz, &c->d_ctr, &c->d_flags, &c->d_ijobs, &c->d_iouts, &c->d_cat, &c->d_catdesc, &c->d_chain, &c->d_par1, &c->d_par2 };
 	for (DevBuf *b : db) b->release();
-	PinBuf *pb[] = { &c->h_jobs, &c->h_outs, &c->h_misc, &c->h_stage, &c->h_ones, &c->h_cat };
+	PinBuf *pb[] = { &c->h_jobs, &c->h_outs, &c->h_misc, &c->h_stage, &c->h_ones, &c->h_cat, &c->h_par };
 	for (PinBuf *b : pb) b->release();
 	for (int f = 0; f < 3; f++)
 		for (cudaEvent_t e : c->timers[f].ev) cudaEventDestroy(e);
@@ -769,6 +769,96 @@ int nxgpu_dhtgen(nxgpu_ctx *c, const uint32_t *lhist, int num_lhist, const uint3
 
 /* ------------------------------- inflate ------------------------------- */
 
+} // extern "C"
+namespace nxgpu {
+// A descriptor takes the parallel path when it is long enough to hold several deflate blocks (zlib closes a block every
+// 16 Ki symbols, 20-60 KiB of compressed text) and the launch does not fill the GPU anyway.
+void inflate_par_select(InflateJob *jobs, size_t n, std::vector<std::pair<size_t, InflateJob>> &picked)
+{
+	picked.clear();
+	const char *e = getenv("NXGPU_INFLATE_PAR_MIN");          // bytes of source; 0 = never (developer / test switch)
+	const uint64_t par_min = e ? strtoull(e, nullptr, 0) : 256 * 1024;
+	if (par_min == 0 || n > 32)
+		return;
+	for (size_t i = 0; i < n; i++) {
+		const InflateJob &j = jobs[i];
+		if (j.src_len < par_min || j.single_block || (j.wrap & (kWrapDry | kWrapSkip | kWrapNoHeader)) || j.stop_map || j.hist_ptr)
+			continue;
+		picked.emplace_back(i, j);
+		jobs[i].wrap |= kWrapSkip;
+	}
+}
+
+int inflate_parallel(nxgpu_ctx *c, const InflateJob &job, InflateOut *d_final)
+{
+	int rc;
+	const uint32_t n = job.src_len;
+	const size_t map_bytes = align_up((size_t)n + 64, 256);
+	const uint32_t surv_cap = n / 32 + 1024;                  // the filter passes one bit offset in ~1200
+	const uint32_t cand_cap = surv_cap < 65536 ? surv_cap : 65536;
+	const size_t p1 = map_bytes + (size_t)surv_cap * 8 + (size_t)cand_cap * 8 + 256 + 2 * sizeof(InflateJob);
+	if ((rc = c->d_par1.reserve(p1))) return rc;
+	if ((rc = c->h_par.reserve((size_t)cand_cap * 8 + 256 + sizeof(InflateJob)))) return rc;
+	if ((rc = c->d_misc.reserve(64))) return rc;
+	uint8_t *b1 = static_cast<uint8_t *>(c->d_par1.p);
+	uint32_t *map = reinterpret_cast<uint32_t *>(b1);
+	uint64_t *surv = reinterpret_cast<uint64_t *>(b1 + map_bytes);
+	uint64_t *cand = surv + surv_cap;
+	uint32_t *counts = reinterpret_cast<uint32_t *>(cand + cand_cap);
+	InflateJob *d_job = reinterpret_cast<InflateJob *>(reinterpret_cast<uint8_t *>(counts) + 128);
+	uint8_t *hp = static_cast<uint8_t *>(c->h_par.p);
+	uint32_t *h_counts = reinterpret_cast<uint32_t *>(hp);
+	InflateJob *h_job = reinterpret_cast<InflateJob *>(hp + 128);
+	uint64_t *h_cand = reinterpret_cast<uint64_t *>(hp + 256 + sizeof(InflateJob) - sizeof(InflateJob) % 8 + 8);
+	*h_job = job;
+	timer_begin(c, 1);
+	NXGPU_CUDA_OK(cudaMemcpyAsync(d_job, h_job, sizeof(InflateJob), cudaMemcpyHostToDevice, c->stream));
+	const bool is_job = (job.wrap & 0xff) == kWrapJob;
+	NXGPU_CUDA_OK(launch_blockfind(job.src, n, is_job ? job.start_bit : 0, map, surv, surv_cap, cand, cand_cap, counts, c->stream));
+	NXGPU_CUDA_OK(cudaMemcpyAsync(h_counts, counts, 8, cudaMemcpyDeviceToHost, c->stream));
+	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	c->launches += 2;
+	const uint32_t n_cand = h_counts[1];
+	if (h_counts[0] > surv_cap || n_cand > cand_cap || n_cand == 0) {
+		// nothing to split at (one huge block, stored data) or more look-alikes than the lists hold: one warp
+		NXGPU_CUDA_OK(launch_inflate(d_job, d_final, 1, static_cast<uint32_t *>(c->d_misc.p), c->stream));
+		timer_end(c, 1);
+		c->launches++;
+		return 0;
+	}
+	NXGPU_CUDA_OK(cudaMemcpyAsync(h_cand, cand, (size_t)n_cand * 8, cudaMemcpyDeviceToHost, c->stream));
+	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	std::sort(h_cand, h_cand + n_cand);
+	NXGPU_CUDA_OK(cudaMemcpyAsync(cand, h_cand, (size_t)n_cand * 8, cudaMemcpyHostToDevice, c->stream));
+	const size_t nc = n_cand;
+	const size_t p2 = nc * 65536 + nc * 32768 + align_up(nc * sizeof(SpecOut), 256) + align_up(nc * sizeof(InflateJob), 256) +
+			  align_up(nc * sizeof(InflateOut), 256) + align_up(nc * sizeof(ChainMeta), 256) + 1024;
+	if ((rc = c->d_par2.reserve(p2))) return rc;
+	uint8_t *b2 = static_cast<uint8_t *>(c->d_par2.p);
+	ParPlan P;
+	memset(&P, 0, sizeof(P));
+	P.job = job;
+	P.map = map;
+	P.cands = cand;
+	P.n_cand = n_cand;
+	P.rings = reinterpret_cast<uint16_t *>(b2); b2 += nc * 65536;
+	P.hists = b2; b2 += nc * 32768;
+	P.spec = reinterpret_cast<SpecOut *>(b2); b2 += align_up(nc * sizeof(SpecOut), 256);
+	P.cjobs = reinterpret_cast<InflateJob *>(b2); b2 += align_up(nc * sizeof(InflateJob), 256);
+	P.couts = reinterpret_cast<InflateOut *>(b2); b2 += align_up(nc * sizeof(InflateOut), 256);
+	P.meta = reinterpret_cast<ChainMeta *>(b2); b2 += align_up(nc * sizeof(ChainMeta), 256);
+	P.n_chain = reinterpret_cast<uint32_t *>(b2);
+	P.head_out = reinterpret_cast<InflateOut *>(b2 + 64);
+	P.final_out = d_final;
+	P.retry_job = d_job + 1;
+	NXGPU_CUDA_OK(launch_inflate_par(P, static_cast<uint32_t *>(c->d_misc.p), c->stream));
+	timer_end(c, 1);
+	c->launches += 6;
+	return 0;
+}
+} // namespace nxgpu
+extern "C" {
+
 int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n, nxgpu_inflate_result *results, int mem)
 {
 	if (!c || (!items && n) || (!results && n)) return NXGPU_E_ARG;
@@ -847,6 +937,8 @@ int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n,
 	if ((rc = c->d_ranges.reserve(n * rb + (n + n_groups + 1) * 4))) return rc;
 	if ((rc = c->d_parts.reserve(n * pb))) return rc;
 	if ((rc = c->d_cks.reserve(n * 8 + 16))) return rc;
+	std::vector<std::pair<size_t, InflateJob>> par;
+	inflate_par_select(jh, n, par);
 	NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_jobs.p, jh, n * sizeof(InflateJob), cudaMemcpyHostToDevice, c->stream));
 	const InflateJob *dj = static_cast<const InflateJob *>(c->d_jobs.p);
 	InflateOut *dout = static_cast<InflateOut *>(c->d_outs.p);
@@ -859,6 +951,8 @@ int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n,
 		timer_begin(c, 1);
 		NXGPU_CUDA_OK(launch_inflate(dj + g0, dout + g0, (uint32_t)ng, static_cast<uint32_t *>(c->d_misc.p), c->stream));
 		timer_end(c, 1);
+		for (const auto &pj : par)            // (n <= 32: one group)
+			if ((rc = inflate_parallel(c, pj.second, dout + pj.first))) return rc;
 		// crc32 / adler32 of every output, lengths taken from the device results
 		uint32_t *d_rs = d_rs_all + g0 + g;
 		NXGPU_CUDA_OK(launch_ranges_from_inflate(dj + g0, dout + g0, (uint32_t)ng, d_rng + g0 * rb, d_rs, c->stream));
