@@ -303,17 +303,24 @@ checksum_combine_kernel(const Range *__restrict__ ranges, const Partial *__restr
 	}
 }
 
-// ranges straight from inflate results: one range per job
-__global__ void ranges_from_inflate_kernel(const InflateJob *jobs, const InflateOut *outs, uint32_t n, Range *ranges, uint32_t *rs)
+// ranges straight from inflate results: per_job ranges per job (1 for batches of small members; a few long outputs are
+// cut so that every SM takes a share — one 64 MiB output as a single range kept one CTA busy for 2 ms)
+__global__ void ranges_from_inflate_kernel(const InflateJob *jobs, const InflateOut *outs, uint32_t n, Range *ranges, uint32_t *rs, uint32_t per_job)
 {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t i = t / per_job, k = t % per_job;
 	if (i < n) {
+		const uint64_t len = outs[i].rc == 0 || outs[i].rc == NXGPU_E_BUF ? outs[i].out_len : 0;
+		uint64_t piece = (len + per_job - 1) / per_job;
+		piece = (piece + kTile - 1) / kTile * kTile;
+		const uint64_t from = piece * k < len ? piece * k : len;
+		const uint64_t to = from + piece < len ? from + piece : len;
 		Range R;
-		R.src = jobs[i].dst; R.len = outs[i].rc == 0 || outs[i].rc == NXGPU_E_BUF ? outs[i].out_len : 0; R.after = 0; R.job = i; R.pad_ = 0;
-		ranges[i] = R;
+		R.src = jobs[i].dst + from; R.len = to - from; R.after = len - to; R.job = i; R.pad_ = 0;
+		ranges[t] = R;
 	}
-	if (i <= n)
-		rs[i] = i;
+	if (k == 0 && i <= n)
+		rs[i] = i * per_job;
 }
 
 PerDeviceOnce g_tables_once;
@@ -425,9 +432,9 @@ cudaError_t launch_checksum_combine(const void *d_ranges, const void *d_parts, c
 	return cudaGetLastError();
 }
 
-cudaError_t launch_ranges_from_inflate(const InflateJob *jobs, const InflateOut *outs, uint32_t n, void *d_ranges, uint32_t *d_rs, cudaStream_t s)
+cudaError_t launch_ranges_from_inflate(const InflateJob *jobs, const InflateOut *outs, uint32_t n, void *d_ranges, uint32_t *d_rs, cudaStream_t s, uint32_t per_job)
 {
-	ranges_from_inflate_kernel<<<(n + 1 + 255) / 256, 256, 0, s>>>(jobs, outs, n, static_cast<Range *>(d_ranges), d_rs);
+	ranges_from_inflate_kernel<<<((n + 1) * per_job + 255) / 256, 256, 0, s>>>(jobs, outs, n, static_cast<Range *>(d_ranges), d_rs, per_job);
 	return cudaGetLastError();
 }
 

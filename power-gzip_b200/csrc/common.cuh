@@ -215,7 +215,7 @@ cudaError_t launch_checksum_ranges(const void *d_ranges, uint32_t n_ranges, void
 cudaError_t launch_checksum_combine(const void *d_ranges, const void *d_parts, const uint32_t *d_rs, uint32_t n_jobs,
 				    const uint32_t *d_crc_seed, const uint32_t *d_adler_seed,
 				    uint32_t *d_crc_out, uint32_t *d_adler_out, cudaStream_t s, uint32_t max_ranges_per_job = 1);
-cudaError_t launch_ranges_from_inflate(const InflateJob *jobs, const InflateOut *outs, uint32_t n, void *d_ranges, uint32_t *d_rs, cudaStream_t s);
+cudaError_t launch_ranges_from_inflate(const InflateJob *jobs, const InflateOut *outs, uint32_t n, void *d_ranges, uint32_t *d_rs, cudaStream_t s, uint32_t per_job = 1);
 uint32_t host_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2);
 // stitch.cu
 struct BitPiece { const uint8_t *src; uint64_t nbits; uint64_t dst_bit; };

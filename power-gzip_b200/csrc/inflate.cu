@@ -23,19 +23,30 @@ constexpr int kWarpsPerCta = 4;
 constexpr int kLitBits = 10, kDistBits = 9;
 constexpr uint32_t kInWords = 128;         // per-warp staging ring for the compressed input (512 B)
 constexpr uint32_t kReadAhead = 8;         // job mode: source bytes the engine has read behind the point where it stopped by itself
-constexpr uint32_t kInAhead = 64;          // the warp tops the ring up while fewer words than this lie ahead
+constexpr uint32_t kInAhead = 60;          // the warp tops the ring up (64 words) while fewer words than this lie ahead: a batch consumes at most
+                                           // 48 + 3, and the three words of the bit window in front of the read position stay in the ring
+                                           // (fast_walk re-reads them): 59 + 64 + 3 <= kInWords
 
 struct WarpTables {
-	uint32_t lit[1 << kLitBits];      // codelen | type<<4 | nextra<<6 | value<<10   (0 = slow path); type 2 literal (value = byte),
-	                                  // 3 length (value = base - 3), 1 end of block: bit 5 set = the fast loop handles it
-	uint32_t dist[1 << kDistBits];    // codelen | nextra<<4 | (base - 1)<<8
+	uint32_t lit[1 << kLitBits];      // ent_make(): bits consumed (code + extra) | codelen<<5 | type<<9 | value<<11   (0 = slow path); type 2
+	                                  // literal (value = byte), 3 length (value = base - 3), 1 end of block: bit 10 = the fast loop handles it
+	uint32_t dist[1 << kDistBits];    // bits consumed | codelen<<5 | (base - 1)<<11
 	uint16_t lit_sorted[288];
 	uint16_t dist_sorted[32];
 	uint16_t lit_count[16], dist_count[16];
 	uint8_t lens[320];
-	uint32_t q[32];                   // decoded symbols: literal, or tok_match(len, dist)
+	uint32_t q[32];                   // decoded symbols: literal, or tok_match(len, dist); from fast_walk: the bit window at the symbol
+	uint32_t q2[32];                  // fast_walk: the bit window at the symbol's distance code
 	uint32_t in[kInWords];            // compressed input, word w of the member at in[w % kInWords]
 };
+
+// table entry: the number of bits the symbol part consumes sits in the low five bits, where a funnel shift in wrap mode
+// reads it without an extraction
+__device__ __forceinline__ uint32_t ent_make(uint32_t tot, uint32_t cl, uint32_t type, uint32_t value) { return tot | (cl << 5) | (type << 9) | (value << 11); }
+__device__ __forceinline__ uint32_t ent_tot(uint32_t e) { return e & 31; }
+__device__ __forceinline__ uint32_t ent_cl(uint32_t e) { return (e >> 5) & 15; }
+__device__ __forceinline__ uint32_t ent_type(uint32_t e) { return (e >> 9) & 3; }
+__device__ __forceinline__ uint32_t ent_val(uint32_t e) { return e >> 11; }
 
 __constant__ uint16_t k_len_base[29] = { 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258 };
 __constant__ uint8_t k_len_extra[29] = { 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0 };
@@ -137,19 +148,6 @@ struct BitReader {
 	__device__ __forceinline__ uint32_t byte_pos() const { return (uint32_t)(bits_abs() >> 3) - skip; }
 };
 
-__device__ __forceinline__ uint32_t lds32(uint32_t saddr)
-{
-	uint32_t v;
-	// (no memory clobber: every producer of these words — table build, input staging, fill_single — is
-	// separated from the readers by __syncwarp() or a call, which order a volatile asm)
-	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
-	return v;
-}
-__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v)
-{
-	asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
-}
-
 // canonical decode, one bit at a time (codes longer than the primary table)
 __device__ int slow_decode(BitReader &br, const uint16_t *count, const uint16_t *sorted)
 {
@@ -231,13 +229,13 @@ __device__ bool build_table(const uint8_t *lens, int n, uint32_t *lut, int lut_b
 				const uint32_t code = __brev(nc + r) >> (32 - l);
 				uint32_t e;
 				if (is_dist) {
-					e = s < 30 ? ((uint32_t)l | ((uint32_t)k_dist_extra[s] << 4) | ((uint32_t)(k_dist_base[s] - 1) << 8)) : 0;
+					e = s < 30 ? ent_make(l + k_dist_extra[s], l, 0, k_dist_base[s] - 1) : 0;
 				} else if (s < 256) {
-					e = (uint32_t)l | (2u << 4) | ((uint32_t)s << 10);
+					e = ent_make(l, l, 2, s);
 				} else if (s == 256) {
-					e = (uint32_t)l | (1u << 4);
+					e = ent_make(l, l, 1, 0);
 				} else if (s < 286) {
-					e = (uint32_t)l | (3u << 4) | ((uint32_t)k_len_extra[s - 257] << 6) | ((uint32_t)(k_len_base[s - 257] - 3) << 10);
+					e = ent_make(l + k_len_extra[s - 257], l, 3, k_len_base[s - 257] - 3);
 				} else {
 					e = 0;
 				}
@@ -289,6 +287,288 @@ __device__ int parse_dyn_header(BitReader &br, uint8_t *lens, int &hlit, int &hd
 	return rc;
 }
 
+// Lane 0's table walk, written for latency.  A lone warp has nobody to hide behind: it issues an instruction every two
+// to three cycles at best, a dependent ALU result takes 4-5, a shared-memory load ~25 and a branch whose condition
+// comes out of a load stalls until it is there (ncu source page; the first version of this loop — three-word window,
+// funnel shift per look-up, seven branches, 80 instructions — spent 263 cycles per symbol).  So:
+//  * the bit window is 64 bits kept shifted left by two, so a table index is one AND away (byte offset of a 4-byte
+//    entry); it is topped up with a ring word, by predication, whenever 30 bits or fewer are left;
+//  * a table entry carries the bits its part of the symbol consumes (code + extra bits) in its low five bits, which is
+//    where a wrap-mode funnel shift reads its shift amount: AND -> LDS -> funnel shift is the whole chain per code;
+//  * every symbol does both look-ups, a literal consumes nothing at the second;
+//  * lane 0 neither forms tokens nor judges symbols: it queues the two 32-bit windows the look-ups were made from (q, q2)
+//    for every slot that is left, and the loop is counted — a symbol the tables do not resolve (long code, end of
+//    block, more than the 31 bits one top-up guarantees) is followed by bounded garbage.  The other lanes redo the
+//    look-ups, all slots at once, find the first such symbol, add up the bits in front of it and form the tokens
+//    (walk_batch).
+template <int kOff> __device__ __forceinline__ uint32_t lds_at(uint32_t saddr)
+{
+	uint32_t v;
+	asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(saddr), "n"(kOff));
+	return v;
+}
+template <int kOff> __device__ __forceinline__ void sts_at(uint32_t saddr, uint32_t v)
+{
+	asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(saddr), "n"(kOff), "r"(v) : "memory");
+}
+// tsa: 32-bit shared address of the warp's WarpTables (computed once by the caller: deriving it from a generic pointer
+// costs an S2UR and address arithmetic inside the loop)
+__device__ __forceinline__ void fast_walk(const BitReader &br, uint32_t tsa, uint32_t qn)
+{
+	constexpr int kLit = (int)offsetof(WarpTables, lit), kDist = (int)offsetof(WarpTables, dist), kQ = (int)offsetof(WarpTables, q),
+		      kQ2 = (int)offsetof(WarpTables, q2), kIn = (int)offsetof(WarpTables, in);
+	uint32_t cnt = 32 - br.bo;                                  // valid bits in the window
+	const uint32_t first = br.w0 >> br.bo;
+	uint32_t lo = first << 2, hi = first >> 30;
+	uint32_t next = br.w1;                                       // the ring word behind the window
+	uint32_t wo = ((br.wpos - 1) << 2) & (4 * kInWords - 4);     // byte offset in the ring of the word behind `next`
+	uint32_t qa = tsa + 4 * qn;
+	const uint32_t qe = tsa + 4 * 32;
+#pragma unroll 2
+	do {
+		{
+			const uint32_t sh = cnt + 2;
+			lo |= __funnelshift_lc(0, next, sh);                 // next << sh; nothing once sh > 31
+			const uint32_t add_hi = __funnelshift_lc(next, 0, sh); // next >> (32 - sh)
+			if (cnt <= 30) {
+				hi |= add_hi;
+				cnt += 32;
+				next = lds_at<kIn>(tsa + wo);
+				wo = (wo + 4) & (4 * kInWords - 4);
+			}
+		}
+		const uint32_t e = lds_at<kLit>(tsa + (lo & ((4u << kLitBits) - 4)));
+		const uint32_t lo1 = __funnelshift_r(lo, hi, e);            // shifts by e & 31
+		const uint32_t hi1 = __funnelshift_r(hi, 0, e);
+		const uint32_t d = lds_at<kDist>(tsa + (lo1 & ((4u << kDistBits) - 4)));
+		sts_at<kQ>(qa, lo);
+		sts_at<kQ2>(qa, lo1);
+		qa += 4;
+		const uint32_t dsel = (e & 0x600) == 0x600 ? d : 0u;          // a length: the distance code follows
+		lo = __funnelshift_r(lo1, hi1, dsel);
+		hi = __funnelshift_r(hi1, 0, dsel);
+		cnt -= (e & 31) + (dsel & 31);
+	} while (qa != qe);
+}
+
+// One batch of up to 32 symbols into T.q[0 .. qn), as tokens (all lanes call this; the read position lives in lane 0).
+// status: 0 = the queue is full or can be refilled, 1 = end of block, 2 = the source ran out inside a symbol (lane 0:
+// sym_at = where that symbol starts, in bits from the first source byte), 3 = a code the tables do not know.
+constexpr uint32_t kWalkEob = 1, kWalkSrcEnd = 2, kWalkBadCode = 3;
+__device__ __forceinline__ uint32_t walk_batch(BitReader &br, WarpTables &T, uint32_t tsa, uint32_t lane, uint32_t &status, uint64_t &sym_at)
+{
+	constexpr int kIn = (int)offsetof(WarpTables, in);
+	uint32_t qn = 0;
+	status = 0;
+	// overruns can only happen once the last words of the source are in the window: a batch consumes at most
+	// 32 x 48 bits = 48 words.  Until then the ring cannot run dry either: the staging left >= 60 words ahead.
+	const bool careful = __shfl_sync(0xffffffffu, (int)(br.wpos + 52 > br.end_word), 0) != 0;
+	for (;;) {
+		if (!careful) {
+			if (lane == 0)
+				fast_walk(br, tsa, qn);
+			__syncwarp();
+			// every lane judges the symbol in its slot
+			const uint32_t lo = T.q[lane], lo1 = T.q2[lane];
+			const uint32_t e = T.lit[(lo >> 2) & ((1u << kLitBits) - 1)];
+			const uint32_t d = T.dist[(lo1 >> 2) & ((1u << kDistBits) - 1)];
+			const bool is_len = ent_type(e) == 3;
+			const uint32_t used = ent_tot(e) + (is_len ? ent_tot(d) : 0u);
+			// resolved by the tables (literal / length with a short distance code) inside the bits a top-up guarantees
+			const bool ok = (e & 0x400) && !(is_len && d == 0) && used <= 31;
+			const uint32_t bad = __ballot_sync(0xffffffffu, lane >= qn && !ok);
+			const uint32_t fb = bad ? (uint32_t)__ffs(bad) - 1 : 32u;
+			const bool mine = lane >= qn && lane < fb;
+			uint32_t sum = mine ? used : 0u;
+			for (int o = 16; o; o >>= 1)
+				sum += __shfl_xor_sync(0xffffffffu, sum, o);
+			if (mine) {
+				const uint32_t cl = ent_cl(e), dl = ent_cl(d);
+				const uint32_t v = ent_val(e) + ((lo >> (cl + 2)) & ~(~0u << (ent_tot(e) - cl)));
+				const uint32_t dm1 = ent_val(d) + ((lo1 >> (dl + 2)) & ~(~0u << (ent_tot(d) - dl)));
+				T.q[lane] = is_len ? (0x80000000u | (v << 15) | dm1) : v;
+			}
+			if (lane == 0) {
+				// the symbols in front of the first unresolved one are consumed
+				const uint64_t at = br.bits_abs() + sum;
+				const uint32_t w = (uint32_t)(at >> 5);
+				br.w0 = lds_at<kIn>(tsa + ((w << 2) & (4 * kInWords - 4)));
+				br.w1 = lds_at<kIn>(tsa + (((w + 1) << 2) & (4 * kInWords - 4)));
+				br.w2 = lds_at<kIn>(tsa + (((w + 2) << 2) & (4 * kInWords - 4)));
+				br.wpos = w + 3;
+				br.bo = (uint32_t)at & 31;
+			}
+			qn = fb;
+			if (qn == 32)
+				break;
+		}
+		// the general code: one symbol (careful: as many as fit)
+		uint32_t st = 0;
+		if (lane == 0) {
+			do {
+				const uint32_t s_wpos = br.wpos, s_bo = br.bo;     // where this symbol starts
+				bool err = false;
+				uint32_t tokv = 0;
+				int kind = 0;                            // 0 literal, 1 match, 2 end of block
+				const uint32_t w = br.peek32();
+				const uint32_t e = T.lit[w & ((1u << kLitBits) - 1)];
+				const uint32_t cl = ent_cl(e);
+				uint32_t len = 0;
+				if (cl) {
+					const uint32_t tc = ent_type(e);
+					if (tc == 2) {
+						br.drop(cl);
+						tokv = ent_val(e);
+					} else if (tc == 3) {
+						kind = 1;
+						const uint32_t nextra = ent_tot(e) - cl;
+						len = ent_val(e) + 3 + ((w >> cl) & ((1u << nextra) - 1));
+						br.drop(cl + nextra);
+					} else {
+						kind = 2;
+						br.drop(cl);
+					}
+				} else {
+					const int sym = slow_decode(br, T.lit_count, T.lit_sorted);
+					if (sym < 0 || sym >= 286) { err = true; kind = 2; }
+					else if (sym < 256) { tokv = (uint32_t)sym; }
+					else if (sym == 256) { kind = 2; }
+					else { kind = 1; len = k_len_base[sym - 257] + br.get(k_len_extra[sym - 257]); }
+				}
+				if (kind == 1) {
+					const uint32_t wd = br.peek32();
+					const uint32_t d = T.dist[wd & ((1u << kDistBits) - 1)];
+					const uint32_t dl = ent_cl(d);
+					uint32_t dist = 1;
+					if (dl) {
+						const uint32_t dextra = ent_tot(d) - dl;
+						dist = ent_val(d) + 1 + ((wd >> dl) & ((1u << dextra) - 1));
+						br.drop(dl + dextra);
+					} else {
+						const int ds = slow_decode(br, T.dist_count, T.dist_sorted);
+						if (ds < 0 || ds >= 30) err = true;
+						else dist = k_dist_base[ds] + br.get(k_dist_extra[ds]);
+					}
+					tokv = tok_match(len, dist);
+				}
+				if (careful && br.overrun()) {
+					// the symbol needs bits the source does not have
+					sym_at = (uint64_t)(s_wpos - 3) * 32 + s_bo - br.skip * 8;
+					st = kWalkSrcEnd;
+					break;
+				}
+				if (err) { st = kWalkBadCode; break; }
+				if (kind == 2) { st = kWalkEob; break; }
+				T.q[qn++] = tokv;
+			} while (careful && qn < 32);
+		}
+		__syncwarp();
+		qn = __shfl_sync(0xffffffffu, qn, 0);
+		st = __shfl_sync(0xffffffffu, st, 0);
+		status = st;
+		if (st || careful || qn == 32)
+			break;
+	}
+	return qn;
+}
+
+// A batch of tokens into a ring of the last 32 Ki output symbols in shared memory: ring[(base + b) % 32 Ki] for the
+// batch's bytes b in [0, total).  All lanes call; t / is_m / mylen / incl: the lane's token, its length and the inclusive
+// prefix sum.  E: uint8_t (the real window) or uint16_t (speculation: bytes and window markers).
+//  * Lane `lane` moves bytes b0 + lane and b0 + 32 + lane of every round of 64: the owner of a byte comes out of one
+//    warp-wide OR and a population count.  (The first version searched it with five dependent shuffle steps per byte,
+//    600 cycles per round for a lone warp; a contiguous span per lane was tried too and lost to divergence: every lane
+//    sits in a different token, 4100 cycles per batch of ~500 bytes.)
+//  * A match that reads this batch's own output (distance < bytes produced up to and including it) is skipped by the
+//    spans and copied afterwards, in order, by the whole warp.
+//  * A match whose source lies so far back that it shares ring slots with this batch's output (distance > 32 Ki - total)
+//    is copied first, in order, before anything else is written.
+constexpr uint32_t kRingMask = 32768 - 1;
+// ring element i of a ring at shared address rsa (a generic pointer would cost an S2UR + address arithmetic per access)
+template <typename E> __device__ __forceinline__ uint32_t ring_ld(uint32_t rsa, uint32_t i)
+{
+	uint32_t v;
+	if (sizeof(E) == 1)
+		asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(rsa + (i & kRingMask)) : "memory");
+	else
+		asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(rsa + 2 * (i & kRingMask)) : "memory");
+	return v;
+}
+template <typename E> __device__ __forceinline__ void ring_st(uint32_t rsa, uint32_t i, uint32_t v)
+{
+	if (sizeof(E) == 1)
+		asm volatile("st.shared.u8 [%0], %1;" ::"r"(rsa + (i & kRingMask)), "r"(v) : "memory");
+	else
+		asm volatile("st.shared.u16 [%0], %1;" ::"r"(rsa + 2 * (i & kRingMask)), "r"(v) : "memory");
+}
+template <typename E>
+__device__ __forceinline__ void ring_fill(E *ring, uint32_t base, uint32_t lane, uint32_t t, bool is_m, uint32_t mylen, uint32_t incl, uint32_t total)
+{
+	const uint32_t rsa = (uint32_t)__cvta_generic_to_shared(ring);
+	const uint32_t my_at = base + incl - mylen;
+	uint32_t fm = __ballot_sync(0xffffffffu, is_m && tok_dist(t) > 32768 - total);
+	uint32_t mm = __ballot_sync(0xffffffffu, is_m && tok_dist(t) < incl);
+	const uint32_t skip = fm | mm;
+	while (fm) {
+		const int src_lane = __ffs(fm) - 1;
+		fm &= fm - 1;
+		const uint32_t mt = __shfl_sync(0xffffffffu, t, src_lane);
+		const uint32_t wp = __shfl_sync(0xffffffffu, my_at, src_lane);
+		const uint32_t len = tok_len(mt), dist = tok_dist(mt);
+		for (uint32_t k = lane; k < len; k += 32)
+			ring_st<E>(rsa, wp + k, ring_ld<E>(rsa, wp + k - dist));
+		__syncwarp();
+	}
+	{
+		// byte b of the batch belongs to the token whose start is the last one at or in front of b: per round of 32 bytes the
+		// tokens that start inside it are OR-reduced into a bit mask (one REDUX), and a population count gives every lane
+		// its owner.  Two rounds per iteration, all loads in front of all stores.
+		const uint32_t start = incl - mylen;                    // lanes behind the last token: start = total, owns nothing live
+		uint32_t before = 0;                                     // tokens that start in front of the round
+		const uint32_t upto = 0xffffffffu >> (31 - lane);        // bits 0 .. lane
+		for (uint32_t b0 = 0; b0 < total; b0 += 64) {
+			const uint32_t ra = start - b0, rb = start - b0 - 32;
+			const uint32_t ma = __reduce_or_sync(0xffffffffu, ra < 32 ? 1u << ra : 0u);
+			const uint32_t mb = __reduce_or_sync(0xffffffffu, rb < 32 ? 1u << rb : 0u);
+			const uint32_t oa = (before + __popc(ma & upto) - 1) & 31;
+			before += __popc(ma);
+			const uint32_t ob = (before + __popc(mb & upto) - 1) & 31;
+			before += __popc(mb);
+			const uint32_t ta = __shfl_sync(0xffffffffu, t, oa), tb = __shfl_sync(0xffffffffu, t, ob);
+			const uint32_t ba = b0 + lane, bb = ba + 32;
+			const bool ca = ba < total && tok_is_match(ta) && !((skip >> oa) & 1);
+			const bool cb = bb < total && tok_is_match(tb) && !((skip >> ob) & 1);
+			uint32_t xa = ta, xb = tb;
+			if (ca) xa = ring_ld<E>(rsa, base + ba - tok_dist(ta));
+			if (cb) xb = ring_ld<E>(rsa, base + bb - tok_dist(tb));
+			if (ba < total && (ca || !tok_is_match(ta))) ring_st<E>(rsa, base + ba, xa);
+			if (bb < total && (cb || !tok_is_match(tb))) ring_st<E>(rsa, base + bb, xb);
+		}
+	}
+	__syncwarp();
+	while (mm) {
+		const int src_lane = __ffs(mm) - 1;
+		mm &= mm - 1;
+		const uint32_t mt = __shfl_sync(0xffffffffu, t, src_lane);
+		const uint32_t wp = __shfl_sync(0xffffffffu, my_at, src_lane);
+		const uint32_t len = tok_len(mt), dist = tok_dist(mt);
+		if (dist >= len || dist >= 32) {
+			// each 32-byte pass reads bytes that earlier passes (or earlier symbols) wrote
+			for (uint32_t k = 0; k < len; k += 32) {
+				if (k + lane < len)
+					ring_st<E>(rsa, wp + k + lane, ring_ld<E>(rsa, wp + k + lane - dist));
+				if (dist < len)
+					__syncwarp();
+			}
+		} else {
+			// short period: the pattern in front of the match repeats
+			for (uint32_t k = lane; k < len; k += 32)
+				ring_st<E>(rsa, wp + k, ring_ld<E>(rsa, wp - dist + (k % dist)));
+		}
+		__syncwarp();
+	}
+}
+
 // kWin: the last 32 KiB of output are mirrored in a shared-memory ring (win), and every match source is read from
 // there instead of from global memory.  A warp that is alone with its stream (a lone uncompress() through
 // nxu_run_job, a handful of large members) otherwise pays an L2 round trip per materialise step and per
@@ -301,12 +581,8 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, u
 	const uint32_t lane = threadIdx.x & 31;
 	const bool job = J.wrap == kWrapJob;     // NX decompress-job semantics: stop at the source end and report where
 	const uint64_t total_bits = (uint64_t)J.src_len * 8;
-	// shared-window addresses of the tables, computed once (the fast decode loop addresses them directly)
-	uint32_t lit_sa = (uint32_t)__cvta_generic_to_shared(T.lit);
-	asm volatile("" : "+r"(lit_sa));
-	const uint32_t dist_sa = lit_sa + (uint32_t)offsetof(WarpTables, dist);
-	const uint32_t q_sa = lit_sa + (uint32_t)offsetof(WarpTables, q);
-	const uint32_t ring_sa = lit_sa + (uint32_t)offsetof(WarpTables, in);
+	uint32_t tsa = (uint32_t)__cvta_generic_to_shared(&T);      // fast_walk addresses the tables and queues through this
+	asm volatile("" : "+r"(tsa));
 	BitReader br;
 	br.setup(J.src, J.src_len, T.in);   // every lane knows the geometry; the read position lives in lane 0
 	int rc = 0;                      // uniform after each broadcast
@@ -529,125 +805,24 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, u
 					__syncwarp();
 				}
 			}
-			uint32_t qn = 0;
-			if (lane == 0) {
-				// overruns can only happen once the last words of the source are in the window: a batch
-				// consumes at most 32 x 48 bits = 48 words
-				const bool careful = br.wpos + 52 > br.end_word;
-				while (qn < 32) {
-					if (!careful) {
-						// ---- fast loop: symbols straight out of the tables, no bounds checks needed.  The
-						// ring cannot run dry here: the staging above left >= 64 words ahead and a batch
-						// consumes at most 48.  Anything else (long code, end of block) drops to the
-						// general code below for one symbol.
-						uint32_t w0 = br.w0, w1 = br.w1, w2 = br.w2, bo = br.bo, wpos = br.wpos;
-						do {
-							const uint32_t w = __funnelshift_r(w0, w1, bo);
-							const uint32_t e = lds32(lit_sa + ((w << 2) & ((4u << kLitBits) - 4)));
-							if (!(e & 0x20))
-								break;
-							uint32_t tokv = e >> 10;
-							uint32_t adv = e & 15;
-							if (e & 0x10) {
-								const uint32_t nextra = (e >> 6) & 15;
-								tokv += (w >> adv) & ~(~0u << nextra);
-								bo += adv + nextra;
-								if (bo >= 32) {
-									w0 = w1; w1 = w2; w2 = lds32(ring_sa + ((wpos << 2) & (4 * kInWords - 4))); wpos++;
-									bo -= 32;
-								}
-								const uint32_t wd = __funnelshift_r(w0, w1, bo);
-								const uint32_t d = lds32(dist_sa + ((wd << 2) & ((4u << kDistBits) - 4)));
-								const uint32_t dl = d & 15;
-								if (!dl)
-									break;       // long distance code: the general code redoes the whole symbol (br is unchanged)
-								const uint32_t dextra = (d >> 4) & 15;
-								const uint32_t dm1 = (d >> 8) + ((wd >> dl) & ~(~0u << dextra));
-								tokv = 0x80000000u | (tokv << 15) | dm1;
-								adv = dl + dextra;
-							}
-							bo += adv;
-							if (bo >= 32) {
-								w0 = w1; w1 = w2; w2 = lds32(ring_sa + ((wpos << 2) & (4 * kInWords - 4))); wpos++;
-								bo -= 32;
-							}
-							sts32(q_sa + 4 * qn, tokv);
-							qn++;
-							br.w0 = w0; br.w1 = w1; br.w2 = w2; br.bo = bo; br.wpos = wpos;
-						} while (qn < 32);
-						if (qn == 32)
-							break;
+			uint32_t wst;
+			uint64_t sym_at = 0;
+			const uint32_t qn = walk_batch(br, T, tsa, lane, wst, sym_at);
+			if (wst == kWalkSrcEnd) {
+				if (job) {
+					if (lane == 0) {
+						o_sfbt = (btype == 1 ? 0xau : 0xcu) | (final_block ? 1u : 0u);
+						o_subc = (uint32_t)(total_bits - sym_at);
 					}
-					const uint32_t s_wpos = br.wpos, s_bo = br.bo;     // where this symbol starts (careful mode)
-					int err = 0;
-					uint32_t tokv = 0;
-					int kind = 0;                            // 0 literal, 1 match, 2 end of block
-					const uint32_t w = br.peek32();
-					const uint32_t e = T.lit[w & ((1u << kLitBits) - 1)];
-					const uint32_t cl = e & 15;
-					uint32_t type, len = 0;
-					if (cl) {
-						const uint32_t tc = (e >> 4) & 3;
-						if (tc == 2) {
-							type = 0;
-							br.drop(cl);
-							tokv = e >> 10;
-						} else if (tc == 3) {
-							type = 1;
-							const uint32_t nextra = (e >> 6) & 15;
-							len = (e >> 10) + 3 + ((w >> cl) & ((1u << nextra) - 1));
-							br.drop(cl + nextra);
-						} else {
-							type = 2;
-							br.drop(cl);
-						}
-					} else {
-						const int sym = slow_decode(br, T.lit_count, T.lit_sorted);
-						if (sym < 0 || sym >= 286) { err = 66; type = 2; }
-						else if (sym < 256) { type = 0; tokv = (uint32_t)sym; }
-						else if (sym == 256) { type = 2; }
-						else { type = 1; len = k_len_base[sym - 257] + br.get(k_len_extra[sym - 257]); }
-					}
-					if (type == 2) {
-						kind = 2;
-					} else if (type == 1) {
-						const uint32_t wd = br.peek32();
-						const uint32_t d = T.dist[wd & ((1u << kDistBits) - 1)];
-						const uint32_t dl = d & 15;
-						uint32_t dist = 1;
-						if (dl) {
-							const uint32_t dextra = (d >> 4) & 15;
-							dist = (d >> 8) + 1 + ((wd >> dl) & ((1u << dextra) - 1));
-							br.drop(dl + dextra);
-						} else {
-							const int ds = slow_decode(br, T.dist_count, T.dist_sorted);
-							if (ds < 0 || ds >= 30) err = 66;
-							else dist = k_dist_base[ds] + br.get(k_dist_extra[ds]);
-						}
-						tokv = tok_match(len, dist); kind = 1;
-					}
-					if (careful && br.overrun()) {
-						// the symbol needs bits the source does not have
-						if (job) {
-							const uint64_t sym_at = (uint64_t)(s_wpos - 3) * 32 + s_bo - br.skip * 8;
-							o_sfbt = (btype == 1 ? 0xau : 0xcu) | (final_block ? 1u : 0u);
-							o_subc = (uint32_t)(total_bits - sym_at);
-							suspended = true;
-						} else {
-							rc = NXGPU_E_DATA;
-						}
-						break;
-					}
-					if (err) { rc = job ? err : NXGPU_E_DATA; break; }
-					if (kind == 2) { block_done = true; break; }
-					T.q[qn++] = tokv;
+					suspended = true;
+				} else {
+					rc = NXGPU_E_DATA;
 				}
+			} else if (wst == kWalkBadCode) {
+				rc = job ? 66 : NXGPU_E_DATA;
+			} else if (wst == kWalkEob) {
+				block_done = true;
 			}
-			__syncwarp();
-			qn = __shfl_sync(0xffffffffu, qn, 0);
-			rc = __shfl_sync(0xffffffffu, rc, 0);
-			block_done = __shfl_sync(0xffffffffu, (int)block_done, 0) != 0;
-			suspended = __shfl_sync(0xffffffffu, (int)suspended, 0) != 0;
 			if (rc)
 				break;
 			// ---- materialise the queue ----
@@ -675,6 +850,15 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, u
 			// the literals are materialised byte-parallel: output byte b belongs to the first symbol whose
 			// inclusive prefix exceeds b (binary search over the lanes' prefixes by shuffle), so all the
 			// loads of a batch are in flight together.  The rest (short distances) follow one by one.
+			if (kWin) {
+				// the batch goes into the window ring, then out to the target in one coalesced sweep
+				ring_fill<uint8_t>(win, wofs + out, lane, t, is_m, mylen, incl, total);
+				uint8_t *const dq = J.dst + out;
+				for (uint32_t i = lane; i < total; i += 32)
+					dq[i] = win[(wofs + out + i) & (kWinBytes - 1)];
+				out += total;
+				continue;
+			}
 			uint32_t mm = __ballot_sync(0xffffffffu, is_m && tok_dist(t) < incl);
 			uint8_t *const dq = J.dst + out;
 			for (uint32_t b0 = 0; b0 < total; b0 += 64) {
@@ -692,18 +876,10 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, u
 				uint32_t xa = ta, xb = tb;
 				const bool ca = ba < total && tok_is_match(ta) && tok_dist(ta) >= ia;
 				const bool cb = bb < total && tok_is_match(tb) && tok_dist(tb) >= ib;
-				if (kWin) {
-					const uint32_t wa = wofs + out + ba, wb = wofs + out + bb;
-					if (ca) xa = win[(wa - tok_dist(ta)) & (kWinBytes - 1)];
-					if (cb) xb = win[(wb - tok_dist(tb)) & (kWinBytes - 1)];
-					if (ba < total && (ca || !tok_is_match(ta))) { dq[ba] = (uint8_t)xa; win[wa & (kWinBytes - 1)] = (uint8_t)xa; }
-					if (bb < total && (cb || !tok_is_match(tb))) { dq[bb] = (uint8_t)xb; win[wb & (kWinBytes - 1)] = (uint8_t)xb; }
-				} else {
-					if (ca) xa = dq[(int32_t)ba - (int32_t)tok_dist(ta)];
-					if (cb) xb = dq[(int32_t)bb - (int32_t)tok_dist(tb)];
-					if (ba < total && (ca || !tok_is_match(ta))) dq[ba] = (uint8_t)xa;
-					if (bb < total && (cb || !tok_is_match(tb))) dq[bb] = (uint8_t)xb;
-				}
+				if (ca) xa = dq[(int32_t)ba - (int32_t)tok_dist(ta)];
+				if (cb) xb = dq[(int32_t)bb - (int32_t)tok_dist(tb)];
+				if (ba < total && (ca || !tok_is_match(ta))) dq[ba] = (uint8_t)xa;
+				if (bb < total && (cb || !tok_is_match(tb))) dq[bb] = (uint8_t)xb;
 			}
 			__syncwarp();
 			while (mm) {
@@ -713,27 +889,7 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, u
 				const uint32_t mo = __shfl_sync(0xffffffffu, my_out, src_lane);
 				const uint32_t len = tok_len(mt), dist = tok_dist(mt);
 				uint8_t *d = J.dst + mo;
-				if (kWin) {
-					volatile uint8_t *vw = win;
-					const uint32_t wp = wofs + mo;
-					if (dist >= len || dist >= 32) {
-						for (uint32_t k = 0; k < len; k += 32) {
-							if (k + lane < len) {
-								const uint8_t v = vw[(wp + k + lane - dist) & (kWinBytes - 1)];
-								d[k + lane] = v;
-								vw[(wp + k + lane) & (kWinBytes - 1)] = v;
-							}
-							if (dist < len)
-								__syncwarp();
-						}
-					} else {
-						for (uint32_t k = lane; k < len; k += 32) {
-							const uint8_t v = vw[(wp - dist + (k % dist)) & (kWinBytes - 1)];
-							d[k] = v;
-							vw[(wp + k) & (kWinBytes - 1)] = v;
-						}
-					}
-				} else if (dist >= len || dist >= 32) {
+				if (dist >= len || dist >= 32) {
 					// each 32-byte pass reads bytes that earlier passes (or earlier symbols) wrote
 					for (uint32_t k = 0; k < len; k += 32) {
 						if (k + lane < len)

@@ -44,6 +44,17 @@ blockfind_filter_kernel(const uint8_t *__restrict__ src, uint32_t src_len, uint6
 	const uint64_t end = (uint64_t)skip + src_len;
 	const uint64_t total_bits = (uint64_t)src_len * 8;
 	const uint32_t n_words = (uint32_t)((end + 3) >> 2);
+	// Kraft sum of four 3-bit code lengths at once (unit 1/128)
+	__shared__ uint16_t kraft4[4096];
+	for (uint32_t v = threadIdx.x; v < 4096; v += blockDim.x) {
+		uint32_t sum = 0;
+		for (int f = 0; f < 4; f++) {
+			const uint32_t l = (v >> (3 * f)) & 7;
+			if (l) sum += 128u >> l;
+		}
+		kraft4[v] = (uint16_t)sum;
+	}
+	__syncthreads();
 	for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += gridDim.x * blockDim.x) {
 		uint32_t w[4];
 #pragma unroll
@@ -61,14 +72,9 @@ blockfind_filter_kernel(const uint8_t *__restrict__ src, uint32_t src_len, uint6
 			const uint32_t o2 = o + 17;
 			const uint32_t k2 = o2 >> 5, s2 = o2 & 31;
 			const uint32_t c0 = __funnelshift_r(w[k2], w[k2 + 1], s2), c1 = __funnelshift_r(w[k2 + 1], w[k2 + 2], s2);
-			const uint64_t cl = (uint64_t)c0 | ((uint64_t)c1 << 32);
-			uint32_t sum = 0;
-#pragma unroll
-			for (int i = 0; i < 19; i++) {
-				const uint32_t l = (uint32_t)(cl >> (3 * i)) & 7;
-				if (i < (int)hclen && l)
-					sum += 128u >> l;
-			}
+			const uint64_t cl = ((uint64_t)c0 | ((uint64_t)c1 << 32)) & ((1ull << (3 * hclen)) - 1);
+			const uint32_t sum = kraft4[(uint32_t)cl & 4095] + kraft4[(uint32_t)(cl >> 12) & 4095] + kraft4[(uint32_t)(cl >> 24) & 4095] +
+					     kraft4[(uint32_t)(cl >> 36) & 4095] + kraft4[(uint32_t)(cl >> 48) & 4095];
 			if (sum != 128)
 				continue;
 			const int64_t p = (int64_t)wi * 32 + o - (int64_t)skip * 8;
@@ -182,11 +188,8 @@ __device__ void spec_one(const uint8_t *src, uint32_t src_len, uint64_t start_bi
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint64_t total_bits = (uint64_t)src_len * 8;
-	uint32_t lit_sa = (uint32_t)__cvta_generic_to_shared(T.lit);
-	asm volatile("" : "+r"(lit_sa));
-	const uint32_t dist_sa = lit_sa + (uint32_t)offsetof(WarpTables, dist);
-	const uint32_t q_sa = lit_sa + (uint32_t)offsetof(WarpTables, q);
-	const uint32_t ring_sa = lit_sa + (uint32_t)offsetof(WarpTables, in);
+	uint32_t tsa = (uint32_t)__cvta_generic_to_shared(&T);
+	asm volatile("" : "+r"(tsa));
 	BitReader br;
 	br.setup(src, src_len, T.in);
 	if (lane == 0) {
@@ -202,7 +205,7 @@ __device__ void spec_one(const uint8_t *src, uint32_t src_len, uint64_t start_bi
 	__syncwarp();
 	uint32_t out = 0, max_back = 0, status = kSpecError;
 #ifdef NXGPU_PAR_PROFILE
-	long long t_walk = 0, t_mat = 0, t_seq = 0, n_batches = 0, n_seq = 0; const long long t_begin = clock64();
+	long long t_walk = 0, t_mat = 0, t_seq = 0, n_batches = 0, n_seq = 0, t_fast = 0, n_fast = 0, n_calls = 0; const long long t_begin = clock64();
 #endif
 	for (;;) {
 		// ---- block header (lane 0) ----
@@ -270,107 +273,15 @@ __device__ void spec_one(const uint8_t *src, uint32_t src_len, uint64_t start_bi
 						__syncwarp();
 					}
 				}
-				uint32_t qn = 0;
 #ifdef NXGPU_PAR_PROFILE
 				const long long t0 = clock64();
 #endif
-				if (lane == 0) {
-					const bool careful = br.wpos + 52 > br.end_word;
-					while (qn < 32) {
-						if (!careful) {
-							// the same table walk as inflate_one's fast loop
-							uint32_t w0 = br.w0, w1 = br.w1, w2 = br.w2, bo = br.bo, wpos = br.wpos;
-							do {
-								const uint32_t w = __funnelshift_r(w0, w1, bo);
-								const uint32_t e = lds32(lit_sa + ((w << 2) & ((4u << kLitBits) - 4)));
-								if (!(e & 0x20))
-									break;
-								uint32_t tokv = e >> 10;
-								uint32_t adv = e & 15;
-								if (e & 0x10) {
-									const uint32_t nextra = (e >> 6) & 15;
-									tokv += (w >> adv) & ~(~0u << nextra);
-									bo += adv + nextra;
-									if (bo >= 32) {
-										w0 = w1; w1 = w2; w2 = lds32(ring_sa + ((wpos << 2) & (4 * kInWords - 4))); wpos++;
-										bo -= 32;
-									}
-									const uint32_t wd = __funnelshift_r(w0, w1, bo);
-									const uint32_t d = lds32(dist_sa + ((wd << 2) & ((4u << kDistBits) - 4)));
-									const uint32_t dl = d & 15;
-									if (!dl)
-										break;
-									const uint32_t dextra = (d >> 4) & 15;
-									const uint32_t dm1 = (d >> 8) + ((wd >> dl) & ~(~0u << dextra));
-									tokv = 0x80000000u | (tokv << 15) | dm1;
-									adv = dl + dextra;
-								}
-								bo += adv;
-								if (bo >= 32) {
-									w0 = w1; w1 = w2; w2 = lds32(ring_sa + ((wpos << 2) & (4 * kInWords - 4))); wpos++;
-									bo -= 32;
-								}
-								sts32(q_sa + 4 * qn, tokv);
-								qn++;
-								br.w0 = w0; br.w1 = w1; br.w2 = w2; br.bo = bo; br.wpos = wpos;
-							} while (qn < 32);
-							if (qn == 32)
-								break;
-						}
-						bool err = false;
-						uint32_t tokv = 0;
-						int kind = 0;                            // 0 literal, 1 match, 2 end of block
-						const uint32_t w = br.peek32();
-						const uint32_t e = T.lit[w & ((1u << kLitBits) - 1)];
-						const uint32_t cl = e & 15;
-						uint32_t len = 0;
-						if (cl) {
-							const uint32_t tc = (e >> 4) & 3;
-							if (tc == 2) {
-								br.drop(cl);
-								tokv = e >> 10;
-							} else if (tc == 3) {
-								kind = 1;
-								const uint32_t nextra = (e >> 6) & 15;
-								len = (e >> 10) + 3 + ((w >> cl) & ((1u << nextra) - 1));
-								br.drop(cl + nextra);
-							} else {
-								kind = 2;
-								br.drop(cl);
-							}
-						} else {
-							const int sym = slow_decode(br, T.lit_count, T.lit_sorted);
-							if (sym < 0 || sym >= 286) { err = true; kind = 2; }
-							else if (sym < 256) { tokv = (uint32_t)sym; }
-							else if (sym == 256) { kind = 2; }
-							else { kind = 1; len = k_len_base[sym - 257] + br.get(k_len_extra[sym - 257]); }
-						}
-						if (kind == 1) {
-							const uint32_t wd = br.peek32();
-							const uint32_t d = T.dist[wd & ((1u << kDistBits) - 1)];
-							const uint32_t dl = d & 15;
-							uint32_t dist = 1;
-							if (dl) {
-								const uint32_t dextra = (d >> 4) & 15;
-								dist = (d >> 8) + 1 + ((wd >> dl) & ((1u << dextra) - 1));
-								br.drop(dl + dextra);
-							} else {
-								const int ds = slow_decode(br, T.dist_count, T.dist_sorted);
-								if (ds < 0 || ds >= 30) err = true;
-								else dist = k_dist_base[ds] + br.get(k_dist_extra[ds]);
-							}
-							tokv = tok_match(len, dist);
-						}
-						if (careful && br.overrun()) { stop = kSpecSrcEnd; break; }
-						if (err) { stop = kSpecError; break; }
-						if (kind == 2) { block_done = true; break; }
-						T.q[qn++] = tokv;
-					}
-				}
-				__syncwarp();
-				qn = __shfl_sync(0xffffffffu, qn, 0);
-				stop = __shfl_sync(0xffffffffu, stop, 0);
-				block_done = __shfl_sync(0xffffffffu, (int)block_done, 0) != 0;
+				uint32_t wst;
+				uint64_t sym_at = 0;
+				const uint32_t qn = walk_batch(br, T, tsa, lane, wst, sym_at);
+				if (wst == kWalkSrcEnd) stop = kSpecSrcEnd;
+				else if (wst == kWalkBadCode) stop = kSpecError;
+				else if (wst == kWalkEob) block_done = true;
 				if (stop)
 					break;
 #ifdef NXGPU_PAR_PROFILE
@@ -391,53 +302,10 @@ __device__ void spec_one(const uint8_t *src, uint32_t src_len, uint64_t start_bi
 				if (total > out_cap - out) { stop = kSpecTooLong; break; }
 				if (is_m && tok_dist(t) > my_out)
 					max_back = max(max_back, tok_dist(t) - my_out);
-				uint32_t mm = __ballot_sync(0xffffffffu, is_m && tok_dist(t) < incl);
-				for (uint32_t b0 = 0; b0 < total; b0 += 64) {
-					const uint32_t ba = b0 + lane, bb = ba + 32;
-					uint32_t la = 0, lb = 0;
-#pragma unroll
-					for (int s = 16; s; s >>= 1) {
-						const uint32_t va = __shfl_sync(0xffffffffu, incl, la + s - 1);
-						const uint32_t vb = __shfl_sync(0xffffffffu, incl, lb + s - 1);
-						if (va <= ba) la += s;
-						if (vb <= bb) lb += s;
-					}
-					const uint32_t ta = __shfl_sync(0xffffffffu, t, la), ia = __shfl_sync(0xffffffffu, incl, la);
-					const uint32_t tb = __shfl_sync(0xffffffffu, t, lb), ib = __shfl_sync(0xffffffffu, incl, lb);
-					uint32_t xa = ta, xb = tb;
-					const bool ca = ba < total && tok_is_match(ta) && tok_dist(ta) >= ia;
-					const bool cb = bb < total && tok_is_match(tb) && tok_dist(tb) >= ib;
-					const uint32_t wa = out + ba, wb = out + bb;
-					if (ca) xa = win[(wa - tok_dist(ta)) & (kRingSyms - 1)];
-					if (cb) xb = win[(wb - tok_dist(tb)) & (kRingSyms - 1)];
-					if (ba < total && (ca || !tok_is_match(ta))) win[wa & (kRingSyms - 1)] = (uint16_t)xa;
-					if (bb < total && (cb || !tok_is_match(tb))) win[wb & (kRingSyms - 1)] = (uint16_t)xb;
-				}
-				__syncwarp();
 #ifdef NXGPU_PAR_PROFILE
 				const long long t2 = clock64();
-				n_seq += __popc(mm);
 #endif
-				while (mm) {
-					const int src_lane = __ffs(mm) - 1;
-					mm &= mm - 1;
-					const uint32_t mt = __shfl_sync(0xffffffffu, t, src_lane);
-					const uint32_t wp = __shfl_sync(0xffffffffu, my_out, src_lane);
-					const uint32_t len = tok_len(mt), dist = tok_dist(mt);
-					volatile uint16_t *vw = win;
-					if (dist >= len || dist >= 32) {
-						for (uint32_t k = 0; k < len; k += 32) {
-							if (k + lane < len)
-								vw[(wp + k + lane) & (kRingSyms - 1)] = vw[(wp + k + lane - dist) & (kRingSyms - 1)];
-							if (dist < len)
-								__syncwarp();
-						}
-					} else {
-						for (uint32_t k = lane; k < len; k += 32)
-							vw[(wp + k) & (kRingSyms - 1)] = vw[(wp - dist + (k % dist)) & (kRingSyms - 1)];
-					}
-					__syncwarp();
-				}
+				ring_fill<uint16_t>(win, out, lane, t, is_m, mylen, incl, total);
 				out += total;
 #ifdef NXGPU_PAR_PROFILE
 				{ const long long t3 = clock64(); t_walk += t1 - t0; t_mat += t2 - t1; t_seq += t3 - t2; n_batches++; }
@@ -464,8 +332,8 @@ __device__ void spec_one(const uint8_t *src, uint32_t src_len, uint64_t start_bi
 		O.pad_ = 0;
 #ifdef NXGPU_PAR_PROFILE
 		if (status == kSpecLinked && (start_bit >> 3) % 7 == 0)
-			printf("spec unit @%llu: out %u, %lld batches, total %lld cyc, walk %lld, par-mat %lld, seq-mat %lld (%lld matches)\n",
-			       (unsigned long long)start_bit, out, n_batches, clock64() - t_begin, t_walk, t_mat, t_seq, n_seq);
+			printf("spec unit @%llu: out %u, %lld batches, total %lld cyc, walk %lld (%lld %lld %lld), par-mat %lld, seq-mat %lld (%lld matches)\n",
+			       (unsigned long long)start_bit, out, n_batches, clock64() - t_begin, t_walk, t_fast, n_fast, n_calls, t_mat, t_seq, n_seq);
 #endif
 	}
 	if (status == kSpecLinked) {
@@ -506,16 +374,20 @@ __global__ void inflate_link_kernel(const ParPlan P)
 	if (H.rc == 0 && (H.flags & kInflateMapStop)) {
 		uint64_t e = (uint64_t)H.end_bit_lo | ((uint64_t)H.end_bit_hi << 32);
 		uint64_t off = H.out_len;
+		uint32_t idx = 0;
 		const uint32_t wrap = (P.job.wrap & 0xff) == kWrapJob ? kWrapJob : ((H.flags >> 8) & 0xff) | kWrapNoHeader;
 		while (n < P.n_cand) {
-			// the candidate that starts at bit e
-			uint32_t lo = 0, hi = P.n_cand;
+			// the candidate that starts at bit e: the chain only moves forward, gallop from the last hit
+			uint32_t lo = idx, hi = idx, step = 1;
+			while (hi < P.n_cand && P.cands[hi] < e) { lo = hi + 1; hi += step; step *= 2; }
+			if (hi > P.n_cand) hi = P.n_cand;
 			while (lo < hi) {
 				const uint32_t mid = (lo + hi) >> 1;
 				if (P.cands[mid] < e) lo = mid + 1; else hi = mid;
 			}
 			if (lo >= P.n_cand || P.cands[lo] != e)
 				break;                              // (cannot happen: the map and the list hold the same bits)
+			idx = lo + 1;
 			const SpecOut &S = P.spec[lo];
 			const uint64_t have = (uint64_t)P.job.hist_len + off;      // bytes in front of the piece
 			const bool last = S.status != kSpecLinked || S.max_back > have || off + S.out_len > P.job.dst_cap;
@@ -606,9 +478,19 @@ inflate_chain_kernel(const ParPlan P, uint32_t *next_job)
 // ---- 6. one result for the caller ----
 __global__ void inflate_finish_kernel(const ParPlan P)
 {
-	if (threadIdx.x != 0 || blockIdx.x != 0)
-		return;
+	const uint32_t lane = threadIdx.x;          // one warp
 	const uint32_t n = *P.n_chain;
+	bool good = true;
+	for (uint32_t k = lane; k + 1 < n; k += 32) {
+		const InflateOut &o = P.couts[k];
+		const ChainMeta &M = P.meta[k];
+		const uint64_t end = (uint64_t)o.end_bit_lo | ((uint64_t)o.end_bit_hi << 32);
+		if (o.rc != 0 || !(o.flags & kInflateMapStop) || o.out_len != M.exp_len || end != M.exp_end)
+			good = false;
+	}
+	good = __all_sync(0xffffffffu, good);
+	if (lane != 0)
+		return;
 	InflateJob R = P.job;
 	R.wrap |= kWrapSkip;
 	if (n == 0) {
@@ -622,14 +504,6 @@ __global__ void inflate_finish_kernel(const ParPlan P)
 		*P.retry_job = R;
 		return;
 	}
-	bool good = true;
-	for (uint32_t k = 0; k + 1 < n; k++) {
-		const InflateOut &o = P.couts[k];
-		const ChainMeta &M = P.meta[k];
-		const uint64_t end = (uint64_t)o.end_bit_lo | ((uint64_t)o.end_bit_hi << 32);
-		if (o.rc != 0 || !(o.flags & kInflateMapStop) || o.out_len != M.exp_len || end != M.exp_end)
-			good = false;
-	}
 	const ChainMeta &L = P.meta[n - 1];
 	InflateOut O = P.couts[n - 1];
 	if (O.flags & kInflateMapStop)
@@ -642,7 +516,6 @@ __global__ void inflate_finish_kernel(const ParPlan P)
 		const bool job = (P.job.wrap & 0xff) == kWrapJob;
 		if (job || (O.rc == 0 && (O.flags & 1)))
 			O.in_used += (uint32_t)(L.bit >> 3);
-		O.flags &= ~(kWrapNoHeader << 8);
 	}
 	*P.final_out = O;
 	*P.retry_job = R;

@@ -868,6 +868,7 @@ int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n,
 	int rc;
 	if ((rc = c->h_jobs.reserve(n * sizeof(InflateJob)))) return rc;
 	InflateJob *jh = static_cast<InflateJob *>(c->h_jobs.p);
+	memset(jh, 0, n * sizeof(InflateJob));
 	bool dst_contig = true;
 	if (mem == NXGPU_MEM_HOST) {
 		uint64_t in_total = 0, out_total = 0;
@@ -934,8 +935,13 @@ int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n,
 	// (a group is at least one full wave of warps, so the kernel loses nothing)
 	const size_t wave = 4 * 7 * (size_t)kNumSMs;
 	const size_t n_groups = (mem == NXGPU_MEM_HOST && dst_contig && n >= 2 * wave) ? std::min<size_t>(4, n / wave) : 1;
-	if ((rc = c->d_ranges.reserve(n * rb + (n + n_groups + 1) * 4))) return rc;
-	if ((rc = c->d_parts.reserve(n * pb))) return rc;
+	// a few long outputs: every SM takes a share of each checksum
+	uint32_t K = 1;
+	if (n <= 32)
+		for (size_t i = 0; i < n; i++)
+			if (items[i].dst_cap >= (4u << 20)) K = kNumSMs;
+	if ((rc = c->d_ranges.reserve(n * K * rb + (n + n_groups + 1) * 4))) return rc;
+	if ((rc = c->d_parts.reserve(n * K * pb))) return rc;
 	if ((rc = c->d_cks.reserve(n * 8 + 16))) return rc;
 	std::vector<std::pair<size_t, InflateJob>> par;
 	inflate_par_select(jh, n, par);
@@ -944,7 +950,7 @@ int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n,
 	InflateOut *dout = static_cast<InflateOut *>(c->d_outs.p);
 	uint8_t *d_rng = static_cast<uint8_t *>(c->d_ranges.p);
 	uint8_t *d_prt = static_cast<uint8_t *>(c->d_parts.p);
-	uint32_t *d_rs_all = reinterpret_cast<uint32_t *>(d_rng + n * rb);
+	uint32_t *d_rs_all = reinterpret_cast<uint32_t *>(d_rng + n * K * rb);
 	uint32_t *d_crc = static_cast<uint32_t *>(c->d_cks.p), *d_adler = d_crc + n;
 	for (size_t g = 0; g < n_groups; g++) {
 		const size_t g0 = g * n / n_groups, g1 = (g + 1) * n / n_groups, ng = g1 - g0;
@@ -955,11 +961,11 @@ int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n,
 			if ((rc = inflate_parallel(c, pj.second, dout + pj.first))) return rc;
 		// crc32 / adler32 of every output, lengths taken from the device results
 		uint32_t *d_rs = d_rs_all + g0 + g;
-		NXGPU_CUDA_OK(launch_ranges_from_inflate(dj + g0, dout + g0, (uint32_t)ng, d_rng + g0 * rb, d_rs, c->stream));
+		NXGPU_CUDA_OK(launch_ranges_from_inflate(dj + g0, dout + g0, (uint32_t)ng, d_rng + g0 * K * rb, d_rs, c->stream, K));
 		timer_begin(c, 2);
-		NXGPU_CUDA_OK(launch_checksum_ranges(d_rng + g0 * rb, (uint32_t)ng, d_prt + g0 * pb, 3, c->stream));
+		NXGPU_CUDA_OK(launch_checksum_ranges(d_rng + g0 * K * rb, (uint32_t)(ng * K), d_prt + g0 * K * pb, 3, c->stream));
 		timer_end(c, 2);
-		NXGPU_CUDA_OK(launch_checksum_combine(d_rng + g0 * rb, d_prt + g0 * pb, d_rs, (uint32_t)ng, nullptr, nullptr, d_crc + g0, d_adler + g0, c->stream));
+		NXGPU_CUDA_OK(launch_checksum_combine(d_rng + g0 * K * rb, d_prt + g0 * K * pb, d_rs, (uint32_t)ng, nullptr, nullptr, d_crc + g0, d_adler + g0, c->stream, K));
 		c->launches += 2;
 		if (mem == NXGPU_MEM_HOST && dst_contig) {
 			uint8_t *h0 = static_cast<uint8_t *>(items[g0].dst);
