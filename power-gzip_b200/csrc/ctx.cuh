@@ -98,10 +98,10 @@ int deflate_stream_enqueue(nxgpu_ctx *c, const void *src, uint64_t src_len, void
 			   int level, int wrap, uint32_t chunk, int mem, StreamEnq *e);
 int deflate_stream_collect(nxgpu_ctx *c, const StreamEnq &e, void *dst, uint64_t dst_cap, int mem, uint64_t *chunk_offsets, nxgpu_stream_result *res);
 // one stream decoded by many warps (inflate_par.cuh): inflate_par_select() marks the descriptors of a launch that take the
-// parallel path (kWrapSkip in jobs[], the originals in `picked`), inflate_parallel() runs one of them on c->stream
-// behind the launch, result in *d_final
+// parallel path (kWrapSkip in jobs[], the originals in `picked`), inflate_parallel() runs them on c->stream behind that
+// launch, results in the launch's own result slots
 void inflate_par_select(InflateJob *jobs, size_t n, std::vector<std::pair<size_t, InflateJob>> &picked);
-int inflate_parallel(nxgpu_ctx *c, const InflateJob &job, InflateOut *d_final);
+int inflate_parallel(nxgpu_ctx *c, const std::vector<std::pair<size_t, InflateJob>> &picked, InflateOut *d_outs);
 void timer_begin(nxgpu_ctx *c, int fam);
 void timer_end(nxgpu_ctx *c, int fam);
 // nxgpu_job.cu: NX job descriptors, one at a time or coalesced

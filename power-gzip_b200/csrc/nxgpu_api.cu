@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <string>
 #include <algorithm>
 #include <vector>
@@ -789,8 +790,10 @@ void inflate_par_select(InflateJob *jobs, size_t n, std::vector<std::pair<size_t
 	}
 }
 
-int inflate_parallel(nxgpu_ctx *c, const InflateJob &job, InflateOut *d_final)
+// *serial = true: the stream has nothing to split at, nothing was launched, the caller runs it on one warp
+static int inflate_parallel_one(nxgpu_ctx *c, const InflateJob &job, InflateOut *d_final, bool *serial)
 {
+	*serial = false;
 	int rc;
 	const uint32_t n = job.src_len;
 	const size_t map_bytes = align_up((size_t)n + 64, 256);
@@ -819,11 +822,13 @@ int inflate_parallel(nxgpu_ctx *c, const InflateJob &job, InflateOut *d_final)
 	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
 	c->launches += 2;
 	const uint32_t n_cand = h_counts[1];
+	static const bool trace = getenv("NXGPU_TRACE") != nullptr;
+	if (trace)
+		fprintf(stderr, "nxgpu inflate: %u source bytes, %u of %u bit offsets pass the header filter, %u block-start candidates\n", n, h_counts[0], n * 8, n_cand);
 	if (h_counts[0] > surv_cap || n_cand > cand_cap || n_cand == 0) {
 		// nothing to split at (one huge block, stored data) or more look-alikes than the lists hold: one warp
-		NXGPU_CUDA_OK(launch_inflate(d_job, d_final, 1, static_cast<uint32_t *>(c->d_misc.p), c->stream));
 		timer_end(c, 1);
-		c->launches++;
+		*serial = true;
 		return 0;
 	}
 	NXGPU_CUDA_OK(cudaMemcpyAsync(h_cand, cand, (size_t)n_cand * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -854,6 +859,39 @@ int inflate_parallel(nxgpu_ctx *c, const InflateJob &job, InflateOut *d_final)
 	NXGPU_CUDA_OK(launch_inflate_par(P, static_cast<uint32_t *>(c->d_misc.p), c->stream));
 	timer_end(c, 1);
 	c->launches += 6;
+	return 0;
+}
+
+// the descriptors inflate_par_select() picked, on c->stream behind the launch they were taken out of (d_outs: that launch's
+// results).  Streams that turn out to have nothing to split at run together in one more launch, a warp each.
+int inflate_parallel(nxgpu_ctx *c, const std::vector<std::pair<size_t, InflateJob>> &picked, InflateOut *d_outs)
+{
+	std::vector<InflateJob> serial;
+	std::vector<size_t> serial_at;
+	for (const auto &pj : picked) {
+		bool s = false;
+		const int rc = inflate_parallel_one(c, pj.second, d_outs + pj.first, &s);
+		if (rc)
+			return rc;
+		if (s) { serial.push_back(pj.second); serial_at.push_back(pj.first); }
+	}
+	if (serial.empty())
+		return 0;
+	// a job array as long as the original launch's, everything skipped but these (results land in their own slots)
+	const size_t n = serial_at.back() + 1;
+	int rc;
+	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));          // h_par / d_par1 are about to be reused
+	if ((rc = c->h_par.reserve(n * sizeof(InflateJob)))) return rc;
+	if ((rc = c->d_par1.reserve(n * sizeof(InflateJob)))) return rc;
+	InflateJob *h = static_cast<InflateJob *>(c->h_par.p);
+	memset(h, 0, n * sizeof(InflateJob));
+	for (size_t i = 0; i < n; i++) h[i].wrap = kWrapSkip;
+	for (size_t k = 0; k < serial.size(); k++) h[serial_at[k]] = serial[k];
+	NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_par1.p, h, n * sizeof(InflateJob), cudaMemcpyHostToDevice, c->stream));
+	timer_begin(c, 1);
+	NXGPU_CUDA_OK(launch_inflate(static_cast<const InflateJob *>(c->d_par1.p), d_outs, (uint32_t)n, static_cast<uint32_t *>(c->d_misc.p), c->stream));
+	timer_end(c, 1);
+	c->launches++;
 	return 0;
 }
 } // namespace nxgpu
@@ -957,8 +995,7 @@ int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n,
 		timer_begin(c, 1);
 		NXGPU_CUDA_OK(launch_inflate(dj + g0, dout + g0, (uint32_t)ng, static_cast<uint32_t *>(c->d_misc.p), c->stream));
 		timer_end(c, 1);
-		for (const auto &pj : par)            // (n <= 32: one group)
-			if ((rc = inflate_parallel(c, pj.second, dout + pj.first))) return rc;
+		if (!par.empty() && (rc = inflate_parallel(c, par, dout))) return rc;      // (n <= 32: one group)
 		// crc32 / adler32 of every output, lengths taken from the device results
 		uint32_t *d_rs = d_rs_all + g0 + g;
 		NXGPU_CUDA_OK(launch_ranges_from_inflate(dj + g0, dout + g0, (uint32_t)ng, d_rng + g0 * K * rb, d_rs, c->stream, K));

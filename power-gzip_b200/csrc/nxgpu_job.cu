@@ -383,10 +383,8 @@ void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 				   static_cast<uint32_t *>(c->d_misc.p), c->stream) != cudaSuccess) { fail_all(); return; }
 		timer_end(c, 1);
 		c->launches++;
-		for (const auto &pj : par) {
-			ij[pj.first].wrap &= ~kWrapSkip;
-			if (inflate_parallel(c, pj.second, static_cast<InflateOut *>(c->d_iouts.p) + pj.first)) { fail_all(); return; }
-		}
+		// (ij[] may still be on its way up: the skip marks stay)
+		if (!par.empty() && inflate_parallel(c, par, static_cast<InflateOut *>(c->d_iouts.p))) { fail_all(); return; }
 	}
 	// ---- results of the codec kernels (sizes, states) ----
 	const size_t res_bytes = align16(nd * sizeof(DeflateOut)) + align16(ni * sizeof(InflateOut)) + align16(nd * 316 * 4) + n * 288 + n * 8 + 64;
