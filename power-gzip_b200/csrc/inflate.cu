@@ -861,25 +861,30 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, u
 			}
 			uint32_t mm = __ballot_sync(0xffffffffu, is_m && tok_dist(t) < incl);
 			uint8_t *const dq = J.dst + out;
-			for (uint32_t b0 = 0; b0 < total; b0 += 64) {
-				const uint32_t ba = b0 + lane, bb = ba + 32;
-				uint32_t la = 0, lb = 0;
-#pragma unroll
-				for (int s = 16; s; s >>= 1) {
-					const uint32_t va = __shfl_sync(0xffffffffu, incl, la + s - 1);
-					const uint32_t vb = __shfl_sync(0xffffffffu, incl, lb + s - 1);
-					if (va <= ba) la += s;
-					if (vb <= bb) lb += s;
+			{
+				// the owner of every byte of a round of 32: one warp-wide OR of the token starts inside the round and a
+				// population count (see ring_fill); two rounds per iteration, all loads in front of all stores
+				const uint32_t start = incl - mylen;
+				uint32_t before = 0;
+				const uint32_t upto = 0xffffffffu >> (31 - lane);
+				for (uint32_t b0 = 0; b0 < total; b0 += 64) {
+					const uint32_t ra = start - b0, rb = start - b0 - 32;
+					const uint32_t ma = __reduce_or_sync(0xffffffffu, ra < 32 ? 1u << ra : 0u);
+					const uint32_t mb = __reduce_or_sync(0xffffffffu, rb < 32 ? 1u << rb : 0u);
+					const uint32_t oa = (before + __popc(ma & upto) - 1) & 31;
+					before += __popc(ma);
+					const uint32_t ob = (before + __popc(mb & upto) - 1) & 31;
+					before += __popc(mb);
+					const uint32_t ta = __shfl_sync(0xffffffffu, t, oa), tb = __shfl_sync(0xffffffffu, t, ob);
+					const uint32_t ba = b0 + lane, bb = ba + 32;
+					const bool ca = ba < total && tok_is_match(ta) && !((mm >> oa) & 1);
+					const bool cb = bb < total && tok_is_match(tb) && !((mm >> ob) & 1);
+					uint32_t xa = ta, xb = tb;
+					if (ca) xa = dq[(int32_t)ba - (int32_t)tok_dist(ta)];
+					if (cb) xb = dq[(int32_t)bb - (int32_t)tok_dist(tb)];
+					if (ba < total && (ca || !tok_is_match(ta))) dq[ba] = (uint8_t)xa;
+					if (bb < total && (cb || !tok_is_match(tb))) dq[bb] = (uint8_t)xb;
 				}
-				const uint32_t ta = __shfl_sync(0xffffffffu, t, la), ia = __shfl_sync(0xffffffffu, incl, la);
-				const uint32_t tb = __shfl_sync(0xffffffffu, t, lb), ib = __shfl_sync(0xffffffffu, incl, lb);
-				uint32_t xa = ta, xb = tb;
-				const bool ca = ba < total && tok_is_match(ta) && tok_dist(ta) >= ia;
-				const bool cb = bb < total && tok_is_match(tb) && tok_dist(tb) >= ib;
-				if (ca) xa = dq[(int32_t)ba - (int32_t)tok_dist(ta)];
-				if (cb) xb = dq[(int32_t)bb - (int32_t)tok_dist(tb)];
-				if (ba < total && (ca || !tok_is_match(ta))) dq[ba] = (uint8_t)xa;
-				if (bb < total && (cb || !tok_is_match(tb))) dq[bb] = (uint8_t)xb;
 			}
 			__syncwarp();
 			while (mm) {

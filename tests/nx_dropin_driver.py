@@ -13,6 +13,7 @@ nx, in one shot and in small pieces.
 usage: nx_dropin_driver.py <libnxz .so> [size_log2]
        nx_dropin_driver.py <libnxz .so> stress <threads> <iterations>
        nx_dropin_driver.py <libnxz .so> initend [pairs]
+       nx_dropin_driver.py <libnxz .so> lone [size_log2] [level]
 The stress mode follows the reference's test/test_multithread_stress.c:26-120: every thread runs
 compress()/uncompress() over the same ten buffers (4 KiB .. 1 MiB of the 33-symbol alphabet of
 test/test_utils.c:22-28, srand(1)) and checks the round trip; it also reports how many descriptors
@@ -206,6 +207,42 @@ def initend(n):
 
 if STRESS:
     stress(int(sys.argv[3]), int(sys.argv[4]))
+    sys.exit(0)
+def lone(lg, level):
+    """ONE foreign zlib stream through uncompress() (the LD_PRELOAD single-stream case): text-like data compressed by system zlib,
+    inflated by the library under test; system zlib's own inflate on one core is timed beside it."""
+    import time
+    alice = gzip.decompress(open(os.path.join(ROOT, "tests", "golden", "alice29.txt.gz"), "rb").read())
+    rnd = random.Random(7)
+    parts, n = [], 0
+    while n < (1 << lg):
+        o, l = rnd.randrange(len(alice) - 4096), rnd.randrange(200, 4096)
+        parts.append(alice[o:o + l]); n += l
+    data = b"".join(parts)[: 1 << lg]
+    comp = zlib.compress(data, level)
+    src = C.create_string_buffer(comp, len(comp))
+    dst = C.create_string_buffer(len(data))
+    lib.nx_uncompress.argtypes = [C.c_void_p, C.POINTER(C.c_ulong), C.c_void_p, C.c_ulong]
+    best = 1e9
+    for it in range(4):
+        dl = C.c_ulong(len(data))
+        t0 = time.perf_counter()
+        rc = lib.nx_uncompress(dst, C.byref(dl), src, len(comp))     # (uncompress() itself calls uncompress2 through the PLT, which binds to the libz this interpreter already loaded)
+        dt = time.perf_counter() - t0
+        assert rc == 0 and dl.value == len(data), (rc, dl.value)
+        if it:
+            best = min(best, dt)
+    ok = dst.raw == data
+    t0 = time.perf_counter()
+    ref = zlib.decompress(comp)
+    cpu = time.perf_counter() - t0
+    print(json.dumps({"bytes": len(data), "compressed_bytes": len(comp), "level": level, "ok": bool(ok and ref == data),
+                      "uncompress_ms": round(best * 1e3, 2), "GBps": round(len(data) / best / 1e9, 3),
+                      "system_zlib_one_core_ms": round(cpu * 1e3, 2), "system_zlib_one_core_GBps": round(len(data) / cpu / 1e9, 3)}))
+
+
+if len(sys.argv) > 2 and sys.argv[2] == "lone":
+    lone(int(sys.argv[3]) if len(sys.argv) > 3 else 26, int(sys.argv[4]) if len(sys.argv) > 4 else 6)
     sys.exit(0)
 if len(sys.argv) > 2 and sys.argv[2] == "initend":
     initend(int(sys.argv[3]) if len(sys.argv) > 3 else 1000)
