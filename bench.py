@@ -612,6 +612,56 @@ def extras_single_gpu(args, pg, eng, lib, torch, src, hsrc, n, extra, hbm_peak, 
     del dbig
     lib.nxgpu_host_free(hbig)
 
+    # ---- ONE foreign stream (no index, not our encoder): 64 MiB of the benchmark text as system zlib level 6 writes it.  One warp
+    # walks such a stream at ~70 MB/s; the engine finds the block starts, decodes the blocks speculatively and then for real
+    # (csrc/inflate_par.cuh).  Device-resident, from host memory, and through the reference's own nx_uncompress() ----
+    try:
+        ln = min(n, 64 << 20)
+        one = C.string_at(hsrc, ln)
+        t0 = time.perf_counter()
+        zc = zlib.compress(one, 6)
+        t_comp = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        assert zlib.decompress(zc) == one
+        t_cpu = time.perf_counter() - t0
+        dzc = torch.frombuffer(bytearray(zc), dtype=torch.uint8).cuda()
+        dback = torch.empty(ln, dtype=torch.uint8, device="cuda")
+
+        def lone_step():
+            eng.timer_start()
+            r = eng.inflate_batch([pg.InflateItem(dzc.data_ptr(), len(zc), dback.data_ptr(), ln, pg.WRAP_ZLIB, 0)], mem=pg.MEM_DEVICE)[0]
+            assert r.rc == 0 and r.out_len == ln and r.crc32 == zlib.crc32(one)
+            return eng.timer_stop()
+        pl = timed(lone_step, 5, 2)
+        hz, hb = C.c_void_p(), C.c_void_p()
+        lib.nxgpu_host_alloc(len(zc) + 64, C.byref(hz)); lib.nxgpu_host_alloc(ln, C.byref(hb))
+        C.memmove(hz, zc, len(zc))
+        th = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            r = eng.inflate_batch([pg.InflateItem(hz.value, len(zc), hb.value, ln, pg.WRAP_ZLIB, 0)], mem=pg.MEM_HOST)[0]
+            d = time.perf_counter() - t0
+            th = d if th is None else min(th, d)
+        assert r.rc == 0 and C.string_at(hb.value, 4096) == one[:4096]
+        lib.nxgpu_host_free(hz); lib.nxgpu_host_free(hb)
+        lone = {"input": f"first {ln >> 20} MiB of the benchmark text, zlib.compress level 6 ({len(zc)} bytes, one stream, no flush points)",
+                "device_resident_GBps": ln / (sum(pl) / len(pl)) / 1e6, "device_resident_ms_per_step": [round(x, 2) for x in pl],
+                "host_to_host_GBps": ln / th / 1e9,
+                "system_zlib_one_core_GBps": ln / t_cpu / 1e9}
+        gpu_nxz0 = os.path.join(ROOT, "power-gzip_b200", "libnxz_gpu.so")
+        if os.path.exists(gpu_nxz0):
+            through = {}
+            for lg in (20, 22, 24, 26):
+                pr = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "nx_dropin_driver.py"), gpu_nxz0, "lone", str(lg), "6"],
+                                    capture_output=True, text=True, timeout=300, env=dict(os.environ, NX_GZIP_LOGFILE="/tmp/nx_bench.log"))
+                j = json.loads(pr.stdout.strip().splitlines()[-1])
+                through[f"{1 << (lg - 20)} MiB"] = {"GBps": j["GBps"], "system_zlib_one_core_GBps": j["system_zlib_one_core_GBps"], "ok": j["ok"]}
+            lone["through_nx_uncompress"] = {"note": "the reference's nx_uncompress() in NX mode over the engine, alice29-like text, zlib level 6", **through}
+        extra["inflate_one_foreign_stream"] = lone
+        del dzc, dback
+    except Exception as e:                          # noqa: BLE001 - an extra, never fatal
+        extra["inflate_one_foreign_stream"] = {"error": repr(e)[:300]}
+
     # ---- configs[4], second half: many concurrent small z_streams through the UNCHANGED zlib surface.  The reference's own
     # test/test_multithread_stress.c (compress()/uncompress() of 4 KiB - 1 MiB buffers, 64 threads, no Python in the loop) linked
     # against the drop-in library (NX mode: every call is a job on the GPU engine), and the same binary over the reference's

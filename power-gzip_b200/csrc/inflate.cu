@@ -483,6 +483,7 @@ __device__ __forceinline__ uint32_t walk_batch(BitReader &br, WarpTables &T, uin
 //    spans and copied afterwards, in order, by the whole warp.
 //  * A match whose source lies so far back that it shares ring slots with this batch's output (distance > 32 Ki - total)
 //    is copied first, in order, before anything else is written.
+constexpr uint32_t kWinBytes = 32768;
 constexpr uint32_t kRingMask = 32768 - 1;
 // ring element i of a ring at shared address rsa (a generic pointer would cost an S2UR + address arithmetic per access)
 template <typename E> __device__ __forceinline__ uint32_t ring_ld(uint32_t rsa, uint32_t i)
@@ -569,15 +570,122 @@ __device__ __forceinline__ void ring_fill(E *ring, uint32_t base, uint32_t lane,
 	}
 }
 
+// ---- two warps per stream: a walker and a copier ----
+// Walking the bit stream occupies one lane, copying the bytes all 32, and for a warp that is alone with its stream the
+// two phases take about the same time (ncu: ~145 cycles per symbol to walk and judge, ~100 to copy).  With a second warp
+// they overlap: the walker (inflate_one<kWin, true>) hands every batch of tokens and every stored run to the copier
+// through a two-slot queue in shared memory; the copier owns the window ring and the output position, checks the
+// target space and the distances, and reports the first thing that is wrong.  The walker looks at that verdict before
+// every batch and at the end, where the copier's verdict comes first: it concerns an earlier part of the stream.
+struct DuoQueue {
+	uint32_t head, tail;              // commands pushed / taken
+	uint32_t cerr;                    // copier: 0, or the completion code of the first batch it had to refuse
+	uint32_t out_final, done;
+	uint32_t pad_[3];
+	struct Cmd { uint32_t kind, a, b, pad_; uint32_t tok[32]; } cmd[2];   // kind 1: a tokens; 2: b stored bytes at source offset a; 3: end
+};
+constexpr uint32_t kDuoTokens = 1, kDuoStored = 2, kDuoEnd = 3;
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ void st_vol(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+
+// walker warp, all lanes: lane l's token in t (kDuoTokens), or a stored run
+__device__ __forceinline__ void duo_push(DuoQueue &Q, uint32_t &head, uint32_t lane, uint32_t kind, uint32_t a, uint32_t b, uint32_t t)
+{
+	while (head - ld_vol(&Q.tail) >= 2)
+		__nanosleep(40);
+	DuoQueue::Cmd &c = Q.cmd[head & 1];
+	c.tok[lane] = t;
+	if (lane == 0) { c.kind = kind; c.a = a; c.b = b; }
+	__threadfence_block();
+	__syncwarp();
+	head++;
+	if (lane == 0)
+		st_vol(&Q.head, head);
+}
+
+// copier warp: everything inflate_one<true> does with a batch once it is decoded
+__device__ void duo_copier(const InflateJob &J, DuoQueue &Q, uint8_t *win)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const bool job = J.wrap == kWrapJob;
+	const uint32_t wofs = J.hist_len;
+	{
+		const uint32_t h = J.hist_len < kWinBytes ? J.hist_len : kWinBytes;
+		const uint8_t *hp = J.hist_ptr ? J.hist_ptr + kWinBytes : J.dst;
+		for (uint32_t i = lane; i < h; i += 32)
+			win[(wofs - h + i) & (kWinBytes - 1)] = hp[(int32_t)i - (int32_t)h];
+		__syncwarp();
+	}
+	uint32_t out = 0, err = 0, tail = 0;
+	for (;;) {
+		while (ld_vol(&Q.head) == tail)
+			__nanosleep(40);
+		__threadfence_block();
+		const DuoQueue::Cmd &c = Q.cmd[tail & 1];
+		const uint32_t kind = ld_vol(&c.kind), a = ld_vol(&c.a), b = ld_vol(&c.b);
+		const uint32_t t = kind == kDuoTokens && lane < a ? ld_vol(&c.tok[lane]) : 0;
+		__syncwarp();
+		tail++;
+		if (lane == 0)
+			st_vol(&Q.tail, tail);                       // the slot is free again
+		if (kind == kDuoEnd)
+			break;
+		if (err)
+			continue;
+		if (kind == kDuoStored) {
+			if (b > J.dst_cap - out) {
+				err = job ? 13 : NXGPU_E_BUF;
+			} else {
+				for (uint32_t i = lane; i < b; i += 32) {
+					const uint8_t v = J.src[a + i];
+					J.dst[out + i] = v;
+					win[(wofs + out + i) & (kWinBytes - 1)] = v;
+				}
+				out += b;
+				__syncwarp();
+			}
+		} else {
+			const bool is_m = lane < a && tok_is_match(t);
+			const uint32_t mylen = lane < a ? (is_m ? tok_len(t) : 1) : 0;
+			uint32_t incl = mylen;
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+				if (lane >= (uint32_t)o)
+					incl += y;
+			}
+			const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+			const uint32_t my_out = out + incl - mylen;
+			if (total > J.dst_cap - out) {
+				err = job ? 13 : NXGPU_E_BUF;
+			} else if (__any_sync(0xffffffffu, is_m && tok_dist(t) > my_out + J.hist_len)) {
+				err = job ? 67 : NXGPU_E_DATA;
+			} else {
+				ring_fill<uint8_t>(win, wofs + out, lane, t, is_m, mylen, incl, total);
+				uint8_t *const dq = J.dst + out;
+				for (uint32_t i = lane; i < total; i += 32)
+					dq[i] = win[(wofs + out + i) & (kWinBytes - 1)];
+				out += total;
+			}
+		}
+		if (err && lane == 0)
+			st_vol(&Q.cerr, err);
+	}
+	if (lane == 0) {
+		st_vol(&Q.out_final, out);
+		__threadfence_block();
+		st_vol(&Q.done, 1);
+	}
+}
+
 // kWin: the last 32 KiB of output are mirrored in a shared-memory ring (win), and every match source is read from
 // there instead of from global memory.  A warp that is alone with its stream (a lone uncompress() through
 // nxu_run_job, a handful of large members) otherwise pays an L2 round trip per materialise step and per
 // short-distance match: 54 MB/s.  With thousands of members in flight the other warps hide that latency and the
 // 32 KiB per warp would cost occupancy, so the batch kernel keeps reading the window from L1/L2.
-constexpr uint32_t kWinBytes = 32768;
-template <bool kWin>
-__device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, uint8_t *win)
+template <bool kWin, bool kDuo = false>
+__device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, uint8_t *win, DuoQueue *Q = nullptr)
 {
+	uint32_t duo_head = 0;               // kDuo: commands pushed so far
 	const uint32_t lane = threadIdx.x & 31;
 	const bool job = J.wrap == kWrapJob;     // NX decompress-job semantics: stop at the source end and report where
 	const uint64_t total_bits = (uint64_t)J.src_len * 8;
@@ -589,7 +697,7 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, u
 	uint32_t out = 0;
 	// window ring: output position p (counted from the first history byte) lives at win[p % 32 KiB]
 	const uint32_t wofs = J.hist_len;
-	if (kWin) {
+	if (kWin && !kDuo) {
 		const uint32_t h = J.hist_len < kWinBytes ? J.hist_len : kWinBytes;
 		const uint8_t *hp = J.hist_ptr ? J.hist_ptr + kWinBytes : J.dst;      // one past the last history byte
 		for (uint32_t i = lane; i < h; i += 32)
@@ -750,13 +858,20 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, u
 				if (!job) { rc = NXGPU_E_DATA; break; }
 				n = J.src_len > stored_at ? J.src_len - stored_at : 0;   // copy what is there, resume later
 			}
-			if (n > J.dst_cap - out) { rc = job ? 13 : NXGPU_E_BUF; break; }
-			for (uint32_t i = lane; i < n && !dry; i += 32) {
-				const uint8_t v = J.src[stored_at + i];
-				J.dst[out + i] = v;
-				if (kWin) win[(wofs + out + i) & (kWinBytes - 1)] = v;
+			if (kDuo) {
+				// the copier owns the target and the window
+				if (ld_vol(&Q->cerr)) { rc = (int)ld_vol(&Q->cerr); break; }
+				if (n)
+					duo_push(*Q, duo_head, lane, kDuoStored, stored_at, n, 0);
+			} else {
+				if (n > J.dst_cap - out) { rc = job ? 13 : NXGPU_E_BUF; break; }
+				for (uint32_t i = lane; i < n && !dry; i += 32) {
+					const uint8_t v = J.src[stored_at + i];
+					J.dst[out + i] = v;
+					if (kWin) win[(wofs + out + i) & (kWinBytes - 1)] = v;
+				}
+				out += n;
 			}
-			out += n;
 			if (n < stored_len) {
 				o_sfbt = 0x8 | (final_block ? 1u : 0u);
 				o_rem = stored_len - n;
@@ -827,6 +942,12 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, u
 				break;
 			// ---- materialise the queue ----
 			const uint32_t t = lane < qn ? T.q[lane] : 0;
+			if (kDuo) {
+				if (ld_vol(&Q->cerr)) { rc = (int)ld_vol(&Q->cerr); break; }
+				if (qn)
+					duo_push(*Q, duo_head, lane, kDuoTokens, qn, 0, t);
+				continue;
+			}
 			const bool is_m = lane < qn && tok_is_match(t);
 			const uint32_t mylen = lane < qn ? (is_m ? tok_len(t) : 1) : 0;
 			uint32_t incl = mylen;
@@ -916,6 +1037,16 @@ __device__ void inflate_one(const InflateJob &J, InflateOut &O, WarpTables &T, u
 		block_ended = true;
 	}
 
+	if (kDuo) {
+		// the copier finishes what it was given; its verdict is about an earlier part of the stream than anything found here
+		duo_push(*Q, duo_head, lane, kDuoEnd, 0, 0, 0);
+		while (!ld_vol(&Q->done))
+			__nanosleep(40);
+		__threadfence_block();
+		const uint32_t ce = ld_vol(&Q->cerr);
+		if (ce) rc = (int)ce;
+		out = ld_vol(&Q->out_final);
+	}
 	if (job) {
 		// ---- NX completion state (lib/nx_inflate.c:1372-1609 reads these) ----
 		const bool in_dyn = suspended && (__shfl_sync(0xffffffffu, o_sfbt, 0) & 0xe) == 0xc;
@@ -1036,29 +1167,47 @@ inflate_kernel(const InflateJob *__restrict__ jobs, InflateOut *__restrict__ out
 	}
 }
 
-// a few large streams: one warp per CTA with its 32 KiB window in shared memory (see inflate_one<kWin>)
-__global__ void __launch_bounds__(32)
+// a few large streams: a walker warp and a copier warp per CTA, the 32 KiB window in shared memory (see inflate_one<kWin, kDuo>)
+constexpr size_t kDuoTables = (sizeof(WarpTables) + 15) & ~(size_t)15;
+constexpr size_t kDuoQueueAt = kDuoTables, kDuoWinAt = (kDuoTables + sizeof(DuoQueue) + 15) & ~(size_t)15;
+// one stream on the two warps of a CTA (64 threads, both warps call)
+__device__ __forceinline__ void inflate_duo(const InflateJob &J, InflateOut &O, uint8_t *smem_raw)
+{
+	WarpTables &T = *reinterpret_cast<WarpTables *>(smem_raw);
+	DuoQueue &Q = *reinterpret_cast<DuoQueue *>(smem_raw + kDuoQueueAt);
+	uint8_t *win = smem_raw + kDuoWinAt;
+	if (threadIdx.x < 8)
+		reinterpret_cast<uint32_t *>(&Q)[threadIdx.x] = 0;
+	__syncthreads();
+	if (threadIdx.x < 32)
+		inflate_one<true, true>(J, O, T, win, &Q);
+	else
+		duo_copier(J, Q, win);
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(64)
 inflate_solo_kernel(const InflateJob *__restrict__ jobs, InflateOut *__restrict__ outs, uint32_t n_jobs, uint32_t *next_job)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
-	WarpTables &T = *reinterpret_cast<WarpTables *>(smem_raw);
-	uint8_t *win = smem_raw + ((sizeof(WarpTables) + 15) & ~(size_t)15);
-	const uint32_t lane = threadIdx.x & 31;
+	__shared__ uint32_t s_job;
 	for (;;) {
-		uint32_t j = 0;
-		if (lane == 0)
-			j = atomicAdd(next_job, 1u);
-		j = __shfl_sync(0xffffffffu, j, 0);
+		if (threadIdx.x == 0)
+			s_job = atomicAdd(next_job, 1u);
+		__syncthreads();
+		const uint32_t j = s_job;
+		__syncthreads();
 		if (j >= n_jobs)
 			break;
 		const InflateJob J = jobs[j];
 		if (J.wrap & kWrapSkip)
 			continue;
-		if ((J.wrap & kWrapDry) != 0)
-			inflate_one<false>(J, outs[j], T, nullptr);
-		else
-			inflate_one<true>(J, outs[j], T, win);
-		__syncwarp();
+		if ((J.wrap & kWrapDry) != 0) {
+			if (threadIdx.x < 32)
+				inflate_one<false>(J, outs[j], *reinterpret_cast<WarpTables *>(smem_raw), nullptr);
+			continue;
+		}
+		inflate_duo(J, outs[j], smem_raw);
 	}
 }
 
@@ -1119,7 +1268,7 @@ static cudaError_t launch_inflate_t(const InflateJob *jobs, InflateOut *outs, ui
 static cudaError_t launch_inflate_solo(const InflateJob *jobs, InflateOut *outs, uint32_t n_jobs, uint32_t *counter, cudaStream_t s)
 {
 	static PerDeviceOnce once;
-	const size_t smem = ((sizeof(WarpTables) + 15) & ~(size_t)15) + kWinBytes;
+	const size_t smem = kDuoWinAt + kWinBytes;
 	cudaError_t e = once.run([smem] { return cudaFuncSetAttribute(inflate_solo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
 	if (e != cudaSuccess)
 		return e;
@@ -1127,7 +1276,7 @@ static cudaError_t launch_inflate_solo(const InflateJob *jobs, InflateOut *outs,
 	if (e != cudaSuccess)
 		return e;
 	const uint32_t grid = n_jobs < (uint32_t)(kNumSMs * 5) ? n_jobs : (uint32_t)(kNumSMs * 5);
-	inflate_solo_kernel<<<grid ? grid : 1, 32, smem, s>>>(jobs, outs, n_jobs, counter);
+	inflate_solo_kernel<<<grid ? grid : 1, 64, smem, s>>>(jobs, outs, n_jobs, counter);
 	return cudaGetLastError();
 }
 
@@ -1155,8 +1304,7 @@ cudaError_t launch_blockfind(const uint8_t *src, uint32_t src_len, uint64_t firs
 cudaError_t launch_inflate_par(const ParPlan &plan, uint32_t *counter, cudaStream_t s)
 {
 	static PerDeviceOnce once;
-	const size_t tables = (sizeof(WarpTables) + 15) & ~(size_t)15;
-	const size_t smem_spec = tables + kRingSyms * 2, smem_chain = tables + kWinBytes;
+	const size_t smem_spec = kDuoWinAt + kRingSyms * 2, smem_chain = kDuoWinAt + kWinBytes;
 	cudaError_t e = once.run([=] {
 		cudaError_t r = cudaFuncSetAttribute(inflate_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_spec);
 		if (r != cudaSuccess)
@@ -1168,13 +1316,13 @@ cudaError_t launch_inflate_par(const ParPlan &plan, uint32_t *counter, cudaStrea
 	e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
 	if (e != cudaSuccess)
 		return e;
-	inflate_spec_kernel<<<plan.n_cand + 1, 32, smem_spec, s>>>(plan);
+	inflate_spec_kernel<<<plan.n_cand + 1, 64, smem_spec, s>>>(plan);
 	inflate_link_kernel<<<1, 32, 0, s>>>(plan);
 	if (plan.n_cand) {
 		const uint32_t gw = plan.n_cand < (uint32_t)kNumSMs * 2 ? plan.n_cand : (uint32_t)kNumSMs * 2;
 		inflate_windows_kernel<<<gw, 1024, 0, s>>>(plan);
 		const uint32_t gc = plan.n_cand < (uint32_t)kNumSMs * 5 ? plan.n_cand : (uint32_t)kNumSMs * 5;
-		inflate_chain_kernel<<<gc, 32, smem_chain, s>>>(plan, counter);
+		inflate_chain_kernel<<<gc, 64, smem_chain, s>>>(plan, counter);
 	}
 	inflate_finish_kernel<<<1, 32, 0, s>>>(plan);
 	e = cudaGetLastError();

@@ -182,9 +182,10 @@ blockfind_verify_kernel(const uint8_t *__restrict__ src, uint32_t src_len, const
 	}
 }
 
-// ---- 2. speculative decode of one candidate (one warp) ----
-__device__ void spec_one(const uint8_t *src, uint32_t src_len, uint64_t start_bit, const uint32_t *__restrict__ map, uint32_t out_cap,
-			 bool strict, WarpTables &T, uint16_t *win, uint16_t *ring_out, SpecOut &O)
+// ---- 2. speculative decode of one candidate: a walker warp and a copier warp (see DuoQueue in inflate.cu) ----
+// walker: headers, tables, symbols; hands token batches and stored runs to the copier; decides how the piece ends
+__device__ void spec_walker(const uint8_t *src, uint32_t src_len, uint64_t start_bit, const uint32_t *__restrict__ map, bool strict,
+			    WarpTables &T, DuoQueue &Q, SpecOut &O)
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint64_t total_bits = (uint64_t)src_len * 8;
@@ -196,18 +197,9 @@ __device__ void spec_one(const uint8_t *src, uint32_t src_len, uint64_t start_bi
 		br.seek((uint32_t)(start_bit >> 3));
 		br.drop((uint32_t)(start_bit & 7));
 	}
-	// the window in front of the piece: symbol s = "byte s of the 32 KiB that end where the piece starts"
-	{
-		uint32_t *w32 = reinterpret_cast<uint32_t *>(win);
-		for (uint32_t i = lane; i < kRingSyms / 2; i += 32)
-			w32[i] = (0x8000u | (2 * i)) | ((0x8000u | (2 * i + 1)) << 16);
-	}
-	__syncwarp();
-	uint32_t out = 0, max_back = 0, status = kSpecError;
-#ifdef NXGPU_PAR_PROFILE
-	long long t_walk = 0, t_mat = 0, t_seq = 0, n_batches = 0, n_seq = 0, t_fast = 0, n_fast = 0, n_calls = 0; const long long t_begin = clock64();
-#endif
+	uint32_t status = kSpecError, head = 0;
 	for (;;) {
+		if (ld_vol(&Q.cerr)) { status = kSpecTooLong; break; }
 		// ---- block header (lane 0) ----
 		uint32_t btype = 0, stored_len = 0, stored_at = 0, fin = 0, bad = 0;
 		int hlit = 0, hdist = 0;
@@ -237,10 +229,8 @@ __device__ void spec_one(const uint8_t *src, uint32_t src_len, uint64_t start_bi
 			stored_len = __shfl_sync(0xffffffffu, stored_len, 0);
 			stored_at = __shfl_sync(0xffffffffu, stored_at, 0);
 			if ((uint64_t)stored_at + stored_len > src_len) { status = kSpecSrcEnd; break; }
-			if (stored_len > out_cap - out) { status = kSpecTooLong; break; }
-			for (uint32_t i = lane; i < stored_len; i += 32)
-				win[(out + i) & (kRingSyms - 1)] = src[stored_at + i];
-			out += stored_len;
+			if (stored_len)
+				duo_push(Q, head, lane, kDuoStored, stored_at, stored_len, 0);
 			if (lane == 0)
 				br.seek(stored_at + stored_len);
 			__syncwarp();
@@ -273,9 +263,6 @@ __device__ void spec_one(const uint8_t *src, uint32_t src_len, uint64_t start_bi
 						__syncwarp();
 					}
 				}
-#ifdef NXGPU_PAR_PROFILE
-				const long long t0 = clock64();
-#endif
 				uint32_t wst;
 				uint64_t sym_at = 0;
 				const uint32_t qn = walk_batch(br, T, tsa, lane, wst, sym_at);
@@ -284,32 +271,9 @@ __device__ void spec_one(const uint8_t *src, uint32_t src_len, uint64_t start_bi
 				else if (wst == kWalkEob) block_done = true;
 				if (stop)
 					break;
-#ifdef NXGPU_PAR_PROFILE
-				const long long t1 = clock64();
-#endif
-				// ---- the queue goes into the ring (nothing else is written) ----
-				const uint32_t t = lane < qn ? T.q[lane] : 0;
-				const bool is_m = lane < qn && tok_is_match(t);
-				const uint32_t mylen = lane < qn ? (is_m ? tok_len(t) : 1) : 0;
-				uint32_t incl = mylen;
-				for (int o = 1; o < 32; o <<= 1) {
-					const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-					if (lane >= (uint32_t)o)
-						incl += y;
-				}
-				const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-				const uint32_t my_out = out + incl - mylen;
-				if (total > out_cap - out) { stop = kSpecTooLong; break; }
-				if (is_m && tok_dist(t) > my_out)
-					max_back = max(max_back, tok_dist(t) - my_out);
-#ifdef NXGPU_PAR_PROFILE
-				const long long t2 = clock64();
-#endif
-				ring_fill<uint16_t>(win, out, lane, t, is_m, mylen, incl, total);
-				out += total;
-#ifdef NXGPU_PAR_PROFILE
-				{ const long long t3 = clock64(); t_walk += t1 - t0; t_mat += t2 - t1; t_seq += t3 - t2; n_batches++; }
-#endif
+				if (ld_vol(&Q.cerr)) { stop = kSpecTooLong; break; }
+				if (qn)
+					duo_push(Q, head, lane, kDuoTokens, qn, 0, lane < qn ? T.q[lane] : 0);
 			}
 			if (stop) { status = stop; break; }
 		}
@@ -322,19 +286,79 @@ __device__ void spec_one(const uint8_t *src, uint32_t src_len, uint64_t start_bi
 		if (at >= total_bits) { status = kSpecSrcEnd; break; }
 		if ((map[at >> 5] >> (at & 31)) & 1) { status = kSpecLinked; break; }
 	}
+	if (lane == 0)
+		O.end_bit = br.bits_used();
+	duo_push(Q, head, lane, kDuoEnd, status, 0, 0);
+}
+
+// copier: the ring of the last 32 Ki symbols (bytes, or markers "window byte s" for what lies in front of the piece), the
+// piece's length, how far back it reached; dumps the ring if the piece ended on a candidate
+__device__ void spec_copier(const uint8_t *src, uint32_t out_cap, DuoQueue &Q, uint16_t *win, uint16_t *ring_out, SpecOut &O)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	{
+		uint32_t *w32 = reinterpret_cast<uint32_t *>(win);
+		for (uint32_t i = lane; i < kRingSyms / 2; i += 32)
+			w32[i] = (0x8000u | (2 * i)) | ((0x8000u | (2 * i + 1)) << 16);
+	}
+	__syncwarp();
+	uint32_t out = 0, max_back = 0, tail = 0, status = kSpecError;
+	bool too_long = false;
+	for (;;) {
+		while (ld_vol(&Q.head) == tail)
+			__nanosleep(40);
+		__threadfence_block();
+		const DuoQueue::Cmd &c = Q.cmd[tail & 1];
+		const uint32_t kind = ld_vol(&c.kind), a = ld_vol(&c.a), b = ld_vol(&c.b);
+		const uint32_t t = kind == kDuoTokens && lane < a ? ld_vol(&c.tok[lane]) : 0;
+		__syncwarp();
+		tail++;
+		if (lane == 0)
+			st_vol(&Q.tail, tail);
+		if (kind == kDuoEnd) { status = a; break; }
+		if (too_long)
+			continue;
+		if (kind == kDuoStored) {
+			if (b > out_cap - out) {
+				too_long = true;
+			} else {
+				for (uint32_t i = lane; i < b; i += 32)
+					win[(out + i) & (kRingSyms - 1)] = src[a + i];
+				out += b;
+				__syncwarp();
+			}
+		} else {
+			const bool is_m = lane < a && tok_is_match(t);
+			const uint32_t mylen = lane < a ? (is_m ? tok_len(t) : 1) : 0;
+			uint32_t incl = mylen;
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+				if (lane >= (uint32_t)o)
+					incl += y;
+			}
+			const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+			const uint32_t my_out = out + incl - mylen;
+			if (total > out_cap - out) {
+				too_long = true;
+			} else {
+				if (is_m && tok_dist(t) > my_out)
+					max_back = max(max_back, tok_dist(t) - my_out);
+				ring_fill<uint16_t>(win, out, lane, t, is_m, mylen, incl, total);
+				out += total;
+			}
+		}
+		if (too_long && lane == 0)
+			st_vol(&Q.cerr, 1);
+	}
+	if (too_long)
+		status = kSpecTooLong;
 	for (int o = 16; o; o >>= 1)
 		max_back = max(max_back, __shfl_xor_sync(0xffffffffu, max_back, o));
 	if (lane == 0) {
-		O.end_bit = br.bits_used();
 		O.out_len = out;
 		O.status = status;
 		O.max_back = max_back;
 		O.pad_ = 0;
-#ifdef NXGPU_PAR_PROFILE
-		if (status == kSpecLinked && (start_bit >> 3) % 7 == 0)
-			printf("spec unit @%llu: out %u, %lld batches, total %lld cyc, walk %lld (%lld %lld %lld), par-mat %lld, seq-mat %lld (%lld matches)\n",
-			       (unsigned long long)start_bit, out, n_batches, clock64() - t_begin, t_walk, t_fast, n_fast, n_calls, t_mat, t_seq, n_seq);
-#endif
 	}
 	if (status == kSpecLinked) {
 		__syncwarp();
@@ -345,23 +369,29 @@ __device__ void spec_one(const uint8_t *src, uint32_t src_len, uint64_t start_bi
 	}
 }
 
-// piece 0 (the descriptor itself, stopping at the first candidate boundary) and every candidate, one warp per CTA
-__global__ void __launch_bounds__(32)
+// piece 0 (the descriptor itself, stopping at the first candidate boundary) and every candidate: two warps per CTA
+__global__ void __launch_bounds__(64)
 inflate_spec_kernel(const ParPlan P)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
-	WarpTables &T = *reinterpret_cast<WarpTables *>(smem_raw);
-	uint8_t *win = smem_raw + ((sizeof(WarpTables) + 15) & ~(size_t)15);
 	if (blockIdx.x == 0) {
 		InflateJob J = P.job;
 		J.stop_map = P.map;
 		J.map_bit0 = 0;
-		inflate_one<true>(J, *P.head_out, T, win);
+		inflate_duo(J, *P.head_out, smem_raw);
 		return;
 	}
+	WarpTables &T = *reinterpret_cast<WarpTables *>(smem_raw);
+	DuoQueue &Q = *reinterpret_cast<DuoQueue *>(smem_raw + kDuoQueueAt);
+	uint16_t *win = reinterpret_cast<uint16_t *>(smem_raw + kDuoWinAt);
+	if (threadIdx.x < 8)
+		reinterpret_cast<uint32_t *>(&Q)[threadIdx.x] = 0;
+	__syncthreads();
 	const uint32_t u = blockIdx.x - 1;
-	spec_one(P.job.src, P.job.src_len, P.cands[u], P.map, P.job.dst_cap, (P.job.wrap & 0xff) != kWrapJob, T,
-		 reinterpret_cast<uint16_t *>(win), P.rings + (size_t)u * kRingSyms, P.spec[u]);
+	if (threadIdx.x < 32)
+		spec_walker(P.job.src, P.job.src_len, P.cands[u], P.map, (P.job.wrap & 0xff) != kWrapJob, T, Q, P.spec[u]);
+	else
+		spec_copier(P.job.src, P.job.dst_cap, Q, win, P.rings + (size_t)u * kRingSyms, P.spec[u]);
 }
 
 // ---- 3. link: piece k starts where piece k-1 ended (one thread) ----
@@ -452,26 +482,24 @@ inflate_windows_kernel(const ParPlan P)
 }
 
 // ---- 5. the real decode of the chained pieces: inflate_one with the window in shared memory ----
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(64)
 inflate_chain_kernel(const ParPlan P, uint32_t *next_job)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
-	WarpTables &T = *reinterpret_cast<WarpTables *>(smem_raw);
-	uint8_t *win = smem_raw + ((sizeof(WarpTables) + 15) & ~(size_t)15);
-	const uint32_t lane = threadIdx.x & 31;
+	__shared__ uint32_t s_job;
 	const uint32_t n = *P.n_chain;
 	for (;;) {
-		uint32_t j = 0;
-		if (lane == 0)
-			j = atomicAdd(next_job, 1u);
-		j = __shfl_sync(0xffffffffu, j, 0);
+		if (threadIdx.x == 0)
+			s_job = atomicAdd(next_job, 1u);
+		__syncthreads();
+		const uint32_t j = s_job;
+		__syncthreads();
 		if (j >= n)
 			break;
 		// the longest-running piece first: the last one runs to the end of the job
 		const uint32_t k = n - 1 - j;
 		const InflateJob J = P.cjobs[k];
-		inflate_one<true>(J, P.couts[k], T, win);
-		__syncwarp();
+		inflate_duo(J, P.couts[k], smem_raw);
 	}
 }
 
