@@ -839,7 +839,13 @@ static int inflate_parallel_one(nxgpu_ctx *c, const InflateJob &job, InflateOut 
 	const size_t nc = n_cand;
 	const size_t p2 = nc * 65536 + nc * 32768 + align_up(nc * sizeof(SpecOut), 256) + align_up(nc * sizeof(InflateJob), 256) +
 			  align_up(nc * sizeof(InflateOut), 256) + align_up(nc * sizeof(ChainMeta), 256) + 1024;
-	if ((rc = c->d_par2.reserve(p2))) return rc;
+	if (c->d_par2.reserve(p2)) {
+		// no room for the rings of this many pieces: one warp
+		cudaGetLastError();
+		timer_end(c, 1);
+		*serial = true;
+		return 0;
+	}
 	uint8_t *b2 = static_cast<uint8_t *>(c->d_par2.p);
 	ParPlan P;
 	memset(&P, 0, sizeof(P));
