@@ -100,7 +100,7 @@ int deflate_stream_collect(nxgpu_ctx *c, const StreamEnq &e, void *dst, uint64_t
 // one stream decoded by many warps (inflate_par.cuh): inflate_par_select() marks the descriptors of a launch that take the
 // parallel path (kWrapSkip in jobs[], the originals in `picked`), inflate_parallel() runs them on c->stream behind that
 // launch, results in the launch's own result slots
-void inflate_par_select(InflateJob *jobs, size_t n, std::vector<std::pair<size_t, InflateJob>> &picked);
+void inflate_par_select(InflateJob *jobs, size_t n, std::vector<std::pair<size_t, InflateJob>> &picked, bool dry_too = false);
 int inflate_parallel(nxgpu_ctx *c, const std::vector<std::pair<size_t, InflateJob>> &picked, InflateOut *d_outs);
 void timer_begin(nxgpu_ctx *c, int fam);
 void timer_end(nxgpu_ctx *c, int fam);

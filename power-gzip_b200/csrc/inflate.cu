@@ -1318,6 +1318,13 @@ cudaError_t launch_inflate_par(const ParPlan &plan, uint32_t *counter, cudaStrea
 		return e;
 	inflate_spec_kernel<<<plan.n_cand + 1, 64, smem_spec, s>>>(plan);
 	inflate_link_kernel<<<1, 32, 0, s>>>(plan);
+	if (plan.job.wrap & kWrapDry) {
+		inflate_dry_finish_kernel<<<1, 32, 0, s>>>(plan);
+		e = cudaGetLastError();
+		if (e != cudaSuccess)
+			return e;
+		return launch_inflate_solo(plan.retry_job, plan.final_out, 1, counter, s);
+	}
 	if (plan.n_cand) {
 		const uint32_t gw = plan.n_cand < (uint32_t)kNumSMs * 2 ? plan.n_cand : (uint32_t)kNumSMs * 2;
 		inflate_windows_kernel<<<gw, 1024, 0, s>>>(plan);

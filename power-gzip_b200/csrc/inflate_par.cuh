@@ -378,7 +378,13 @@ inflate_spec_kernel(const ParPlan P)
 		InflateJob J = P.job;
 		J.stop_map = P.map;
 		J.map_bit0 = 0;
-		inflate_duo(J, *P.head_out, smem_raw);
+		if (J.wrap & kWrapDry) {
+			// counting only (member discovery): nothing to copy, one warp
+			if (threadIdx.x < 32)
+				inflate_one<false>(J, *P.head_out, *reinterpret_cast<WarpTables *>(smem_raw), nullptr);
+		} else {
+			inflate_duo(J, *P.head_out, smem_raw);
+		}
 		return;
 	}
 	WarpTables &T = *reinterpret_cast<WarpTables *>(smem_raw);
@@ -544,6 +550,50 @@ __global__ void inflate_finish_kernel(const ParPlan P)
 		const bool job = (P.job.wrap & 0xff) == kWrapJob;
 		if (job || (O.rc == 0 && (O.flags & 1)))
 			O.in_used += (uint32_t)(L.bit >> 3);
+	}
+	*P.final_out = O;
+	*P.retry_job = R;
+}
+
+// ---- dry run (kWrapDry: where does the member end, how long is its output): pieces 1.. were only ever counted, so the
+// chain itself is the answer when its last piece ran into the final block ----
+__global__ void inflate_dry_finish_kernel(const ParPlan P)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0)
+		return;
+	const uint32_t n = *P.n_chain;
+	InflateJob R = P.job;
+	R.wrap |= kWrapSkip;
+	InflateOut O = *P.head_out;
+	bool good = true;
+	if (n == 0) {
+		good = !(O.flags & kInflateMapStop);
+	} else {
+		const ChainMeta &L = P.meta[n - 1];
+		const SpecOut &S = P.spec[L.unit];
+		const uint32_t wrap = (O.flags >> 8) & 0xff;
+		const uint64_t p = (S.end_bit + 7) >> 3;
+		const uint64_t tr = wrap == NXGPU_WRAP_GZIP ? 8 : wrap == NXGPU_WRAP_ZLIB ? 4 : 0;
+		good = S.status == kSpecFinal && S.max_back <= (uint64_t)P.job.hist_len + L.out_off &&
+		       (uint64_t)L.out_off + S.out_len <= P.job.dst_cap && p + tr <= P.job.src_len;
+		if (good) {
+			const uint8_t *s = P.job.src + p;
+			O.rc = 0;
+			O.out_len = L.out_off + S.out_len;
+			O.in_used = (uint32_t)(p + tr);
+			O.flags = 1 | (wrap << 8);
+			O.trailer_crc = 0; O.trailer_isize = 0;
+			if (wrap == NXGPU_WRAP_GZIP) {
+				O.trailer_crc = s[0] | (uint32_t)s[1] << 8 | (uint32_t)s[2] << 16 | (uint32_t)s[3] << 24;
+				O.trailer_isize = s[4] | (uint32_t)s[5] << 8 | (uint32_t)s[6] << 16 | (uint32_t)s[7] << 24;
+			} else if (wrap == NXGPU_WRAP_ZLIB) {
+				O.trailer_crc = (uint32_t)s[0] << 24 | (uint32_t)s[1] << 16 | (uint32_t)s[2] << 8 | s[3];
+			}
+		}
+	}
+	if (!good) {
+		O.rc = kInflateRetry;
+		R.wrap &= ~kWrapSkip;
 	}
 	*P.final_out = O;
 	*P.retry_job = R;

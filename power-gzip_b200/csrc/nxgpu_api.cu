@@ -775,7 +775,7 @@ namespace nxgpu {
 // A descriptor takes the parallel path when it is long enough to hold several deflate blocks (zlib closes a block every
 // 16 Ki symbols, 20-60 KiB of compressed text) and the launch does not fill the GPU anyway.  The path costs two block
 // decodes plus ~0.4 ms; one warp needs ~2 ms per block (measured: a 109 KB source 7.7 ms, a 424 KB one 5.2 ms in parallel).
-void inflate_par_select(InflateJob *jobs, size_t n, std::vector<std::pair<size_t, InflateJob>> &picked)
+void inflate_par_select(InflateJob *jobs, size_t n, std::vector<std::pair<size_t, InflateJob>> &picked, bool dry_too)
 {
 	picked.clear();
 	const char *e = getenv("NXGPU_INFLATE_PAR_MIN");          // bytes of source; 0 = never (developer / test switch)
@@ -784,7 +784,7 @@ void inflate_par_select(InflateJob *jobs, size_t n, std::vector<std::pair<size_t
 		return;
 	for (size_t i = 0; i < n; i++) {
 		const InflateJob &j = jobs[i];
-		if (j.src_len < par_min || j.single_block || (j.wrap & (kWrapDry | kWrapSkip | kWrapNoHeader)) || j.stop_map || j.hist_ptr)
+		if (j.src_len < par_min || j.single_block || (j.wrap & (kWrapSkip | kWrapNoHeader)) || ((j.wrap & kWrapDry) && !dry_too) || j.stop_map || j.hist_ptr)
 			continue;
 		picked.emplace_back(i, j);
 		jobs[i].wrap |= kWrapSkip;
@@ -1197,12 +1197,16 @@ int nxgpu_gunzip_concat(nxgpu_ctx *c, const void *src, uint64_t src_len, void *d
 		jh[i].dst = nullptr;
 		jh[i].dst_cap = 0xffffffffu;
 	}
+	// a few candidates in a long buffer (a .gz file with one big member): each is counted by many warps
+	std::vector<std::pair<size_t, InflateJob>> par;
+	inflate_par_select(jh, n_cand, par, true);
 	NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_ijobs.p, jh, (size_t)n_cand * sizeof(InflateJob), cudaMemcpyHostToDevice, c->stream));
 	timer_begin(c, 1);
 	NXGPU_CUDA_OK(launch_inflate(static_cast<const InflateJob *>(c->d_ijobs.p), static_cast<InflateOut *>(c->d_iouts.p), n_cand,
 				     static_cast<uint32_t *>(c->d_misc.p), c->stream));
 	timer_end(c, 1);
 	c->launches++;
+	if (!par.empty() && (rc = inflate_parallel(c, par, static_cast<InflateOut *>(c->d_iouts.p)))) return rc;
 	std::vector<InflateOut> dry(n_cand);
 	NXGPU_CUDA_OK(cudaMemcpyAsync(dry.data(), c->d_iouts.p, (size_t)n_cand * sizeof(InflateOut), cudaMemcpyDeviceToHost, c->stream));
 	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));

@@ -227,3 +227,29 @@ def test_descriptor_errors_by_many_warps(oracle, pg, alice, monkeypatch):
         assert n_err >= 1
     finally:
         lib.nx_function_end(C.byref(dev))
+
+
+@pytest.mark.gpu
+def test_gunzip_of_files_with_a_few_big_members(engine, pg, alice, monkeypatch):
+    """nxgpu_gunzip_concat on what .gz files usually are — one big member, or a few: the dry run that finds where every
+    member ends goes through the many-warp path too (counting only), then the real decode; result == gzip.decompress, with
+    header look-alikes in the data, zero padding behind the last member, and the one-warp dry run as the reference."""
+    rnd = random.Random(4)
+    fake = b"\x1f\x8b\x08\x00" + bytes(14)
+    a = pg.makedata(1, 22, alice)
+    b = (alice[:200000] + fake * 3 + rnd.randbytes(70000)) * 5
+    files = {"one": [a], "two": [a, b], "three-with-stored": [b, rnd.randbytes(300000), a[: 1 << 20]]}
+    for name, parts in files.items():
+        blob = b"".join(gzip_member(d, 6 if i != 1 else (0 if name == "three-with-stored" else 9)) for i, d in enumerate(parts))
+        want = b"".join(parts)
+        for pad in (b"", bytes(300)):
+            monkeypatch.setenv(PAR, "65536")
+            got, members = engine.gunzip(blob + pad, len(want))
+            assert members == len(parts) and got == want, (name, members, len(got), len(want))
+            monkeypatch.setenv(PAR, "0")
+            assert engine.gunzip(blob + pad, len(want)) == (want, len(parts)), name
+
+
+def gzip_member(d, level):
+    import gzip as _gzip
+    return _gzip.compress(d, level, mtime=0)
