@@ -402,7 +402,9 @@ __device__ __forceinline__ uint32_t walk_batch(BitReader &br, WarpTables &T, uin
 			if (qn == 32)
 				break;
 		}
-		// the general code: one symbol (careful: as many as fit)
+		// the general code: one symbol (careful: as many as fit).  (Every lane has read its queue slot: the ballot and the
+		// shuffles above sit between those reads and lane 0's write below.)
+		__syncwarp();
 		uint32_t st = 0;
 		if (lane == 0) {
 			do {
