@@ -46,6 +46,7 @@ class ZStream(C.Structure):
 
 lib.compress2.argtypes = [C.c_void_p, C.POINTER(C.c_ulong), C.c_void_p, C.c_ulong, C.c_int]
 lib.uncompress.argtypes = [C.c_void_p, C.POINTER(C.c_ulong), C.c_void_p, C.c_ulong]
+lib.nx_uncompress.argtypes = [C.c_void_p, C.POINTER(C.c_ulong), C.c_void_p, C.c_ulong]
 lib.compressBound.restype = C.c_ulong
 lib.compressBound.argtypes = [C.c_ulong]
 lib.crc32.restype = C.c_ulong
@@ -76,7 +77,9 @@ def nx_compress2(data, level):
 def nx_uncompress(blob, n_out):
     out = C.create_string_buffer(max(n_out, 1))
     n = C.c_ulong(n_out)
-    rc = lib.uncompress(out, C.byref(n), blob, len(blob))
+    # nx_uncompress is what uncompress() calls in NX mode (lib/nx_uncompr.c:123-139); uncompress() itself goes through the PLT to
+    # uncompress2, which in this interpreter binds to the libz that Python's zlib module has already loaded
+    rc = lib.nx_uncompress(out, C.byref(n), blob, len(blob))
     assert rc == 0, f"uncompress rc={rc}"
     return out.raw[: n.value]
 
