@@ -554,6 +554,17 @@ def extras_single_gpu(args, pg, eng, lib, torch, src, hsrc, n, extra, hbm_peak, 
         return eng.timer_stop()
     ps = timed(inflate_stream_step, max(2, min(args.steps, 3)), 1)
     extra["ratio_level6_independent_chunks"] = n / ri.out_len
+    # the ordinary (primed) member of the same input, no index: block starts found on the device, many warps (csrc/inflate_par.cuh)
+    rp = eng.deflate_stream_device(src.data_ptr(), n, dst.data_ptr(), cap, level=6, wrap=pg.WRAP_GZIP, chunk=CHUNK)
+    if rp.out_len < (1 << 31):
+        def inflate_primed_step():
+            eng.timer_start()
+            r = eng.inflate_batch([pg.InflateItem(dst.data_ptr(), rp.out_len, back.data_ptr(), n, pg.WRAP_GZIP, 0)], mem=pg.MEM_DEVICE)[0]
+            ms = eng.timer_stop()
+            assert r.rc == 0 and r.out_len == n and r.crc32 == rp.crc32 and (r.flags & 3) == 3
+            return ms
+        pp = timed(inflate_primed_step, 3, 1)
+        extra["inflate_primed_member_no_index_GBps"] = n / (sum(pp) / len(pp)) / 1e6
     extra["inflate_stream_one_member_GBps"] = n / (sum(ps) / len(ps)) / 1e6
     assert bool(torch.equal(back[: 1 << 24], src[: 1 << 24]))
     del back, dst

@@ -253,3 +253,33 @@ def test_gunzip_of_files_with_a_few_big_members(engine, pg, alice, monkeypatch):
 def gzip_member(d, level):
     import gzip as _gzip
     return _gzip.compress(d, level, mtime=0)
+
+
+@pytest.mark.gpu
+def test_full_size_member_round_trip_through_the_many_warp_decode(engine, pg, alice, monkeypatch):
+    """BASELINE.json configs[1] at full size: 1 GiB of the benchmark text -> one gzip member with
+    primed 256 KiB chunks (no index kept) -> inflated again as ONE foreign member: 4096+ block-start candidates, speculative
+    pieces, chain.  Device-resident end to end; the checks are the size-independent ones: lengths, the trailer, and the
+    crc32 / adler32 of the 1 GiB output against the values the deflate side computed from the input."""
+    monkeypatch.delenv(PAR, raising=False)
+    lib = pg.load_library()
+    n = 1 << 30
+    dsrc = engine.alloc(n)
+    seed = C.create_string_buffer(alice, len(alice))
+    host = C.c_void_p()
+    lib.nxgpu_host_alloc(n + 64, C.byref(host))
+    try:
+        assert lib.nxgpu_makedata(1, 30, C.addressof(seed), len(alice), host, n + 16) == n
+        engine._check(lib.nxgpu_memcpy_h2d(engine.ctx, dsrc.ptr, host, n), "h2d")
+    finally:
+        lib.nxgpu_host_free(host)
+    cap = engine.deflate_bound(n)
+    ddst = engine.alloc(cap)
+    res = engine.deflate_stream_device(dsrc.ptr, n, ddst.ptr, cap, level=6, wrap=pg.WRAP_GZIP)
+    assert res.crc32 == 0xf50ac623 and res.n_chunks == 4096           # crc32 of makedata -s 1 -b 30 (bench.py verifies the same value with zlib)
+    dsrc.free()
+    dback = engine.alloc(n)
+    r = engine.inflate_batch([pg.InflateItem(ddst.ptr, res.out_len, dback.ptr, n, pg.WRAP_GZIP, 0)], mem=pg.MEM_DEVICE)[0]
+    assert r.rc == 0 and r.out_len == n and r.in_used == res.out_len and (r.flags & 3) == 3
+    assert r.crc32 == res.crc32 and r.adler32 == res.adler32
+    ddst.free(); dback.free()
