@@ -283,3 +283,41 @@ def test_full_size_member_round_trip_through_the_many_warp_decode(engine, pg, al
     assert r.rc == 0 and r.out_len == n and r.in_used == res.out_len and (r.flags & 3) == 3
     assert r.crc32 == res.crc32 and r.adler32 == res.adler32
     ddst.free(); dback.free()
+
+
+@pytest.mark.gpu
+def test_many_shapes_of_streams_through_the_many_warp_decode(engine, pg, alice, monkeypatch):
+    """Streams made with every knob of deflateInit2 that changes the block structure — memLevel 1 (a block every 128 symbols:
+    thousands of pieces far shorter than the window, markers chased through many predecessors), memLevel 9, windowBits 9-15,
+    the RLE / FILTERED / HUFFMAN_ONLY / FIXED strategies, levels 0-9, Z_PARTIAL/SYNC/FULL flushes at random places — over
+    text, binary and mixed inputs of 100 KB - 3 MB: bytes, lengths and checksums against the input, verdict against zlib."""
+    monkeypatch.setenv(PAR, "65536")
+    rnd = random.Random(2024)
+    text = pg.makedata(5, 22, alice)
+    bins = b"".join(rnd.randrange(1 << 30).to_bytes(4, "little") * rnd.randrange(1, 6) for _ in range(150000))
+    pool = [text, alice * 4, bins, bytes(1 << 20) + alice[:100000] + rnd.randbytes(300000) + text[:500000]]
+    strategies = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]
+    n_par = 0
+    for case in range(60):
+        src = pool[case % len(pool)]
+        o = rnd.randrange(0, len(src) // 2)
+        d = src[o: o + rnd.randrange(100000, min(len(src) - o, 3000000))]
+        level = rnd.choice([0, 1, 2, 4, 6, 6, 9])
+        wbits = rnd.choice([9, 11, 13, 15, 15, 15])
+        mem = rnd.choice([1, 1, 4, 8, 9])
+        strat = rnd.choice(strategies)
+        wrap = rnd.choice([wbits, -wbits, wbits + 16])
+        co = zlib.compressobj(level, zlib.DEFLATED, wrap, mem, strat)
+        parts, p = [], 0
+        while p < len(d):
+            step = rnd.randrange(20000, 400000)
+            parts.append(co.compress(d[p:p + step])); p += step
+            if rnd.random() < 0.3:
+                parts.append(co.flush(rnd.choice([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH])))
+        parts.append(co.flush())
+        z = b"".join(parts)
+        got, out = _inflate(engine, pg, z, len(d))
+        assert got[0] == 0 and out == d and got[2] == len(z), (case, level, wbits, mem, strat, wrap, got, len(z), len(d))
+        assert got[4] == zlib.crc32(d) and got[5] == zlib.adler32(d)
+        n_par += len(z) >= 65536
+    assert n_par >= 30
