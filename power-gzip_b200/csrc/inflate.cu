@@ -1,14 +1,18 @@
-// inflate.cu — the NX decompress function (inc_nx/nxu.h:812) as a batched
-// sm_100a kernel: one warp per independent member / sync-point segment.
+// inflate.cu — the NX decompress function (inc_nx/nxu.h:812) as sm_100a kernels.
 //
-// Per warp: the compressed bytes are staged into a small shared-memory ring with coalesced loads;
-// lane 0 walks the Huffman stream through shared-memory lookup tables (10-bit lit/len, 9-bit
-// distance, canonical fall-back for longer codes) and queues up to 32 symbols; then all 32 lanes
-// materialise the queue — a shuffle prefix sum gives every symbol its output offset, literals and
-// every match that does not read this batch's own output are written byte-parallel with all loads
-// in flight at once, the few short-distance matches follow in order.  The window is the output
-// buffer itself (L1/L2-resident), so no history copies are needed (the reference's host side copies
-// 32 KiB per job, lib/nx_inflate.c:1633-1687).
+// inflate_kernel: one warp per independent member / sync-point segment, thousands in flight.  The compressed bytes are
+// staged into a small shared-memory ring with coalesced loads; lane 0 walks the Huffman stream through shared-memory
+// lookup tables (10-bit lit/len, 9-bit distance, canonical fall-back for longer codes) and queues 32 symbols
+// (fast_walk), the 32 lanes judge them and form the tokens (walk_batch); then all lanes materialise the queue — a
+// shuffle prefix sum gives every symbol its output offset, literals and every match that does not read this batch's own
+// output are written byte-parallel (the owner of a byte: one warp-wide OR + a population count), the few short-distance
+// matches follow in order.  The window is the output buffer itself (L1/L2-resident), so no history copies are needed
+// (the reference's host side copies 32 KiB per job, lib/nx_inflate.c:1633-1687).
+//
+// inflate_solo_kernel: a few streams, each on a warp pair — a walker and a copier with a token queue between them, the
+// window in a shared-memory ring (DuoQueue, duo_copier, ring_fill).
+//
+// inflate_par.cuh: ONE stream over many warp pairs (block-start search, speculative decode with window markers, chain).
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>

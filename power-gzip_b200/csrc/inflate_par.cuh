@@ -1,7 +1,7 @@
 // inflate_par.cuh — ONE deflate stream decoded by many warps (included by inflate.cu, inside its namespace).
 //
-// A decompress descriptor (inc_nx/nxu.h:812-815) or a foreign gzip/zlib member is a single bit stream: one warp walks
-// it at ~70 MB/s, below one host core, while 147 SMs idle.  Deflate blocks are independent Huffman-wise, and what they
+// A decompress descriptor (inc_nx/nxu.h:812-815) or a foreign gzip/zlib member is a single bit stream: one warp pair walks
+// it at ~150 MB/s, below one host core, while 147 SMs idle.  Deflate blocks are independent Huffman-wise, and what they
 // need from their predecessors is only the 32 KiB window, so:
 //
 //   1. blockfind     every bit offset of the source is tested for "a dynamic block header starts here" (BTYPE=10, HLIT and
@@ -9,9 +9,9 @@
 //                    and distance codes).  The result is a bit map and a sorted list of candidates.  False positives
 //                    only cost work; a real block start that the test refuses (the lenient codes an NX job may carry)
 //                    only costs parallelism — the map merely has to be a fixed function of the source.
-//   2. speculation   one warp per candidate decodes from its candidate to the first block boundary that is a candidate
-//                    again (stored and fixed blocks are walked through).  The window in front of it is unknown: the
-//                    warp keeps its last 32 Ki symbols as 16-bit values in shared memory, initialised with markers
+//   2. speculation   one warp pair per candidate (a walker and a copier, see DuoQueue) decodes from its candidate to the
+//                    first block boundary that is a candidate again (stored and fixed blocks are walked through).  The
+//                    window in front of it is unknown: the copier keeps the last 32 Ki symbols as 16-bit values in shared memory, initialised with markers
 //                    "window byte s", so a match that reaches in front of the piece copies markers.  Nothing is
 //                    written but the ring, the piece's length and where it ended.  In the same launch piece 0 — from
 //                    the descriptor's own start state (container header, resumed block, history) — is decoded for real.
@@ -21,13 +21,14 @@
 //                    of the job by the serial rule.
 //   4. windows       the 32 KiB in front of every chained piece: a marker is chased through the rings of the
 //                    predecessors until it names a byte (usually zero or one hop), all pieces and slots in parallel.
-//   5. real decode   the serial decoder (inflate_one, window in shared memory) runs every chained piece with its true
-//                    window, writing the target; the last one reports the completion state (SFBT, SUBC, DHT, errors)
+//   5. real decode   the serial decoder (inflate_one + duo_copier, window in shared memory) runs every chained piece with
+//                    its true window, a warp pair per piece, writing the target; the last one reports the completion state (SFBT, SUBC, DHT, errors)
 //                    exactly as the serial engine would, because it is the serial engine.
 //   6. finish        offsets are folded into the last piece's result; pieces that did not end where speculation said
 //                    they would (cannot happen) send the whole descriptor through the serial path.
 //
-// Critical path: two block decodes instead of all of them.
+// Critical path: two block decodes instead of all of them.  A dry run (kWrapDry: where does the member end, how long is
+// its output — nxgpu_gunzip_concat) stops after step 3: the chain is the answer (inflate_dry_finish_kernel).
 
 constexpr uint32_t kSpecLinked = 0, kSpecFinal = 1, kSpecSrcEnd = 2, kSpecError = 3, kSpecTooLong = 4;
 constexpr uint32_t kRingSyms = 32768;
