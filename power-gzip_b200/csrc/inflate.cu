@@ -1333,7 +1333,7 @@ cudaError_t launch_inflate_par(const ParPlan &plan, uint32_t *counter, cudaStrea
 	}
 	if (plan.n_cand) {
 		const uint32_t gw = plan.n_cand < (uint32_t)kNumSMs * 2 ? plan.n_cand : (uint32_t)kNumSMs * 2;
-		inflate_windows_kernel<<<gw, 1024, 0, s>>>(plan);
+		inflate_windows_kernel<<<dim3(gw, 4), 1024, 0, s>>>(plan);
 		const uint32_t gc = plan.n_cand < (uint32_t)kNumSMs * 5 ? plan.n_cand : (uint32_t)kNumSMs * 5;
 		inflate_chain_kernel<<<gc, 64, smem_chain, s>>>(plan, counter);
 	}

@@ -11,8 +11,9 @@
 //                    only costs parallelism — the map merely has to be a fixed function of the source.
 //   2. speculation   one warp pair per candidate (a walker and a copier, see DuoQueue) decodes from its candidate to the
 //                    first block boundary that is a candidate again (stored and fixed blocks are walked through).  The
-//                    window in front of it is unknown: the copier keeps the last 32 Ki symbols as 16-bit values in shared memory, initialised with markers
-//                    "window byte s", so a match that reaches in front of the piece copies markers.  Nothing is
+//                    window in front of it is unknown: the copier keeps the last 32 Ki symbols as 16-bit values in
+//                    shared memory, initialised with markers "window byte s", so a match that reaches in front of the
+//                    piece copies markers.  Nothing is
 //                    written but the ring, the piece's length and where it ended.  In the same launch piece 0 — from
 //                    the descriptor's own start state (container header, resumed block, history) — is decoded for real.
 //   3. link          one thread follows piece 0's end through the candidate list: piece k starts where piece k-1
@@ -144,6 +145,7 @@ blockfind_verify_kernel(const uint8_t *__restrict__ src, uint32_t src_len, const
 		uint32_t lcnt[16], dcnt[16];                 // codes per length
 		for (int l = 0; l < 16; l++) lcnt[l] = dcnt[l] = 0;
 		int nsym = 0, prev = 0;
+		uint32_t kraft_l = 0, kraft_d = 0;           // running Kraft sums, unit 2^-15
 		bool ok = true, eob = false;
 		while (ok && nsym < hlit + hdist) {
 			int code = 0, first = 0, index = 0, sym = -1;
@@ -160,9 +162,10 @@ blockfind_verify_kernel(const uint8_t *__restrict__ src, uint32_t src_len, const
 			else if (sym == 18) { val = 0; rep = 11 + (int)br.get(7); }
 			if (nsym + rep > hlit + hdist) { ok = false; break; }
 			for (int r = 0; r < rep; r++, nsym++) {
-				if (nsym < hlit) { lcnt[val]++; if (nsym == 256 && val) eob = true; }
-				else dcnt[val]++;
+				if (nsym < hlit) { lcnt[val]++; if (nsym == 256 && val) eob = true; if (val) kraft_l += 32768u >> val; }
+				else { dcnt[val]++; if (val) kraft_d += 32768u >> val; }
 			}
+			if (kraft_l > 32768u || kraft_d > 32768u) { ok = false; break; }     // over-subscribed already: most look-alikes end here
 			prev = val;
 		}
 		if (!ok || !eob || br.overrun())
@@ -466,7 +469,8 @@ inflate_windows_kernel(const ParPlan P)
 	for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
 		const int64_t S = P.meta[c].out_off;
 		uint8_t *hist = P.hists + (size_t)c * kWinBytes;
-		for (uint32_t i = threadIdx.x; i < kWinBytes; i += blockDim.x) {
+		// (gridDim.y CTAs share a piece: the chase is a chain of dependent loads, more threads hide it)
+		for (uint32_t i = blockIdx.y * blockDim.x + threadIdx.x; i < kWinBytes; i += blockDim.x * gridDim.y) {
 			int64_t a = S - (int64_t)kWinBytes + i;       // output position, counted from the descriptor's first target byte
 			int cc = (int)c - 1;
 			uint32_t byte = 0;

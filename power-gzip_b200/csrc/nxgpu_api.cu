@@ -802,7 +802,7 @@ static int inflate_parallel_one(nxgpu_ctx *c, const InflateJob &job, InflateOut 
 	const uint32_t cand_cap = surv_cap < 65536 ? surv_cap : 65536;
 	const size_t p1 = map_bytes + (size_t)surv_cap * 8 + (size_t)cand_cap * 8 + 256 + 2 * sizeof(InflateJob);
 	if ((rc = c->d_par1.reserve(p1))) return rc;
-	if ((rc = c->h_par.reserve((size_t)cand_cap * 8 + 256 + sizeof(InflateJob)))) return rc;
+	if ((rc = c->h_par.reserve((size_t)cand_cap * 8 + 512 + sizeof(InflateJob)))) return rc;
 	if ((rc = c->d_misc.reserve(64))) return rc;
 	uint8_t *b1 = static_cast<uint8_t *>(c->d_par1.p);
 	uint32_t *map = reinterpret_cast<uint32_t *>(b1);
@@ -820,6 +820,8 @@ static int inflate_parallel_one(nxgpu_ctx *c, const InflateJob &job, InflateOut 
 	const bool is_job = (job.wrap & 0xff) == kWrapJob;
 	NXGPU_CUDA_OK(launch_blockfind(job.src, n, is_job ? job.start_bit : 0, map, surv, surv_cap, cand, cand_cap, counts, c->stream));
 	NXGPU_CUDA_OK(cudaMemcpyAsync(h_counts, counts, 8, cudaMemcpyDeviceToHost, c->stream));
+	const uint32_t first = cand_cap < 1024 ? cand_cap : 1024;     // the list usually fits one small copy: one synchronisation
+	NXGPU_CUDA_OK(cudaMemcpyAsync(h_cand, cand, (size_t)first * 8, cudaMemcpyDeviceToHost, c->stream));
 	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
 	c->launches += 2;
 	const uint32_t n_cand = h_counts[1];
@@ -832,8 +834,10 @@ static int inflate_parallel_one(nxgpu_ctx *c, const InflateJob &job, InflateOut 
 		*serial = true;
 		return 0;
 	}
-	NXGPU_CUDA_OK(cudaMemcpyAsync(h_cand, cand, (size_t)n_cand * 8, cudaMemcpyDeviceToHost, c->stream));
-	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	if (n_cand > first) {
+		NXGPU_CUDA_OK(cudaMemcpyAsync(h_cand + first, cand + first, (size_t)(n_cand - first) * 8, cudaMemcpyDeviceToHost, c->stream));
+		NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	}
 	std::sort(h_cand, h_cand + n_cand);
 	NXGPU_CUDA_OK(cudaMemcpyAsync(cand, h_cand, (size_t)n_cand * 8, cudaMemcpyHostToDevice, c->stream));
 	const size_t nc = n_cand;
