@@ -1120,7 +1120,8 @@ __device__ void packer_flush(Packer &P, uint32_t nbits)
 		P.out32[P.words_out + i] = P.stage[i];
 	const uint32_t tail = P.stage[full];
 	__syncthreads();
-	for (uint32_t i = threadIdx.x; i < (uint32_t)kStageWords; i += kThreads)
+	// (only the words this round touched: everything behind them is still zero)
+	for (uint32_t i = threadIdx.x; i < full + 3 && i < (uint32_t)kStageWords; i += kThreads)
 		P.stage[i] = (i == 0) ? tail : 0;
 	__syncthreads();
 	P.words_out += full;
@@ -1143,12 +1144,15 @@ __device__ void copy_bits_to_stage(Packer &P, const uint32_t *words, uint32_t nb
 __device__ void encode_tokens(Smem &S, HuffScratch &H, Packer &P, const uint32_t *tok, uint32_t ntok)
 {
 	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+	uint32_t t_next = threadIdx.x < ntok ? __ldcg(&tok[threadIdx.x]) : 0;     // tokens are read one round ahead (L2 latency)
 	for (uint32_t base = 0; base < ntok; base += kThreads) {
 		const uint32_t i = base + threadIdx.x;
 		uint64_t v = 0;
 		uint32_t n = 0;
+		const uint32_t t = t_next;
+		if (i + kThreads < ntok)
+			t_next = __ldcg(&tok[i + kThreads]);
 		if (i < ntok) {
-			const uint32_t t = tok[i];
 			if (!tok_is_match(t)) {
 				v = H.ll_code[t];
 				n = H.ll_len[t];
