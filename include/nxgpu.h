@@ -246,10 +246,11 @@ typedef struct {
 /* NXGPU_MEM_HOST: when the items' targets lie back to back in one host buffer the outputs return in a few large
  * copies, so the bytes of dst[out_len .. dst_cap) of every item are UNSPECIFIED after the call (as are all dst_cap
  * bytes of an item whose rc != 0); only dst[0 .. out_len) is the result.
- * A batch of at most 32 items decodes every item with 64 KiB of source or more on many warps (block starts found by
- * header search, blocks decoded speculatively and then for real: DESIGN.md 4.2); results are those of the one-warp
- * decode.  NXGPU_INFLATE_PAR_MIN=<bytes> moves that threshold (0 = never), a developer / test switch like
- * NXGPU_INFLATE_SOLO_MAX. */
+ * In a batch of at most 32 items the longest streams (64 KiB of source or more) are decoded by many warps each (block
+ * starts found by header search, blocks decoded speculatively and then for real: DESIGN.md 4.2) as long as that shortens
+ * the call: a lone long stream always, sixteen streams of a few hundred KB not.  Results are those of the one-warp-pair
+ * decode.  NXGPU_INFLATE_PAR_MIN=<bytes> sends every stream of that length through it (0 = none), a developer / test
+ * switch like NXGPU_INFLATE_SOLO_MAX. */
 int nxgpu_inflate_batch(nxgpu_ctx *ctx, const nxgpu_inflate_item *items, size_t n,
 			nxgpu_inflate_result *results, int mem);
 

@@ -778,17 +778,46 @@ namespace nxgpu {
 void inflate_par_select(InflateJob *jobs, size_t n, std::vector<std::pair<size_t, InflateJob>> &picked, bool dry_too)
 {
 	picked.clear();
-	const char *e = getenv("NXGPU_INFLATE_PAR_MIN");          // bytes of source; 0 = never (developer / test switch)
+	const char *e = getenv("NXGPU_INFLATE_PAR_MIN");          // bytes of source: every stream this long goes, 0 = never (developer / test switch)
 	const uint64_t par_min = e ? strtoull(e, nullptr, 0) : 64 * 1024;
 	if (par_min == 0 || n > 32)
 		return;
+	std::vector<size_t> elig;
 	for (size_t i = 0; i < n; i++) {
 		const InflateJob &j = jobs[i];
 		if (j.src_len < par_min || j.single_block || (j.wrap & (kWrapSkip | kWrapNoHeader)) || ((j.wrap & kWrapDry) && !dry_too) || j.stop_map || j.hist_ptr)
 			continue;
-		picked.emplace_back(i, j);
-		jobs[i].wrap |= kWrapSkip;
+		elig.push_back(i);
 	}
+	if (elig.empty())
+		return;
+	// The streams of one launch run side by side, a warp pair each, so the launch takes as long as its longest stream
+	// (20-45 MB of source per second); the many-warp decodes run one after the other behind it (~3.5 ms + source / 2 GB/s
+	// each).  Taking the k longest streams out of the launch pays while the launch shrinks by more than they cost:
+	// a lone long stream always goes, sixteen threads with a few hundred KB each stay where they are.
+	std::sort(elig.begin(), elig.end(), [&](size_t a, size_t b) { return jobs[a].src_len > jobs[b].src_len; });
+	uint32_t longest_other = 0;                                // the longest stream that is not eligible at all
+	for (size_t i = 0; i < n; i++)
+		if (std::find(elig.begin(), elig.end(), i) == elig.end() && !(jobs[i].wrap & kWrapSkip) && jobs[i].src_len > longest_other)
+			longest_other = jobs[i].src_len;
+	auto serial_ms = [](uint32_t src) { return src / 30e3; };
+	auto par_ms = [](uint32_t src) { return 3.5 + src / 2e6; };
+	double best = 1e30, cost_par = 0;
+	size_t best_k = 0;
+	if (e)
+		best_k = elig.size();                                  // the switch is set: every eligible stream goes (tests)
+	for (size_t k = 0; k <= elig.size() && !e; k++) {
+		const uint32_t rest = std::max(longest_other, k < elig.size() ? jobs[elig[k]].src_len : 0u);
+		const double t = serial_ms(rest) + cost_par;
+		if (t < best) { best = t; best_k = k; }
+		if (k < elig.size())
+			cost_par += par_ms(jobs[elig[k]].src_len);
+	}
+	for (size_t k = 0; k < best_k; k++) {
+		picked.emplace_back(elig[k], jobs[elig[k]]);
+		jobs[elig[k]].wrap |= kWrapSkip;
+	}
+	std::sort(picked.begin(), picked.end(), [](const std::pair<size_t, InflateJob> &x, const std::pair<size_t, InflateJob> &y) { return x.first < y.first; });
 }
 
 // *serial = true: the stream has nothing to split at, nothing was launched, the caller runs it on one warp
