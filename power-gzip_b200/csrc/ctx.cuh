@@ -57,6 +57,15 @@ struct PinBuf {
 	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// one many-warp inflate in flight (inflate_par.cuh): its own stream and scratch, so that several of them overlap
+struct ParSlot {
+	cudaStream_t st = nullptr;
+	cudaEvent_t ev = nullptr;
+	DevBuf d1, d2;
+	PinBuf h;
+};
+constexpr int kParSlots = 8;
+
 struct KernelTimer {
 	std::vector<cudaEvent_t> ev;      // start/stop pairs
 	size_t used = 0;
@@ -83,6 +92,7 @@ struct nxgpu_ctx {
 	uint64_t launches = 0;
 	DevBuf d_jobs, d_outs, d_tok, d_slots, d_ranges, d_parts, d_rs, d_seeds, d_cks, d_in, d_out, d_offsets, d_misc, d_dst_ptrs, d_dht, d_lz, d_ctr, d_flags, d_ijobs, d_iouts, d_cat, d_catdesc, d_chain, d_par1, d_par2;
 	PinBuf h_jobs, h_outs, h_misc, h_stage, h_ones, h_cat, h_par;
+	ParSlot par[kParSlots];
 	KernelTimer timers[3];           // 0 deflate, 1 inflate, 2 checksum
 	bool timing = true;
 };
@@ -101,7 +111,7 @@ int deflate_stream_collect(nxgpu_ctx *c, const StreamEnq &e, void *dst, uint64_t
 // parallel path (kWrapSkip in jobs[], the originals in `picked`), inflate_parallel() runs them on c->stream behind that
 // launch, results in the launch's own result slots
 void inflate_par_select(InflateJob *jobs, size_t n, std::vector<std::pair<size_t, InflateJob>> &picked, bool dry_too = false);
-int inflate_parallel(nxgpu_ctx *c, const std::vector<std::pair<size_t, InflateJob>> &picked, InflateOut *d_outs);
+int inflate_parallel(nxgpu_ctx *c, const std::vector<std::pair<size_t, InflateJob>> &picked, InflateOut *d_outs, bool inputs_marked = false);
 void timer_begin(nxgpu_ctx *c, int fam);
 void timer_end(nxgpu_ctx *c, int fam);
 // nxgpu_job.cu: NX job descriptors, one at a time or coalesced

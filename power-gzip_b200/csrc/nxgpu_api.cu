@@ -159,6 +159,11 @@ void nxgpu_close(nxgpu_ctx *c)
 	for (DevBuf *b : db) b->release();
 	PinBuf *pb[] = { &c->h_jobs, &c->h_outs, &c->h_misc, &c->h_stage, &c->h_ones, &c->h_cat, &c->h_par };
 	for (PinBuf *b : pb) b->release();
+	for (ParSlot &ps : c->par) {
+		ps.d1.release(); ps.d2.release(); ps.h.release();
+		if (ps.ev) cudaEventDestroy(ps.ev);
+		if (ps.st) cudaStreamDestroy(ps.st);
+	}
 	for (int f = 0; f < 3; f++)
 		for (cudaEvent_t e : c->timers[f].ev) cudaEventDestroy(e);
 	cudaEventDestroy(c->t0); cudaEventDestroy(c->t1);
@@ -792,26 +797,27 @@ void inflate_par_select(InflateJob *jobs, size_t n, std::vector<std::pair<size_t
 	if (elig.empty())
 		return;
 	// The streams of one launch run side by side, a warp pair each, so the launch takes as long as its longest stream
-	// (20-45 MB of source per second); the many-warp decodes run one after the other behind it (~3.5 ms + source / 2 GB/s
-	// each).  Taking the k longest streams out of the launch pays while the launch shrinks by more than they cost:
-	// a lone long stream always goes, sixteen threads with a few hundred KB each stay where they are.
+	// (20-45 MB of source per second).  The many-warp decodes run beside the launch on streams of their own, up to
+	// kParSlots at a time; each costs the host ~0.5 ms (block search, one synchronisation, sort) and ~3 ms + source / 2 GB/s
+	// on the device.  The k longest streams are taken out of the launch while max(launch, decodes) shrinks: a lone long
+	// stream always goes, sixteen threads with a few hundred KB each stay where they are.
 	std::sort(elig.begin(), elig.end(), [&](size_t a, size_t b) { return jobs[a].src_len > jobs[b].src_len; });
 	uint32_t longest_other = 0;                                // the longest stream that is not eligible at all
 	for (size_t i = 0; i < n; i++)
 		if (std::find(elig.begin(), elig.end(), i) == elig.end() && !(jobs[i].wrap & kWrapSkip) && jobs[i].src_len > longest_other)
 			longest_other = jobs[i].src_len;
 	auto serial_ms = [](uint32_t src) { return src / 30e3; };
-	auto par_ms = [](uint32_t src) { return 3.5 + src / 2e6; };
-	double best = 1e30, cost_par = 0;
+	double best = 1e30, dev_ms = 0;
 	size_t best_k = 0;
 	if (e)
 		best_k = elig.size();                                  // the switch is set: every eligible stream goes (tests)
 	for (size_t k = 0; k <= elig.size() && !e; k++) {
 		const uint32_t rest = std::max(longest_other, k < elig.size() ? jobs[elig[k]].src_len : 0u);
-		const double t = serial_ms(rest) + cost_par;
+		const double par = k ? 3.0 + 0.5 * k + dev_ms / (k < (size_t)kParSlots ? k : kParSlots) : 0.0;
+		const double t = std::max(serial_ms(rest), par);
 		if (t < best) { best = t; best_k = k; }
 		if (k < elig.size())
-			cost_par += par_ms(jobs[elig[k]].src_len);
+			dev_ms += jobs[elig[k]].src_len / 2e6;
 	}
 	for (size_t k = 0; k < best_k; k++) {
 		picked.emplace_back(elig[k], jobs[elig[k]]);
@@ -821,7 +827,7 @@ void inflate_par_select(InflateJob *jobs, size_t n, std::vector<std::pair<size_t
 }
 
 // *serial = true: the stream has nothing to split at, nothing was launched, the caller runs it on one warp
-static int inflate_parallel_one(nxgpu_ctx *c, const InflateJob &job, InflateOut *d_final, bool *serial)
+static int inflate_parallel_one(nxgpu_ctx *c, ParSlot &S, const InflateJob &job, InflateOut *d_final, bool *serial)
 {
 	*serial = false;
 	int rc;
@@ -830,28 +836,26 @@ static int inflate_parallel_one(nxgpu_ctx *c, const InflateJob &job, InflateOut 
 	const uint32_t surv_cap = n / 32 + 1024;                  // the filter passes one bit offset in ~1200
 	const uint32_t cand_cap = surv_cap < 65536 ? surv_cap : 65536;
 	const size_t p1 = map_bytes + (size_t)surv_cap * 8 + (size_t)cand_cap * 8 + 256 + 2 * sizeof(InflateJob);
-	if ((rc = c->d_par1.reserve(p1))) return rc;
-	if ((rc = c->h_par.reserve((size_t)cand_cap * 8 + 512 + sizeof(InflateJob)))) return rc;
-	if ((rc = c->d_misc.reserve(64))) return rc;
-	uint8_t *b1 = static_cast<uint8_t *>(c->d_par1.p);
+	if ((rc = S.d1.reserve(p1))) return rc;
+	if ((rc = S.h.reserve((size_t)cand_cap * 8 + 512 + sizeof(InflateJob)))) return rc;
+	uint8_t *b1 = static_cast<uint8_t *>(S.d1.p);
 	uint32_t *map = reinterpret_cast<uint32_t *>(b1);
 	uint64_t *surv = reinterpret_cast<uint64_t *>(b1 + map_bytes);
 	uint64_t *cand = surv + surv_cap;
 	uint32_t *counts = reinterpret_cast<uint32_t *>(cand + cand_cap);
 	InflateJob *d_job = reinterpret_cast<InflateJob *>(reinterpret_cast<uint8_t *>(counts) + 128);
-	uint8_t *hp = static_cast<uint8_t *>(c->h_par.p);
+	uint8_t *hp = static_cast<uint8_t *>(S.h.p);
 	uint32_t *h_counts = reinterpret_cast<uint32_t *>(hp);
 	InflateJob *h_job = reinterpret_cast<InflateJob *>(hp + 128);
 	uint64_t *h_cand = reinterpret_cast<uint64_t *>(hp + 256 + sizeof(InflateJob) - sizeof(InflateJob) % 8 + 8);
 	*h_job = job;
-	timer_begin(c, 1);
-	NXGPU_CUDA_OK(cudaMemcpyAsync(d_job, h_job, sizeof(InflateJob), cudaMemcpyHostToDevice, c->stream));
+	NXGPU_CUDA_OK(cudaMemcpyAsync(d_job, h_job, sizeof(InflateJob), cudaMemcpyHostToDevice, S.st));
 	const bool is_job = (job.wrap & 0xff) == kWrapJob;
-	NXGPU_CUDA_OK(launch_blockfind(job.src, n, is_job ? job.start_bit : 0, map, surv, surv_cap, cand, cand_cap, counts, c->stream));
-	NXGPU_CUDA_OK(cudaMemcpyAsync(h_counts, counts, 8, cudaMemcpyDeviceToHost, c->stream));
+	NXGPU_CUDA_OK(launch_blockfind(job.src, n, is_job ? job.start_bit : 0, map, surv, surv_cap, cand, cand_cap, counts, S.st));
+	NXGPU_CUDA_OK(cudaMemcpyAsync(h_counts, counts, 8, cudaMemcpyDeviceToHost, S.st));
 	const uint32_t first = cand_cap < 1024 ? cand_cap : 1024;     // the list usually fits one small copy: one synchronisation
-	NXGPU_CUDA_OK(cudaMemcpyAsync(h_cand, cand, (size_t)first * 8, cudaMemcpyDeviceToHost, c->stream));
-	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+	NXGPU_CUDA_OK(cudaMemcpyAsync(h_cand, cand, (size_t)first * 8, cudaMemcpyDeviceToHost, S.st));
+	NXGPU_CUDA_OK(cudaStreamSynchronize(S.st));
 	c->launches += 2;
 	const uint32_t n_cand = h_counts[1];
 	static const bool trace = getenv("NXGPU_TRACE") != nullptr;
@@ -859,27 +863,25 @@ static int inflate_parallel_one(nxgpu_ctx *c, const InflateJob &job, InflateOut 
 		fprintf(stderr, "nxgpu inflate: %u source bytes, %u of %u bit offsets pass the header filter, %u block-start candidates\n", n, h_counts[0], n * 8, n_cand);
 	if (h_counts[0] > surv_cap || n_cand > cand_cap || n_cand == 0) {
 		// nothing to split at (one huge block, stored data) or more look-alikes than the lists hold: one warp
-		timer_end(c, 1);
 		*serial = true;
 		return 0;
 	}
 	if (n_cand > first) {
-		NXGPU_CUDA_OK(cudaMemcpyAsync(h_cand + first, cand + first, (size_t)(n_cand - first) * 8, cudaMemcpyDeviceToHost, c->stream));
-		NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));
+		NXGPU_CUDA_OK(cudaMemcpyAsync(h_cand + first, cand + first, (size_t)(n_cand - first) * 8, cudaMemcpyDeviceToHost, S.st));
+		NXGPU_CUDA_OK(cudaStreamSynchronize(S.st));
 	}
 	std::sort(h_cand, h_cand + n_cand);
-	NXGPU_CUDA_OK(cudaMemcpyAsync(cand, h_cand, (size_t)n_cand * 8, cudaMemcpyHostToDevice, c->stream));
+	NXGPU_CUDA_OK(cudaMemcpyAsync(cand, h_cand, (size_t)n_cand * 8, cudaMemcpyHostToDevice, S.st));
 	const size_t nc = n_cand;
 	const size_t p2 = nc * 65536 + nc * 32768 + align_up(nc * sizeof(SpecOut), 256) + align_up(nc * sizeof(InflateJob), 256) +
 			  align_up(nc * sizeof(InflateOut), 256) + align_up(nc * sizeof(ChainMeta), 256) + 1024;
-	if (c->d_par2.reserve(p2)) {
+	if (S.d2.reserve(p2)) {
 		// no room for the rings of this many pieces: one warp
 		cudaGetLastError();
-		timer_end(c, 1);
 		*serial = true;
 		return 0;
 	}
-	uint8_t *b2 = static_cast<uint8_t *>(c->d_par2.p);
+	uint8_t *b2 = static_cast<uint8_t *>(S.d2.p);
 	ParPlan P;
 	memset(&P, 0, sizeof(P));
 	P.job = job;
@@ -896,30 +898,52 @@ static int inflate_parallel_one(nxgpu_ctx *c, const InflateJob &job, InflateOut 
 	P.head_out = reinterpret_cast<InflateOut *>(b2 + 64);
 	P.final_out = d_final;
 	P.retry_job = d_job + 1;
-	NXGPU_CUDA_OK(launch_inflate_par(P, static_cast<uint32_t *>(c->d_misc.p), c->stream));
-	timer_end(c, 1);
+	NXGPU_CUDA_OK(launch_inflate_par(P, counts + 16, S.st));
 	c->launches += 6;
 	return 0;
 }
 
 // the descriptors inflate_par_select() picked, on c->stream behind the launch they were taken out of (d_outs: that launch's
 // results).  Streams that turn out to have nothing to split at run together in one more launch, a warp each.
-int inflate_parallel(nxgpu_ctx *c, const std::vector<std::pair<size_t, InflateJob>> &picked, InflateOut *d_outs)
+int inflate_parallel(nxgpu_ctx *c, const std::vector<std::pair<size_t, InflateJob>> &picked, InflateOut *d_outs, bool inputs_marked)
 {
 	std::vector<InflateJob> serial;
 	std::vector<size_t> serial_at;
-	for (const auto &pj : picked) {
-		bool s = false;
-		const int rc = inflate_parallel_one(c, pj.second, d_outs + pj.first, &s);
-		if (rc)
-			return rc;
-		if (s) { serial.push_back(pj.second); serial_at.push_back(pj.first); }
+	// every decode has its own stream and scratch (up to kParSlots in flight): they start behind the uploads of the inputs
+	// (c->ev_main, recorded by the caller in front of its own launch when inputs_marked: the launch and these decodes then run
+	// side by side), and the context's stream goes on behind all of them
+	timer_begin(c, 1);
+	if (!inputs_marked)
+		NXGPU_CUDA_OK(cudaEventRecord(c->ev_main, c->stream));
+	const size_t used = picked.size() < (size_t)kParSlots ? picked.size() : (size_t)kParSlots;
+	for (size_t k = 0; k < used; k++) {
+		ParSlot &S = c->par[k];
+		if (!S.st) {
+			NXGPU_CUDA_OK(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+			NXGPU_CUDA_OK(cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming));
+		}
+		NXGPU_CUDA_OK(cudaStreamWaitEvent(S.st, c->ev_main, 0));
 	}
+	int rc = 0;
+	for (size_t i = 0; i < picked.size() && !rc; i++) {
+		ParSlot &S = c->par[i % kParSlots];
+		if (i >= (size_t)kParSlots)
+			NXGPU_CUDA_OK(cudaStreamSynchronize(S.st));          // its scratch is about to be reused
+		bool s = false;
+		rc = inflate_parallel_one(c, S, picked[i].second, d_outs + picked[i].first, &s);
+		if (s) { serial.push_back(picked[i].second); serial_at.push_back(picked[i].first); }
+	}
+	for (size_t k = 0; k < used; k++) {
+		NXGPU_CUDA_OK(cudaEventRecord(c->par[k].ev, c->par[k].st));
+		NXGPU_CUDA_OK(cudaStreamWaitEvent(c->stream, c->par[k].ev, 0));
+	}
+	timer_end(c, 1);
+	if (rc)
+		return rc;
 	if (serial.empty())
 		return 0;
 	// a job array as long as the original launch's, everything skipped but these (results land in their own slots)
 	const size_t n = serial_at.back() + 1;
-	int rc;
 	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));          // h_par / d_par1 are about to be reused
 	if ((rc = c->h_par.reserve(n * sizeof(InflateJob)))) return rc;
 	if ((rc = c->d_par1.reserve(n * sizeof(InflateJob)))) return rc;
@@ -1032,10 +1056,12 @@ int nxgpu_inflate_batch(nxgpu_ctx *c, const nxgpu_inflate_item *items, size_t n,
 	uint32_t *d_crc = static_cast<uint32_t *>(c->d_cks.p), *d_adler = d_crc + n;
 	for (size_t g = 0; g < n_groups; g++) {
 		const size_t g0 = g * n / n_groups, g1 = (g + 1) * n / n_groups, ng = g1 - g0;
+		if (!par.empty())
+			NXGPU_CUDA_OK(cudaEventRecord(c->ev_main, c->stream));            // the inputs are up: the many-warp decodes may start
 		timer_begin(c, 1);
 		NXGPU_CUDA_OK(launch_inflate(dj + g0, dout + g0, (uint32_t)ng, static_cast<uint32_t *>(c->d_misc.p), c->stream));
 		timer_end(c, 1);
-		if (!par.empty() && (rc = inflate_parallel(c, par, dout))) return rc;      // (n <= 32: one group)
+		if (!par.empty() && (rc = inflate_parallel(c, par, dout, true))) return rc;      // (n <= 32: one group)
 		// crc32 / adler32 of every output, lengths taken from the device results
 		uint32_t *d_rs = d_rs_all + g0 + g;
 		NXGPU_CUDA_OK(launch_ranges_from_inflate(dj + g0, dout + g0, (uint32_t)ng, d_rng + g0 * K * rb, d_rs, c->stream, K));
@@ -1234,12 +1260,14 @@ int nxgpu_gunzip_concat(nxgpu_ctx *c, const void *src, uint64_t src_len, void *d
 	std::vector<std::pair<size_t, InflateJob>> par;
 	inflate_par_select(jh, n_cand, par, true);
 	NXGPU_CUDA_OK(cudaMemcpyAsync(c->d_ijobs.p, jh, (size_t)n_cand * sizeof(InflateJob), cudaMemcpyHostToDevice, c->stream));
+	if (!par.empty())
+		NXGPU_CUDA_OK(cudaEventRecord(c->ev_main, c->stream));
 	timer_begin(c, 1);
 	NXGPU_CUDA_OK(launch_inflate(static_cast<const InflateJob *>(c->d_ijobs.p), static_cast<InflateOut *>(c->d_iouts.p), n_cand,
 				     static_cast<uint32_t *>(c->d_misc.p), c->stream));
 	timer_end(c, 1);
 	c->launches++;
-	if (!par.empty() && (rc = inflate_parallel(c, par, static_cast<InflateOut *>(c->d_iouts.p)))) return rc;
+	if (!par.empty() && (rc = inflate_parallel(c, par, static_cast<InflateOut *>(c->d_iouts.p), true))) return rc;
 	std::vector<InflateOut> dry(n_cand);
 	NXGPU_CUDA_OK(cudaMemcpyAsync(dry.data(), c->d_iouts.p, (size_t)n_cand * sizeof(InflateOut), cudaMemcpyDeviceToHost, c->stream));
 	NXGPU_CUDA_OK(cudaStreamSynchronize(c->stream));

@@ -378,13 +378,14 @@ void run_jobs_batch(nxgpu_ctx *c, uint8_t *const *crbs, int *rcs, size_t n)
 		std::vector<std::pair<size_t, InflateJob>> par;
 		inflate_par_select(ij, ni, par);
 		if (cudaMemcpyAsync(c->d_ijobs.p, ij, ni * sizeof(InflateJob), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { fail_all(); return; }
+		if (!par.empty() && cudaEventRecord(c->ev_main, c->stream) != cudaSuccess) { fail_all(); return; }   // sources and histories are up
 		timer_begin(c, 1);
 		if (launch_inflate(static_cast<const InflateJob *>(c->d_ijobs.p), static_cast<InflateOut *>(c->d_iouts.p), (uint32_t)ni,
 				   static_cast<uint32_t *>(c->d_misc.p), c->stream) != cudaSuccess) { fail_all(); return; }
 		timer_end(c, 1);
 		c->launches++;
 		// (ij[] may still be on its way up: the skip marks stay)
-		if (!par.empty() && inflate_parallel(c, par, static_cast<InflateOut *>(c->d_iouts.p))) { fail_all(); return; }
+		if (!par.empty() && inflate_parallel(c, par, static_cast<InflateOut *>(c->d_iouts.p), true)) { fail_all(); return; }
 	}
 	// ---- results of the codec kernels (sizes, states) ----
 	const size_t res_bytes = align16(nd * sizeof(DeflateOut)) + align16(ni * sizeof(InflateOut)) + align16(nd * 316 * 4) + n * 288 + n * 8 + 64;
