@@ -321,3 +321,35 @@ def test_many_shapes_of_streams_through_the_many_warp_decode(engine, pg, alice, 
         assert got[4] == zlib.crc32(d) and got[5] == zlib.adler32(d)
         n_par += len(z) >= 65536
     assert n_par >= 30
+
+
+@pytest.mark.gpu
+def test_a_batch_of_long_streams_decodes_side_by_side(engine, pg, alice, monkeypatch):
+    """twelve long members in ONE batch: more many-warp decodes than there are slots (each has its own stream and scratch),
+    running beside each other and beside the launch that takes the short members"""
+    monkeypatch.setenv(PAR, "65536")
+    rnd = random.Random(12)
+    text = pg.makedata(4, 22, alice)
+    members = []
+    for i in range(12):
+        o = rnd.randrange(0, len(text) // 2)
+        d = text[o: o + rnd.randrange(300000, 1500000)]
+        members.append((zlib.compress(d, rnd.choice([1, 6, 9]), wbits=rnd.choice([15, 31, -15])), d))
+    for i in range(6):                                                     # short ones: the ordinary launch
+        d = alice[i * 1000: i * 1000 + 20000]
+        members.append((zlib.compress(d, 6), d))
+    rnd.shuffle(members)
+    blob = b"".join(m for m, _ in members)
+    src = C.create_string_buffer(blob, len(blob))
+    outb = (C.c_char * (sum(len(d) for _, d in members) + 64))()
+    items, so, do = [], 0, 0
+    for m, d in members:
+        items.append(pg.InflateItem(C.addressof(src) + so, len(m), C.addressof(outb) + do, len(d), pg.WRAP_AUTO, 0))
+        so += len(m); do += len(d)
+    for rounds in range(2):
+        res = engine.inflate_batch(items, mem=pg.MEM_HOST)
+        do = 0
+        for (m, d), r in zip(members, res):
+            assert r.rc == 0 and r.out_len == len(d) and r.in_used == len(m) and r.crc32 == zlib.crc32(d), (len(m), len(d), r.rc, r.out_len)
+            assert bytes(memoryview(outb)[do: do + len(d)]) == d
+            do += len(d)
